@@ -1,0 +1,88 @@
+"""Pluggable providers for the two third-party stages the reference takes from
+packages that are not in this image (SURVEY.md §8c "parity unpinned"):
+
+  * over-segmentation (skimage quickshift/felzenszwalb/slic,
+    reference maskers/pixel_classification.py:70-75)  -> label providers here;
+  * the rigid tracker (cv.legacy CSRT, reference main.py:258-261,287)
+    -> bbox providers here.
+
+Both sides of every parity test consume the SAME provider output.
+"""
+import numpy as np
+
+
+def grid_segments(crop, block=16):
+    """Deterministic block-grid label map, labels 0..S-1 in raster order of blocks."""
+    h, w = crop.shape[:2]
+    nbx = (w + block - 1) // block
+    r = np.arange(h, dtype=np.int32)[:, None] // block
+    c = np.arange(w, dtype=np.int32)[None, :] // block
+    return (r * nbx + c).astype(np.int32)
+
+
+def voronoi_segments(crop, n_sites=200, seed=0):
+    """Seeded random-Voronoi label map (irregular superpixel shapes), labels 0..S-1."""
+    h, w = crop.shape[:2]
+    rng = np.random.default_rng(seed + 7919 * h + w)
+    n = max(1, min(n_sites, h * w))
+    sy = rng.integers(0, h, n)
+    sx = rng.integers(0, w, n)
+    yy, xx = np.mgrid[0:h, 0:w]
+    best = np.full((h, w), np.iinfo(np.int64).max, np.int64)
+    lab = np.zeros((h, w), np.int32)
+    for i in range(n):
+        d = (yy - sy[i]) ** 2 + (xx - sx[i]) ** 2
+        m = d < best
+        best[m] = d[m]
+        lab[m] = i
+    _, inv = np.unique(lab, return_inverse=True)
+    return inv.reshape(h, w).astype(np.int32)
+
+
+def make_segment_provider(name, **kw):
+    """Resolve `params.over_segmentation` (config.yaml:29) to a label provider.
+
+    'grid[:block]' and 'voronoi[:sites]' are the deterministic stand-ins; the
+    reference's names ('quickshift', 'felzenszwalb', 'SLIC') map to the grid
+    provider with a block size giving a comparable superpixel count until a
+    native over-segmenter lands.
+    """
+    name = str(name)
+    if name.startswith("grid"):
+        block = int(name.split(":")[1]) if ":" in name else kw.get("block", 16)
+        return lambda crop: grid_segments(crop, block)
+    if name.startswith("voronoi"):
+        sites = int(name.split(":")[1]) if ":" in name else kw.get("n_sites", 200)
+        return lambda crop: voronoi_segments(crop, sites, kw.get("seed", 0))
+    if name in ("quickshift", "felzenszwalb", "SLIC"):
+        block = {"quickshift": 6, "felzenszwalb": 10, "SLIC": 12}[name]
+        return lambda crop: grid_segments(crop, block)
+    raise ValueError("unknown over_segmentation %r" % name)
+
+
+def truth_boxes(truth_frames, fallback):
+    """Per-frame (x, y, w, h) = bounding rectangle of the ground-truth mask
+    (gray > 127); frames with an empty truth reuse the previous box."""
+    boxes = []
+    prev = tuple(int(v) for v in fallback)
+    for t in truth_frames:
+        g = t if t.ndim == 2 else t[..., 0]
+        ys, xs = np.nonzero(g > 127)
+        if len(xs):
+            prev = (int(xs.min()), int(ys.min()), int(xs.max() - xs.min() + 1), int(ys.max() - ys.min() + 1))
+        boxes.append(prev)
+    return boxes
+
+
+class ScriptedBoxTracker:
+    """Stand-in for cv.legacy.MultiTracker (main.py:258-261,287): replays a list
+    of per-frame boxes for each target."""
+
+    def __init__(self, boxes_per_target):
+        self.boxes = boxes_per_target
+        self.i = 0
+
+    def update(self, frame):
+        i = min(self.i, len(self.boxes[0]) - 1)
+        self.i += 1
+        return True, [b[i] for b in self.boxes]

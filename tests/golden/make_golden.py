@@ -1,0 +1,236 @@
+"""Generate the golden vectors in tests/golden/*.npz by running the UNMODIFIED
+reference (/root/reference) in the build container.
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+
+Runs only where /root/reference exists (never on the GPU box).  The reference
+is imported through tests/golden/ref_shim.py; its over-segmentation call is
+served by the deterministic label providers of the product package and the
+rigid tracker is replaced by truth-derived boxes, so that the reference, the
+oracle and the CUDA path all consume identical inputs.
+
+Files written
+  seq_<name>.npz   whole `update()` sequences: fitted models (raw sklearn tree
+                   arrays, PCA), per-frame bbox / return value / mask digest /
+                   IoU counts, and full stage dumps for a few frames
+  stages.npz       direct calls of the reference's getFeatures /
+                   compileSaliencyMap / computeBenchmark on small inputs
+"""
+import hashlib
+import json
+import os
+import sys
+
+import cv2 as cv
+import numpy as np
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+PKG = os.path.join(ROOT, "non-rigid-object-tracking_b200")
+sys.path.insert(0, HERE)
+sys.path.insert(0, PKG)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import ref_shim                                   # noqa: E402
+from pcm.providers import make_segment_provider, truth_boxes   # noqa: E402
+import pcm_oracle as orc                          # noqa: E402
+
+
+def read_video(path):
+    cap = cv.VideoCapture(path)
+    frames = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        frames.append(f)
+    return frames
+
+
+def sha1(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+SEQUENCES = {
+    # name: (video, params, multi_selection, segment provider, n_frames, dump frames)
+    "soldier_default": dict(
+        video="soldier", multi_selection=True, segments="grid:8", n_frames=32, dump=[0, 9, 17],
+        params=dict(n_estimators=20, max_depth=5, n_components=1, novelty_detection=False,
+                    over_segmentation="quickshift", features="8 hsv_lab", dilation_kernel=7, prior_weight=0.0)),
+    "parachute_novelty": dict(
+        video="parachute", multi_selection=True, segments="voronoi:120", n_frames=24, dump=[0, 5, 16, 20],
+        params=dict(n_estimators=30, max_depth=10, n_components=1, novelty_detection=True,
+                    over_segmentation="felzenszwalb", features="6 lab", dilation_kernel=7, prior_weight=0.0)),
+    "worm_rgb3": dict(
+        video="worm", multi_selection=False, segments="grid:5", n_frames=6, dump=[0, 3],
+        params=dict(n_estimators=8, max_depth=7, n_components=1, novelty_detection=False,
+                    over_segmentation="SLIC", features="3 rgb", dilation_kernel=4, prior_weight=0.0)),
+}
+
+
+def run_sequence(name, spec, ref_maskers, ref_benchmark, polygons):
+    v = spec["video"]
+    frames = read_video(os.path.join(PKG, "Input/SegTrack2/Video/%s.mp4" % v))
+    truth = read_video(os.path.join(PKG, "Input/SegTrack2/Truth/%s.mp4" % v))
+    poly = polygons[v]
+    pts, pts_frames, ronis = poly["pts"][0], poly["pts_frame_numbers"], poly["bboxes_roni"][0]
+    config = dict(multi_selection=spec["multi_selection"], params=dict(spec["params"]))
+    seg_fn = make_segment_provider(spec["segments"])
+    ref_shim.set_segment_provider(seg_fn)
+
+    cls = ref_maskers.pixel_classification.PixelClassificationNonRigidMasker
+    captured = {}
+    orig = cls.__dict__["compileSaliencyMap"].__func__
+
+    def spy(**kw):
+        orig(**kw)
+        b = kw["bbox"]
+        captured.update(p1=kw["probs"][:, 1].copy(), sa=np.asarray(kw["outlier_scores"], np.float64).copy(),
+                        segments=np.asarray(kw["segments"], np.int32).copy(),
+                        priors=np.asarray(kw["priors"]).copy(), thr=float(kw["outlier_threshold"]),
+                        pre=kw["mask"][b[1]:b[1] + b[3], b[0]:b[0] + b[2], 2].copy())
+    cls.compileSaliencyMap = staticmethod(spy)
+    try:
+        m = ref_maskers.getMaskerByName("PC", debug=False, frame=frames[0], config=config,
+                                        poly_roi=pts[0], update_mask=False)
+        out = {}
+        n_models = len(pts) if spec["multi_selection"] else 1
+        for s in range(n_models):
+            bbox = cv.boundingRect(np.array(pts[s]))
+            m.addModel(frame=frames[pts_frames[s]], poly_roi=pts[s], bbox=bbox,
+                       bbox_roni=ronis[s], n_frame=pts_frames[s])
+            arrs = orc.sklearn_tree_arrays(m.models[s]["model"])
+            offs = np.cumsum([0] + [len(a[0]) for a in arrs]).astype(np.int64)
+            out["m%d_offsets" % s] = offs
+            out["m%d_feature" % s] = np.concatenate([a[0] for a in arrs]).astype(np.int32)
+            out["m%d_threshold" % s] = np.concatenate([a[1] for a in arrs]).astype(np.float64)
+            out["m%d_left" % s] = np.concatenate([a[2] for a in arrs]).astype(np.int32)
+            out["m%d_right" % s] = np.concatenate([a[3] for a in arrs]).astype(np.int32)
+            out["m%d_value1" % s] = np.concatenate([a[4] for a in arrs]).astype(np.float64)
+            pca = m.novelty_det[s]["model"]
+            if pca is not None:
+                out["m%d_pca_mean" % s] = pca.mean_.astype(np.float64)
+                out["m%d_pca_comp" % s] = pca.components_.astype(np.float64)
+            out["m%d_threshold_novelty" % s] = np.float64(m.novelty_det[s]["threshold"])
+        boxes = truth_boxes(truth[:spec["n_frames"]], cv.boundingRect(np.array(pts[0])))
+        per = dict(bbox=[], ret=[], mask_sha1=[], fg=[], inter=[], union=[], frame_sha1=[], iou=[])
+        for i in range(spec["n_frames"]):
+            mask = np.zeros_like(frames[i])
+            ret = m.update(bbox=boxes[i], frame=frames[i], mask=mask, color=(0, 0, 255))
+            tg = cv.cvtColor(truth[i], cv.COLOR_BGR2GRAY)
+            inter, union = orc.iou_counts(mask[:, :, 2], tg)
+            per["bbox"].append(boxes[i])
+            per["ret"].append(-1 if ret is None else int(ret))
+            per["mask_sha1"].append(sha1(mask[:, :, 2]))
+            per["fg"].append(int(np.count_nonzero(mask[:, :, 2])))
+            per["inter"].append(inter)
+            per["union"].append(union)
+            per["iou"].append(float(ref_benchmark.computeBenchmark(mask[:, :, 2], tg)))
+            per["frame_sha1"].append(sha1(frames[i]))
+            assert not mask[:, :, :2].any()
+            if i in spec["dump"]:
+                eb = orc.enlarge_bbox(boxes[i], frames[i].shape)
+                y0, y1 = orc.slice_extent(eb[1], eb[3], frames[i].shape[0])
+                x0, x1 = orc.slice_extent(eb[0], eb[2], frames[i].shape[1])
+                out["f%d_p1" % i] = captured["p1"]
+                out["f%d_sa" % i] = captured["sa"] if spec["params"]["novelty_detection"] else np.zeros(0)
+                out["f%d_segments" % i] = captured["segments"]
+                out["f%d_priors" % i] = captured["priors"].astype(np.float32)
+                out["f%d_pre" % i] = captured["pre"]
+                out["f%d_post" % i] = mask[y0:y1, x0:x1, 2].copy()
+                out["f%d_rect" % i] = np.array([x0, y0, x1 - x0, y1 - y0], np.int32)
+                out["f%d_thr" % i] = np.float64(captured["thr"])
+                assert captured["pre"].shape == (y1 - y0, x1 - x0)
+        out["bbox"] = np.array(per["bbox"], np.int32)
+        out["ret"] = np.array(per["ret"], np.int32)
+        out["fg"] = np.array(per["fg"], np.int64)
+        out["inter"] = np.array(per["inter"], np.int64)
+        out["union"] = np.array(per["union"], np.int64)
+        out["iou"] = np.array(per["iou"], np.float64)
+        out["mask_sha1"] = np.array(per["mask_sha1"])
+        out["frame_sha1"] = np.array(per["frame_sha1"])
+        out["meta"] = np.array(json.dumps(dict(
+            name=name, video=v, multi_selection=spec["multi_selection"], segments=spec["segments"],
+            params=spec["params"], n_frames=spec["n_frames"], dump=spec["dump"], n_models=n_models,
+            pts_frame_numbers=pts_frames, versions=dict(cv2=cv.__version__, numpy=np.__version__,
+                                                        sklearn=__import__("sklearn").__version__,
+                                                        numba=__import__("numba").__version__))))
+        print(name, "mean IoU %.4f" % np.nanmean(per["iou"]), "rets", [r for r in per["ret"] if r >= 0])
+    finally:
+        cls.compileSaliencyMap = staticmethod(orig)
+    np.savez_compressed(os.path.join(HERE, "seq_%s.npz" % name), **out)
+
+
+def run_stages(ref_maskers, ref_benchmark):
+    cls = ref_maskers.pixel_classification.PixelClassificationNonRigidMasker
+    rng = np.random.default_rng(1234)
+    out = {}
+    # getFeatures on small crops (incl. degenerate shapes); :249-277
+    cases = [(37, 53, "8 hsv_lab"), (1, 1, "6 lab"), (9, 200, "6 lab"), (20, 3, "2 rgb"), (12, 17, "3 rgb_hsv_lab")]
+    for ci, (h, w, feats) in enumerate(cases):
+        crop = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        m = cls(debug=False, frame=crop, config=dict(multi_selection=False, params=dict(features=feats)))
+        frames, params = m.buildFramesParameter(crop)
+        X, _ = m.getFeatures((0, 0, w, h), frames, np.array([], ndmin=2, dtype=np.uint8), int(params[0]), params,
+                             train=False)
+        assert np.array_equal(X, np.rint(X))
+        out["feat%d_crop" % ci] = crop
+        out["feat%d_X" % ci] = X.astype(np.int16)
+        out["feat%d_features" % ci] = np.array(feats)
+    out["feat_n"] = np.int64(len(cases))
+    # compileSaliencyMap direct (:230-246): priors in {-1, 1}, prior_weight 0 / 0.1, novelty on/off
+    sal = [(40, 50, "grid:7", 0.0, False), (33, 61, "voronoi:40", 0.1, True), (64, 64, "voronoi:9", 0.1, False),
+           (25, 31, "grid:4", 0.0, True)]
+    for si, (h, w, seg, pw, nov) in enumerate(sal):
+        crop = np.zeros((h, w, 3), np.uint8)
+        segments = make_segment_provider(seg)(crop)
+        labels, areas = np.unique(segments, return_counts=True)
+        p1 = rng.random(h * w)
+        # push some segments right onto the 0.5 decision boundary
+        p1 = np.clip(0.5 + (p1 - 0.5) * rng.choice([1.0, 1e-3, 1e-6], size=h * w), 0, 1)
+        probs = np.stack([1 - p1, p1], 1)
+        sa = (rng.random((h, w)) * 30) if nov else np.zeros((h, w), np.uint8)
+        thr = 24.5 if nov else 0.0
+        priors = rng.choice(np.array([-1, 1], np.float32), size=len(labels)).astype(np.float32)
+        mask = np.zeros((h + 6, w + 9, 3), np.uint8)
+        bbox = (4, 3, w, h)
+        cls.compileSaliencyMap(probs=probs, mask=mask, segments=segments, outlier_scores=sa, bbox=bbox,
+                               labels=labels, areas=areas, priors=priors, prior_weight=pw,
+                               outlier_threshold=thr, crop_frame_shape=crop.shape)
+        out["sal%d_p1" % si] = p1
+        out["sal%d_sa" % si] = np.asarray(sa, np.float64)
+        out["sal%d_segments" % si] = segments.astype(np.int32)
+        out["sal%d_priors" % si] = priors
+        out["sal%d_pw" % si] = np.float64(pw)
+        out["sal%d_thr" % si] = np.float64(thr)
+        out["sal%d_map" % si] = mask[3:3 + h, 4:4 + w, 2].copy()
+    out["sal_n"] = np.int64(len(sal))
+    # computeBenchmark (benchmark.py:8-14) incl. empty union
+    for bi, (h, w, pm, pt) in enumerate([(30, 40, 0.3, 0.4), (17, 5, 0.0, 0.0), (8, 8, 1.0, 0.1)]):
+        a = (rng.random((h, w)) < pm).astype(np.uint8) * 255
+        b = (rng.random((h, w)) < pt).astype(np.uint8) * rng.integers(1, 256, (h, w)).astype(np.uint8)
+        with np.errstate(all="ignore"):
+            val = ref_benchmark.computeBenchmark(a, b)
+        out["iou%d_mask" % bi] = a
+        out["iou%d_truth" % bi] = b
+        out["iou%d_value" % bi] = np.float64(val)
+    out["iou_n"] = np.int64(3)
+    np.savez_compressed(os.path.join(HERE, "stages.npz"), **out)
+    print("stages done")
+
+
+def main():
+    ref_maskers, ref_benchmark = ref_shim.load()
+    with open(os.path.join(ref_shim.REFERENCE_ROOT, "polygons.yaml")) as f:
+        polygons = yaml.full_load(f)
+    run_stages(ref_maskers, ref_benchmark)
+    only = sys.argv[1:]
+    for name, spec in SEQUENCES.items():
+        if only and name not in only:
+            continue
+        run_sequence(name, spec, ref_maskers, ref_benchmark, polygons)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,89 @@
+"""Shared helpers for the test-suite (golden loading, video decode, model rebuild)."""
+import hashlib
+import json
+import os
+
+import cv2 as cv
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "non-rigid-object-tracking_b200")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+SEQ_NAMES = ["soldier_default", "parachute_novelty", "worm_rgb3"]
+
+
+def sha1(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+_video_cache = {}
+
+
+def read_video(kind, name):
+    key = (kind, name)
+    if key not in _video_cache:
+        cap = cv.VideoCapture(os.path.join(PKG, "Input", "SegTrack2", kind, name + ".mp4"))
+        frames = []
+        while True:
+            ok, f = cap.read()
+            if not ok:
+                break
+            frames.append(f)
+        _video_cache[key] = frames
+    return _video_cache[key]
+
+
+class GoldenSeq:
+    """One tests/golden/seq_<name>.npz with convenience accessors."""
+
+    def __init__(self, name):
+        self.z = np.load(os.path.join(GOLDEN, "seq_%s.npz" % name), allow_pickle=False)
+        self.meta = json.loads(str(self.z["meta"]))
+        self.name = name
+        self.params = self.meta["params"]
+        self.config = dict(multi_selection=self.meta["multi_selection"], params=dict(self.params))
+        self.frames = read_video("Video", self.meta["video"])
+        self.truth = read_video("Truth", self.meta["video"])
+        self.n_models = self.meta["n_models"]
+
+    def frames_match(self):
+        """The decoded frames are the ones the golden vectors were made from."""
+        return all(sha1(self.frames[i]) == str(self.z["frame_sha1"][i]) for i in range(self.meta["n_frames"]))
+
+    def tree_arrays(self, m):
+        z = self.z
+        offs = z["m%d_offsets" % m]
+        out = []
+        for t in range(len(offs) - 1):
+            s = slice(int(offs[t]), int(offs[t + 1]))
+            out.append((z["m%d_feature" % m][s], z["m%d_threshold" % m][s], z["m%d_left" % m][s],
+                        z["m%d_right" % m][s], z["m%d_value1" % m][s]))
+        return out
+
+    def pca(self, m):
+        z = self.z
+        if ("m%d_pca_mean" % m) not in z:
+            return None
+        return z["m%d_pca_mean" % m], z["m%d_pca_comp" % m]
+
+    def novelty_threshold(self, m):
+        return float(self.z["m%d_threshold_novelty" % m])
+
+    def model_frames(self):
+        return self.meta["pts_frame_numbers"][:self.n_models]
+
+    def state_at(self, i):
+        """(index, current_model) the masker holds when frame i is processed."""
+        nf = self.model_frames()
+        cur = 0
+        if self.meta["multi_selection"]:
+            while cur + 1 < len(nf) and i >= nf[cur + 1]:
+                cur += 1
+        return i, cur
+
+
+def polygons():
+    import yaml
+    with open(os.path.join(PKG, "polygons.yaml")) as f:
+        return yaml.full_load(f)
