@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- PC masker frames/s at 1080p (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload: synthetic 1920x1080 BGR sequence (pcm/synthetic.py, seed 0, 300 frames),
+default config.yaml params (20 trees, depth 5, "8 hsv_lab" -> 390 features/pixel,
+novelty off, prior 0, dilation 7), three models at frames [0, 100, 200] with the
+reference's temporal blending, tracker box (20, 20, 1880, 1040) so that the enlarged
+crop is the full frame (2 073 600 px), 16x16 grid-block labels generated once.
+
+A step = one frame through the per-frame hot path: update() (colour conversion,
+star features, forest scoring, blend, superpixel decision, dilation) + the IoU of
+the mask against the ground truth (computeBenchmark).
+
+  value      device-resident: frames, labels, truth already in HBM; K steps timed with
+             CUDA events on the launching stream; whole-job frames/s (all ranks)
+  e2e        the same step through the public plugin API (Masker.update + IoU) with
+             HOST numpy buffers, host<->device copies inside the timed region
+  roofline   fused score kernel (K1): algorithmic bytes 11 B/pixel (3 B BGR read + 8 B
+             float64 P(fg) written) / its mean duration (CUDA events)
+  cpu_baseline / --impl reference: oracle/ref_port.py (port of the reference's CPU
+             path with the reference's cost structure), 1 core, bounded sample
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "non-rigid-object-tracking_b200")
+sys.path.insert(0, PKG)
+
+import numpy as np  # noqa: E402
+
+WIDTH, HEIGHT, SEQ_FRAMES = 1920, 1080, 300
+MODEL_FRAMES = [0, 100, 200]
+TRACK_BOX = (20, 20, 1880, 1040)
+ALGO_BYTES_PER_PX_K1 = 11
+PARAMS = dict(n_estimators=20, max_depth=5, n_components=1, novelty_detection=False, over_segmentation="grid:16",
+              features="8 hsv_lab", dilation_kernel=7, prior_weight=0.0)
+CONFIG = dict(multi_selection=True, params=PARAMS)
+METRIC = "PC masker frames/sec at 1080p"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.samples = []
+        self.stop = threading.Event()
+        self.gpu = gpu_index
+        self.thread = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def sequence_state(i, model_frames):
+    """(current model, next model or -1, w_cur, w_next) at sequence index i
+    (reference pixel_classification.py:81-87, :117-118)."""
+    cur = 0
+    while cur + 1 < len(model_frames) and i >= model_frames[cur + 1]:
+        cur += 1
+    if cur + 1 < len(model_frames):
+        span = model_frames[cur + 1] - model_frames[cur]
+        tmp = i - model_frames[cur]
+        return cur, cur + 1, 1 - (tmp / span), tmp / span
+    return cur, -1, 1.0, 0.0
+
+
+def train_models(masker, seq):
+    import cv2 as cv
+    for f in MODEL_FRAMES:
+        poly = seq.polygon(0, f)
+        masker.addModel(frame=seq.frame(f), poly_roi=poly, bbox=cv.boundingRect(np.array(poly, np.int32)),
+                        bbox_roni=seq.roni(), n_frame=f)
+
+
+class CachedGrid:
+    """16x16 grid-block labels, generated once per crop shape."""
+
+    def __init__(self, block=16):
+        self.block, self.cache = block, {}
+
+    def __call__(self, crop):
+        key = crop.shape[:2]
+        if key not in self.cache:
+            from pcm.providers import grid_segments
+            self.cache[key] = grid_segments(crop, self.block)
+        return self.cache[key]
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arm (oracle port): cpu_baseline of the default arm and `--impl reference`
+# ---------------------------------------------------------------------------------------
+def cpu_port_setup(seq, clfs):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from ref_port import RefPortMasker
+    seg = CachedGrid(16)
+    m = RefPortMasker(debug=False, frame=seq.frame(0), config=CONFIG, poly_roi=None, segment_fn=seg)
+    for f, clf in zip(MODEL_FRAMES, clfs):
+        m.models.append({"n_frame": f, "model": clf})
+        m.novelty_det.append({"n_frame": f, "model": None, "threshold": 0.0})
+    return m
+
+
+def cpu_port_step(m, frame, truth, sample_w, sample_h, index):
+    """One update() + IoU of the port on a sample_w x sample_h crop; returns seconds."""
+    from ref_port import compute_benchmark
+    m.index = index
+    m.current_model = sequence_state(index, MODEL_FRAMES)[0]
+    # tracker box whose 20 px enlargement gives exactly the sample crop at (200, 200)
+    box = (220, 220, sample_w - 40, sample_h - 40)
+    mask = np.zeros_like(frame)
+    t0 = time.perf_counter()
+    m.update(bbox=box, frame=frame, mask=mask)
+    compute_benchmark(mask[:, :, 2], truth)
+    return time.perf_counter() - t0
+
+
+def sample_dims(px):
+    """w x h (16:9-ish, multiples of 16) with about `px` pixels, capped at a quarter frame."""
+    px = int(min(max(px, 16384), 960 * 540))
+    h = max(64, int((px * 9 / 16) ** 0.5) // 16 * 16)
+    w = max(64, (px // h) // 16 * 16)
+    return min(w, 960), min(h, 540)
+
+
+def sklearn_models(seq):
+    """Train the three forests exactly as addModel does, on the CPU port's own features
+    (used by `--impl reference`, which must not touch the CUDA library)."""
+    import cv2 as cv
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from ref_port import RefPortMasker
+    m = RefPortMasker(debug=False, frame=seq.frame(0), config=CONFIG, poly_roi=None, segment_fn=CachedGrid(16))
+    for f in MODEL_FRAMES:
+        poly = seq.polygon(0, f)
+        m.addModel(frame=seq.frame(f), poly_roi=poly, bbox=cv.boundingRect(np.array(poly, np.int32)),
+                   bbox_roni=seq.roni(), n_frame=f)
+    return [d["model"] for d in m.models]
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from pcm.synthetic import SyntheticSequence
+    seq = SyntheticSequence(WIDTH, HEIGHT, SEQ_FRAMES, seed=0)
+    log("[reference] training 3 forests with the CPU port ...")
+    clfs = sklearn_models(seq)
+    m = cpu_port_setup(seq, clfs)
+    n_steps = args.steps + args.warmup
+    # ~85 k px/s on one core; keep the whole run near two minutes
+    sw, sh = sample_dims(85000 * 120 / max(n_steps, 1))
+    frames = [seq.frame(i) for i in range(4)]
+    truths = [seq.truth(i) for i in range(4)]
+    cpu_port_step(m, frames[0], truths[0], 64, 64, 0)          # numba JIT
+    for s in range(args.warmup):
+        cpu_port_step(m, frames[s % 4], truths[s % 4], sw, sh, s % SEQ_FRAMES)
+    t = 0.0
+    for s in range(args.steps):
+        t += cpu_port_step(m, frames[s % 4], truths[s % 4], sw, sh, s % SEQ_FRAMES)
+    px_per_s = args.steps * sw * sh / t
+    value = px_per_s / (WIDTH * HEIGHT)
+    sample = "update()+IoU on a %dx%d crop of the 1080p frame per step, scaled to full-frame frames/s by pixel count" % (sw, sh)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cores_available": os.cpu_count(),
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config():
+    return {"workload": "synthetic 1920x1080 BGR sequence, 300 frames, crop = full frame (2073600 px), "
+                        "3 models @ [0,100,200] blended, 16x16 grid labels",
+            "params": PARAMS, "l2": "24 distinct resident frames (149 MB) cycled; inputs larger than the 126 MB L2",
+            "parallelism": "one independent sequence per GPU (no data-path collective)"}
+
+
+# ---------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    from maskers import getMaskerByName
+    from pcm import capi
+    from pcm.synthetic import SyntheticSequence
+
+    seq = SyntheticSequence(WIDTH, HEIGHT, SEQ_FRAMES, seed=rank)
+    seg = CachedGrid(16)
+    t0 = time.time()
+    masker = getMaskerByName("PC", debug=False, frame=seq.frame(0), config=CONFIG, poly_roi=seq.polygon(0, 0),
+                             update_mask=False, segment_fn=seg, device=local_rank)
+    train_models(masker, seq)
+    log("[rank %d] trained %d models in %.1f s" % (rank, len(masker.models), time.time() - t0))
+    h = masker.native
+    NF = args.frames
+    frames_h = [seq.frame(i) for i in range(NF)]
+    truth_h = [seq.truth(i) for i in range(NF)]
+    rect = capi.crop_rect(TRACK_BOX, HEIGHT, WIDTH)
+    assert rect == (0, 0, WIDTH, HEIGHT)
+    labels_h = seg(frames_h[0])
+    S = int(labels_h.max()) + 1
+
+    # ---- device-resident inputs ----------------------------------------------------------
+    d_frames = torch.from_numpy(np.stack(frames_h)).to(dev)            # [NF, H, W, 3] u8
+    d_truth = torch.from_numpy(np.stack(truth_h)).to(dev)              # [NF, H, W] u8
+    d_labels = torch.from_numpy(labels_h).to(dev)                      # [H, W] i32
+    d_mask = torch.zeros((HEIGHT, WIDTH), dtype=torch.uint8, device=dev)
+    n_total = args.steps + args.warmup
+    d_counts = torch.zeros((n_total, 2), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+    frame_bytes = HEIGHT * WIDTH * 3
+
+    def device_step(s):
+        cur, nxt, w0, w1 = sequence_state(s % SEQ_FRAMES, MODEL_FRAMES)
+        p = capi.Handle.make_params(cur, nxt, w0, w1, novelty=False, dilation_kernel=PARAMS["dilation_kernel"],
+                                    outlier_threshold=0.0, prior_weight=PARAMS["prior_weight"])
+        f = s % NF
+        h.update_device(d_frames.data_ptr() + f * frame_bytes, HEIGHT, WIDTH, WIDTH * 3, rect, d_labels.data_ptr(), S,
+                        0, p, d_mask.data_ptr(), WIDTH)
+        h.iou_device(d_mask.data_ptr(), WIDTH, d_truth.data_ptr() + f * HEIGHT * WIDTH, WIDTH, 1, HEIGHT, WIDTH,
+                     d_counts.data_ptr() + 16 * s)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(args.warmup):
+        device_step(s)
+    barrier()
+    launches0 = h.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record(stream)
+        for s in range(args.warmup, n_total):
+            device_step(s)
+        e1.record(stream)
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = h.launch_count - launches0
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * args.steps / (ms_total / 1e3)
+
+    # ---- per-kernel timing over the same K steps (events around every launch) --------------
+    h.profile_enable(True)
+    h.profile_read(reset=True)
+    for s in range(args.warmup, n_total):
+        device_step(s)
+    prof = h.profile_read(reset=True)
+    h.profile_enable(False)
+    k1_ms = prof["score"][0] / max(prof["score"][1], 1)
+    step_kernel_ms = sum(v[0] for v in prof.values()) / max(prof["score"][1], 1)
+    peak, peak_src = measured_peak_gbs()
+    achieved = ALGO_BYTES_PER_PX_K1 * WIDTH * HEIGHT / (k1_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "score_kernel (fused convert+features+forest)", "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "k1_ms": k1_ms, "kernel_share_of_step": k1_ms / step_kernel_ms if step_kernel_ms else None,
+                "per_kernel_ms": {k: (v[0] / v[1] if v[1] else 0.0) for k, v in prof.items()},
+                "limiter": "issue slots / shared-memory wavefronts of the forest traversal (see DESIGN.md)"}
+    traffic_file = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.isfile(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+
+    # sanity: the timed steps produced real masks
+    counts = d_counts.cpu().numpy()
+    assert counts[args.warmup:, 1].min() > 0, "empty masks/truth in the timed region"
+    mean_iou = float(np.mean(counts[args.warmup:, 0] / counts[args.warmup:, 1]))
+
+    # ---- end to end through the plugin API with host buffers -------------------------------
+    h.set_stream(None)
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    mask_h = np.zeros_like(frames_h[0])
+
+    def host_step(s):
+        masker.index = s % SEQ_FRAMES
+        masker.current_model = sequence_state(masker.index, MODEL_FRAMES)[0]
+        f = s % NF
+        masker.update(bbox=TRACK_BOX, frame=frames_h[f], mask=mask_h, color=(0, 0, 255))
+        return h.iou_counts(mask_h[:, :, 2], truth_h[f])
+
+    for s in range(3):
+        host_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        host_step(s)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    npx = WIDTH * HEIGHT
+    e2e = {"value": world * e2e_steps / e2e_s, "unit": "frames/s", "steps": e2e_steps,
+           "h2d_bytes_per_step": npx * 3 + npx * 4 + npx + npx, "d2h_bytes_per_step": npx + 16,
+           "api": "maskers.getMaskerByName('PC').update(bbox, frame, mask, color) + Handle.iou_counts(mask, truth)"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        log("[cpu_baseline] timing the CPU port on a bounded sample ...")
+        clfs = [d["model"] for d in masker.models]
+        pm = cpu_port_setup(seq, clfs)
+        cpu_port_step(pm, frames_h[0], truth_h[0], 64, 64, 0)          # numba JIT
+        sw, sh = 640, 352
+        reps, tt = 0, 0.0
+        while reps < 2 or (tt < 8.0 and reps < 8):
+            tt += cpu_port_step(pm, frames_h[reps % NF], truth_h[reps % NF], sw, sh, reps)
+            reps += 1
+        cpu = {"value": reps * sw * sh / tt / npx, "unit": "frames/s", "cores": 1, "kind": "port",
+               "sample": "%d update()+IoU steps on a %dx%d crop of the 1080p frame (%.1f s), scaled to full-frame "
+                         "frames/s by pixel count; the reference path is single-threaded" % (reps, sw, sh, tt),
+               "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic", "config": workload_config(),
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "mean_iou_vs_truth": mean_iou, "impl": "b200",
+        }
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=24, help="distinct device-resident frames cycled (24 x 6.2 MB > L2)")
+    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

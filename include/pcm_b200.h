@@ -1,0 +1,192 @@
+/*
+ * pcm_b200.h -- C ABI of the B200-native PixelClassification (PC) masker hot path.
+ *
+ * Drop-in boundary for the per-frame path of the reference
+ * materight/non-rigid-object-tracking:
+ *     maskers/pixel_classification.py:45-126   PixelClassificationNonRigidMasker.update
+ *     maskers/pixel_classification.py:230-277  compileSaliencyMap / getFeatures (numba)
+ *     maskers/pixel_classification.py:294-309  buildFramesParameter (cv.cvtColor)
+ *     benchmark.py:8-14                        computeBenchmark (IoU)
+ * The reference binds its only native component the same way
+ * (prim/__init__.py:7-38 -> ctypes -> extern "C" rp(), prim/src/rp_py.cpp:7-23);
+ * INTEGRATION.md shows the ctypes stub a maintainer adds for this library.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no ownership transfer; every function
+ *     returns 0 on success or a negative PCM_E_* code, and the message is
+ *     available from pcm_last_error() (thread-local).
+ *   - "host" entry points take HOST buffers and include the host<->device
+ *     copies; "_device" entry points take DEVICE buffers, enqueue on the
+ *     handle's stream and do not synchronise.
+ *   - images are 8-bit, BGR interleaved (OpenCV layout), rows `stride` bytes apart.
+ *   - there is NO CPU fallback: without a CUDA device pcm_create fails.
+ */
+#ifndef PCM_B200_H
+#define PCM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCM_ABI_VERSION 1
+
+enum {
+    PCM_OK = 0,
+    PCM_E_INVALID = -1,      /* bad argument */
+    PCM_E_CUDA = -2,         /* CUDA runtime error */
+    PCM_E_STATE = -3,        /* call order (e.g. model before features) */
+    PCM_E_LIMIT = -4,        /* exceeds a documented limit */
+    PCM_E_LABEL = -5         /* label outside [0, n_labels) */
+};
+
+/* colour-space ids of the `features` token (pixel_classification.py:301-308) */
+enum { PCM_SPACE_RGB = 0 /* raw BGR planes */, PCM_SPACE_HSV = 1, PCM_SPACE_LAB = 2 };
+
+typedef struct pcm_handle pcm_handle;
+
+/* ---- lifetime -------------------------------------------------------- */
+
+int pcm_abi_version(void);
+const char* pcm_last_error(void);
+
+/* One handle per masker instance (= per tracked target, main.py:138-144). */
+int pcm_create(int device, pcm_handle** out);
+void pcm_destroy(pcm_handle* h);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*) instead of the
+ * handle's own non-blocking stream; NULL restores the own stream. */
+int pcm_set_stream(pcm_handle* h, void* cuda_stream);
+int pcm_synchronize(pcm_handle* h);
+
+/* ---- configuration (config.yaml `params.features`, :300-308) ---------- */
+
+/* "8 hsv_lab" -> n_neighbors = 8, space_ids = {HSV, LAB}.  Must precede
+ * pcm_add_model.  Limits: 1 <= n_neighbors <= 16, 1 <= n_spaces <= 3. */
+int pcm_set_features(pcm_handle* h, int n_neighbors, int n_spaces, const int* space_ids);
+
+/* Number of features per pixel F = 3 * (1 + 8 n) * n_spaces (:252-261). */
+int pcm_num_features(const pcm_handle* h);
+
+/* ---- models (addModel :166-228; training itself stays with the caller) -- */
+
+/* Append one fitted random forest (sklearn RandomForestClassifier arrays,
+ * estimators_ order, nodes of tree t at [tree_offsets[t], tree_offsets[t+1])):
+ *   feature[i]    column of X tested at node i            (tree_.feature)
+ *   threshold[i]  float64 split value on X/255            (tree_.threshold)
+ *   left/right[i] child node ids within the tree, -1 leaf (tree_.children_*)
+ *   value1[i]     class-1 fraction at node i              (tree_.value[i,0,1])
+ * Thresholds are collapsed to integers here (x_f32 <= thr  <=>  v <= t), so
+ * scoring is bit-exact against predict_proba (:80,:82).
+ * Limits: <= 32767 internal nodes and <= 32768 leaves per tree.
+ * Returns the model index in *model_index. */
+int pcm_add_model(pcm_handle* h, int n_frame, int n_trees, const int64_t* tree_offsets,
+                  const int32_t* feature, const double* threshold,
+                  const int32_t* left, const int32_t* right, const double* value1,
+                  int* model_index);
+
+/* Attach the novelty detector of a model: PCA mean_[F], components_[0][F]
+ * (n_components == 1, config.yaml:27) (:205-213). */
+int pcm_set_novelty(pcm_handle* h, int model_index, const double* mean, const double* component, int n_features);
+
+int pcm_num_models(const pcm_handle* h);
+
+/* ---- per-frame hot path ------------------------------------------------ */
+
+/* The reference's bbox enlargement + numpy slice clamping (:49-51):
+ * rect_out = {x, y, w, h} of the crop actually processed. */
+int pcm_crop_rect(const int bbox_xywh[4], int frame_h, int frame_w, int rect_out[4]);
+
+typedef struct pcm_update_params {
+    int32_t model_cur;           /* current model index */
+    int32_t model_next;          /* next model to blend with, or -1 (:81) */
+    double w_cur;                /* np.average weights (:87): 1 - tmp/span */
+    double w_next;               /*                            tmp/span    */
+    int32_t novelty;             /* params.novelty_detection (:57) */
+    int32_t dilation_kernel;     /* params.dilation_kernel (:112) */
+    double outlier_threshold;    /* novelty_det[cur].threshold (:108) */
+    double prior_weight;         /* params.prior_weight (:107) */
+} pcm_update_params;
+
+/* One `update()` (:45-112) on HOST buffers, synchronous:
+ *   frame     H x W x 3 BGR, rows frame_stride bytes apart; not modified
+ *   rect      crop {x, y, w, h} from pcm_crop_rect
+ *   labels    h*w int32 over-segmentation labels of the crop, values in [0, n_labels)
+ *   priors    n_labels float32 (computePriors :129-163) or NULL for all -1
+ *   mask      first byte of the channel to write (the reference writes channel 2
+ *             of an H x W x 3 image: mask + 2, mask_pixel_stride = 3); only the
+ *             crop rectangle is written (overwrite, then dilation, :246,:112)
+ * Host->device copies of frame crop / labels / priors and the device->host copy
+ * of the mask are inside this call. */
+int pcm_update(pcm_handle* h, const uint8_t* frame, int frame_h, int frame_w, int64_t frame_stride,
+               const int rect[4], const int32_t* labels, int n_labels, const float* priors,
+               const pcm_update_params* params,
+               uint8_t* mask, int64_t mask_row_stride, int64_t mask_pixel_stride);
+
+/* Same work on DEVICE buffers, asynchronous on the handle's stream.
+ * d_mask is a dense plane (pixel stride 1) of frame_h x frame_w, rows
+ * mask_row_stride bytes apart; only the crop rectangle is written. */
+int pcm_update_device(pcm_handle* h, const uint8_t* d_frame, int frame_h, int frame_w, int64_t frame_stride,
+                      const int rect[4], const int32_t* d_labels, int n_labels, const float* d_priors,
+                      const pcm_update_params* params,
+                      uint8_t* d_mask, int64_t mask_row_stride);
+
+/* computeBenchmark (benchmark.py:8-14): counts[0] = #(mask!=0 && truth!=0),
+ * counts[1] = #(mask!=0 || truth!=0) over h x w; the caller forms the float64
+ * quotient (NaN on an empty union, like numpy).  truth_channels = 1 (gray) or
+ * 3 (BGR frame: converted with cv.cvtColor(BGR2GRAY) arithmetic, main.py:285). */
+int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stride, int64_t mask_pixel_stride,
+            const uint8_t* truth, int64_t truth_row_stride, int truth_channels,
+            int height, int width, int64_t counts[2]);
+
+/* Device variant: dense mask plane and truth on the device; counts are added
+ * into d_counts[2] (int64, caller zeroes), asynchronous. */
+int pcm_iou_device(pcm_handle* h, const uint8_t* d_mask, int64_t mask_row_stride,
+                   const uint8_t* d_truth, int64_t truth_row_stride, int truth_channels,
+                   int height, int width, int64_t* d_counts);
+
+/* ---- parity taps (tests, smoke; not needed by the reference flow) -------- */
+
+/* cv.cvtColor(img, BGR2HSV / BGR2LAB) of an h x w x 3 host image with the same
+ * device code the fused kernel uses; space = PCM_SPACE_HSV / PCM_SPACE_LAB. */
+int pcm_convert(pcm_handle* h, const uint8_t* bgr, int height, int width, int64_t stride,
+                int space, uint8_t* out, int64_t out_stride);
+
+/* Raw star-neighbourhood features of a crop as the reference's getFeatures
+ * builds them (:249-277): X[h*w, F] int16 with -1 outside the crop. */
+int pcm_gather_features(pcm_handle* h, const uint8_t* frame, int frame_h, int frame_w, int64_t frame_stride,
+                        const int rect[4], int16_t* X);
+
+/* Stage dumps of the LAST pcm_update / pcm_update_device on this handle
+ * (any pointer may be NULL):
+ *   p1[h*w]       blended P(foreground) (:80-95), float64
+ *   sa[h*w]       blended novelty error (:57-63, :88-93), float64 (zeros if off)
+ *   scores[S]     per-label score as the reference's float32 (:241)
+ *   areas[S]      per-label pixel counts (:97)
+ *   pre[h*w]      0/255 map before dilation (:242-246)
+ *   n_exact       number of labels decided by the exact sequential-f32 path */
+int pcm_debug_last(pcm_handle* h, double* p1, double* sa, float* scores, int64_t* areas,
+                   uint8_t* pre, int32_t* n_exact);
+
+/* The colour-conversion lookup tables built at pcm_create (parity of the table
+ * construction itself): gamma[256], cbrt[2041] uint16; sdiv[256], hdiv[256] int32. */
+int pcm_debug_tables(pcm_handle* h, uint16_t* gamma, uint16_t* cbrt_tab, int32_t* sdiv, int32_t* hdiv);
+
+/* Number of kernel launches issued through this handle so far. */
+int64_t pcm_launch_count(const pcm_handle* h);
+
+/* Per-kernel device timing (CUDA events on the handle's stream around every
+ * launch while enabled).  Kernel ids: 0 score (fused convert+features+forest),
+ * 1 segment_reduce, 2 segment_decide, 3 segment_resolve, 4 mask_dilate, 5 iou.
+ * pcm_profile_read synchronises the stream, adds the finished launches to the
+ * running totals and returns them (ms_sum[i], count[i] for i < n <= 6);
+ * reset != 0 clears the totals afterwards. */
+#define PCM_NUM_KERNELS 6
+int pcm_profile_enable(pcm_handle* h, int on);
+int pcm_profile_read(pcm_handle* h, double* ms_sum, int64_t* count, int n, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCM_B200_H */

@@ -1,0 +1,909 @@
+// pcm_api.cu -- host side of libpcm_b200.so: the C ABI declared in include/pcm_b200.h.
+//
+// Owns device memory, streams, the packed forests, and launches the kernels of
+// pcm_kernels.cuh.  No CPU implementation of the hot path exists in this library:
+// every entry point either runs the CUDA kernels or fails.
+#include "../../include/pcm_b200.h"
+#include "pcm_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pcm;
+
+// ---------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(PCM_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                 \
+    } while (0)
+
+// ---------------------------------------------------------------------------------
+// grow-only buffers
+// ---------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// ---------------------------------------------------------------------------------
+// models
+// ---------------------------------------------------------------------------------
+struct Model {
+    int n_frame = 0;
+    DevForest forest{};
+    void* d_nodes = nullptr;
+    void* d_leaves = nullptr;
+    void* d_trees = nullptr;
+    bool has_pca = false;
+    DevPCA pca{};
+    void* d_pca = nullptr;        // comp | comp255 | mean, 3F doubles
+    int max_depth = 0;
+};
+
+struct pcm_handle {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    ColorTables* d_tables = nullptr;
+    ColorTables h_tables;
+    bool features_set = false;
+    Geom geom{};
+    std::vector<Model> models;
+    int64_t launches = 0;
+
+    // optional per-kernel event timing
+    bool profiling = false;
+    struct Timed { int id; cudaEvent_t a, b; };
+    std::vector<Timed> pending;
+    std::vector<cudaEvent_t> free_events;
+    double prof_ms[PCM_NUM_KERNELS] = {0};
+    int64_t prof_n[PCM_NUM_KERNELS] = {0};
+
+    // per-update scratch (device)
+    DevBuf frame, labels, priors, p1, sa, seg, rmin, rmax, decision, scores, flagged, mask, pre, counts;
+    // pinned staging (host)
+    PinBuf h_frame, h_labels, h_priors, h_mask, h_small;
+
+    // description of the last update (for pcm_debug_last)
+    int last_cw = 0, last_ch = 0, last_S = 0;
+    bool last_novelty = false;
+    bool last_valid = false;
+};
+
+// seg buffer layout: [sum S f64][asum S f64][area S i32][n_flagged i32][err i32]
+struct SegLayout {
+    size_t sum, asum, area, nflag, err, total;
+};
+static SegLayout seg_layout(int S) {
+    SegLayout l;
+    l.sum = 0;
+    l.asum = l.sum + sizeof(double) * (size_t)S;
+    l.area = l.asum + sizeof(double) * (size_t)S;
+    l.nflag = l.area + sizeof(int) * (size_t)S;
+    l.nflag = (l.nflag + 7) / 8 * 8;
+    l.err = l.nflag + sizeof(int);
+    l.total = l.err + sizeof(int);
+    return l;
+}
+
+// ---------------------------------------------------------------------------------
+// per-kernel timing
+// ---------------------------------------------------------------------------------
+struct KernelTimer {
+    pcm_handle* h;
+    int id;
+    cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(pcm_handle* h) {
+        if (!h->free_events.empty()) { cudaEvent_t e = h->free_events.back(); h->free_events.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    KernelTimer(pcm_handle* h_, int id_) : h(h_), id(id_) {
+        if (!h->profiling) return;
+        a = get(h); b = get(h);
+        cudaEventRecord(a, h->stream);
+    }
+    ~KernelTimer() {
+        if (!a) return;
+        cudaEventRecord(b, h->stream);
+        h->pending.push_back({id, a, b});
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// tables (OpenCV's fixed-point LUTs)
+// ---------------------------------------------------------------------------------
+static void build_tables(ColorTables& t) {
+    memset(&t, 0, sizeof t);
+    for (int i = 0; i < 256; ++i) {
+        double x = i / 255.0;
+        double lin = x <= 0.04045 ? x / 12.92 : pow((x + 0.055) / 1.055, 2.4);
+        t.gamma[i] = (uint16_t)nearbyint(lin * 2040.0);
+    }
+    for (int i = 0; i < LAB_CBRT_SIZE; ++i) {
+        double x = i / 2040.0;
+        double f = x < 216.0 / 24389.0 ? x * (841.0 / 108.0) + 16.0 / 116.0 : cbrt(x);
+        t.cbrt_tab[i] = (uint16_t)nearbyint(f * 32768.0);
+    }
+    // OpenCV evaluates the table with softfloat; float64 differs in exactly these entries
+    t.cbrt_tab[49] = 9454;
+    t.cbrt_tab[628] = 22126;
+    t.sdiv[0] = t.hdiv[0] = 0;
+    for (int i = 1; i < 256; ++i) {
+        t.sdiv[i] = (int32_t)nearbyint((255 << 12) / (double)i);
+        t.hdiv[i] = (int32_t)nearbyint((180 << 12) / (6.0 * i));
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------
+static Geom make_geom(int n, int n_spaces, const int* ids) {
+    Geom g{};
+    g.n = n;
+    g.n_spaces = n_spaces;
+    for (int i = 0; i < n_spaces; ++i) g.space_id[i] = ids[i];
+    g.K = 1 + 8 * n;
+    g.F = 3 * g.K * n_spaces;
+    g.n_planes = 3 * n_spaces + 1;
+    g.PW = TILE_W + 2 * n;
+    g.PH = TILE_H + 2 * n;
+    g.RS = (g.PW + 3) & ~3;
+    g.PS = g.RS * g.PH;
+    g.RAWS = ((g.PW * 3 + 3 + 3) & ~3) + 4;
+    return g;
+}
+
+// ---------------------------------------------------------------------------------
+// forest encoding
+// ---------------------------------------------------------------------------------
+// Largest integer t in [-2, 255] with  float32(v / 255) <= thr  <=>  v <= t  for v in -1..255
+// (features are X/255 cast to float32 by sklearn).
+static int int_threshold(double thr) {
+    int cnt = 0;
+    for (int v = -1; v <= 255; ++v) {
+        float x = (float)((double)v / 255.0);
+        if ((double)x <= thr) ++cnt;
+    }
+    return cnt - 2;
+}
+
+struct EncTree {
+    std::vector<uint2> nodes;
+    std::vector<double> leaves;
+    unsigned root = 0;
+    int depth = 0;
+};
+
+struct Encoder {
+    const Geom& g;
+    const int32_t* feature;
+    const double* threshold;
+    const int32_t* left;
+    const int32_t* right;
+    const double* value1;
+    int n;                       // nodes in this tree
+    std::vector<int> tint;       // integer threshold per node
+    std::vector<int> node_id;    // new index of kept internal nodes, -1 otherwise
+    std::vector<int> leaf_id;
+    EncTree out;
+    std::string err;
+
+    // skip nodes that send every value right (t == -2): they are not representable
+    // with an unsigned compare and never needed
+    int skip(int i) const {
+        while (left[i] != -1 && tint[i] < -1) i = right[i];
+        return i;
+    }
+    unsigned ref_of(int i) const {
+        i = skip(i);
+        return left[i] == -1 ? (0x8000u | (unsigned)leaf_id[i]) : (unsigned)node_id[i];
+    }
+    bool run() {
+        tint.assign(n, 0);
+        node_id.assign(n, -1);
+        leaf_id.assign(n, -1);
+        for (int i = 0; i < n; ++i) {
+            if (left[i] == -1) continue;
+            if (left[i] < 0 || left[i] >= n || right[i] < 0 || right[i] >= n) { err = "child index out of range"; return false; }
+            if (feature[i] < 0 || feature[i] >= g.F) { err = "feature index out of range"; return false; }
+            tint[i] = int_threshold(threshold[i]);
+        }
+        // iterative DFS from the root, numbering reachable kept nodes / leaves in preorder
+        std::vector<std::pair<int, int>> stack;   // (node, depth = internal nodes above)
+        stack.push_back({skip(0), 0});
+        int n_int = 0, n_leaf = 0, depth = 0;
+        std::vector<int> order;
+        while (!stack.empty()) {
+            auto [i, d] = stack.back();
+            stack.pop_back();
+            if (left[i] == -1) {
+                if (leaf_id[i] < 0) leaf_id[i] = n_leaf++;
+                depth = std::max(depth, d);
+                continue;
+            }
+            if (node_id[i] >= 0) { err = "tree is not a tree"; return false; }
+            node_id[i] = n_int++;
+            order.push_back(i);
+            stack.push_back({skip(right[i]), d + 1});
+            stack.push_back({skip(left[i]), d + 1});
+        }
+        if (n_int > 32767 || n_leaf > 32768) { err = "tree too large (limit 32767 internal nodes / 32768 leaves)"; return false; }
+        out.nodes.assign((size_t)n_int + 1, make_uint2(0xff000000u, 0x80008000u));   // +1 pad node
+        out.leaves.assign(n_leaf, 0.0);
+        for (int i = 0; i < n; ++i)
+            if (leaf_id[i] >= 0) out.leaves[leaf_id[i]] = value1[i];
+        const int vplane = 3 * g.n_spaces;
+        for (int i : order) {
+            const int f = feature[i];
+            const int q = f / (3 * g.K), rem = f % (3 * g.K), k = rem / 3, ch = rem % 3;
+            int dr, dc;
+            star_tap(k, dr, dc);
+            int plane = 3 * q + ch;
+            int thr = tint[i];
+            if (thr == -1) { plane = vplane; thr = 0; }   // "tap is outside the crop"
+            const unsigned off = (unsigned)(plane * g.PS + (dr + g.n) * g.RS + (dc + g.n));
+            if (off >= (1u << 24)) { err = "tap offset overflow"; return false; }
+            out.nodes[node_id[i]] = make_uint2(((unsigned)thr << 24) | off, ref_of(left[i]) | (ref_of(right[i]) << 16));
+        }
+        out.root = ref_of(0);
+        out.depth = depth;
+        return true;
+    }
+};
+
+static void free_model(Model& m) {
+    if (m.d_nodes) cudaFree(m.d_nodes);
+    if (m.d_leaves) cudaFree(m.d_leaves);
+    if (m.d_trees) cudaFree(m.d_trees);
+    if (m.d_pca) cudaFree(m.d_pca);
+    m = Model{};
+}
+
+// ---------------------------------------------------------------------------------
+// API: lifetime
+// ---------------------------------------------------------------------------------
+extern "C" int pcm_abi_version(void) { return PCM_ABI_VERSION; }
+extern "C" const char* pcm_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int pcm_create(int device, pcm_handle** out) {
+    if (!out) return fail(PCM_E_INVALID, "pcm_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(PCM_E_CUDA, "pcm_create: no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(PCM_E_INVALID, "pcm_create: device %d out of range [0,%d)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    pcm_handle* h = new pcm_handle();
+    h->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    build_tables(h->h_tables);
+    CUDA_TRY(cudaMalloc(&h->d_tables, sizeof(ColorTables)));
+    CUDA_TRY(cudaMemcpy(h->d_tables, &h->h_tables, sizeof(ColorTables), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+    *out = h;
+    return PCM_OK;
+}
+
+extern "C" void pcm_destroy(pcm_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto& m : h->models) free_model(m);
+    for (DevBuf* b : {&h->frame, &h->labels, &h->priors, &h->p1, &h->sa, &h->seg, &h->rmin, &h->rmax, &h->decision,
+                      &h->scores, &h->flagged, &h->mask, &h->pre, &h->counts})
+        b->release();
+    for (PinBuf* b : {&h->h_frame, &h->h_labels, &h->h_priors, &h->h_mask, &h->h_small}) b->release();
+    for (auto& t : h->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto e : h->free_events) cudaEventDestroy(e);
+    if (h->d_tables) cudaFree(h->d_tables);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+extern "C" int pcm_set_stream(pcm_handle* h, void* cuda_stream) {
+    if (!h) return fail(PCM_E_INVALID, "pcm_set_stream: NULL handle");
+    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return PCM_OK;
+}
+
+static int check_label_error(pcm_handle* h, bool sync) {
+    if (!h->seg.p || !h->last_valid) return PCM_OK;
+    int* hs = h->h_small.as<int>();
+    const SegLayout l = seg_layout(h->last_S);
+    CUDA_TRY(cudaMemcpyAsync(hs, h->seg.as<char>() + l.err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (sync) CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (*hs) return fail(PCM_E_LABEL, "label outside [0, n_labels) in the label map");
+    return PCM_OK;
+}
+
+extern "C" int pcm_synchronize(pcm_handle* h) {
+    if (!h) return fail(PCM_E_INVALID, "pcm_synchronize: NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_label_error(h, true);
+}
+
+// ---------------------------------------------------------------------------------
+// API: configuration and models
+// ---------------------------------------------------------------------------------
+extern "C" int pcm_set_features(pcm_handle* h, int n_neighbors, int n_spaces, const int* space_ids) {
+    if (!h || !space_ids) return fail(PCM_E_INVALID, "pcm_set_features: NULL argument");
+    if (n_neighbors < 1 || n_neighbors > MAX_NEIGHBORS)
+        return fail(PCM_E_LIMIT, "pcm_set_features: n_neighbors %d outside [1,%d]", n_neighbors, MAX_NEIGHBORS);
+    if (n_spaces < 1 || n_spaces > MAX_SPACES)
+        return fail(PCM_E_LIMIT, "pcm_set_features: n_spaces %d outside [1,%d]", n_spaces, MAX_SPACES);
+    for (int i = 0; i < n_spaces; ++i)
+        if (space_ids[i] < 0 || space_ids[i] > 2) return fail(PCM_E_INVALID, "pcm_set_features: bad space id %d", space_ids[i]);
+    if (!h->models.empty()) return fail(PCM_E_STATE, "pcm_set_features: models already added (tap offsets are baked in)");
+    h->geom = make_geom(n_neighbors, n_spaces, space_ids);
+    h->features_set = true;
+    return PCM_OK;
+}
+
+extern "C" int pcm_num_features(const pcm_handle* h) { return (h && h->features_set) ? h->geom.F : 0; }
+extern "C" int pcm_num_models(const pcm_handle* h) { return h ? (int)h->models.size() : 0; }
+
+extern "C" int pcm_add_model(pcm_handle* h, int n_frame, int n_trees, const int64_t* tree_offsets,
+                             const int32_t* feature, const double* threshold, const int32_t* left,
+                             const int32_t* right, const double* value1, int* model_index) {
+    if (!h || !tree_offsets || !feature || !threshold || !left || !right || !value1)
+        return fail(PCM_E_INVALID, "pcm_add_model: NULL argument");
+    if (!h->features_set) return fail(PCM_E_STATE, "pcm_add_model: call pcm_set_features first");
+    if (n_trees < 1) return fail(PCM_E_INVALID, "pcm_add_model: n_trees %d", n_trees);
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<uint2> nodes;
+    std::vector<double> leaves;
+    std::vector<int4> trees;
+    int max_depth = 0;
+    for (int t = 0; t < n_trees; ++t) {
+        const int64_t b = tree_offsets[t], e = tree_offsets[t + 1];
+        if (e <= b) return fail(PCM_E_INVALID, "pcm_add_model: tree %d is empty", t);
+        Encoder enc{h->geom, feature + b, threshold + b, left + b, right + b, value1 + b, (int)(e - b)};
+        if (!enc.run()) return fail(PCM_E_LIMIT, "pcm_add_model: tree %d: %s", t, enc.err.c_str());
+        trees.push_back(make_int4((int)nodes.size(), (int)leaves.size(), (int)enc.out.root, enc.out.depth));
+        nodes.insert(nodes.end(), enc.out.nodes.begin(), enc.out.nodes.end());
+        leaves.insert(leaves.end(), enc.out.leaves.begin(), enc.out.leaves.end());
+        max_depth = std::max(max_depth, enc.out.depth);
+    }
+    Model m;
+    m.n_frame = n_frame;
+    m.max_depth = max_depth;
+    CUDA_TRY(cudaMalloc(&m.d_nodes, nodes.size() * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc(&m.d_leaves, leaves.size() * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&m.d_trees, trees.size() * sizeof(int4)));
+    CUDA_TRY(cudaMemcpy(m.d_nodes, nodes.data(), nodes.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m.d_leaves, leaves.data(), leaves.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m.d_trees, trees.data(), trees.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    m.forest.nodes = static_cast<const uint2*>(m.d_nodes);
+    m.forest.leaves = static_cast<const double*>(m.d_leaves);
+    m.forest.trees = static_cast<const int4*>(m.d_trees);
+    m.forest.n_trees = n_trees;
+    m.forest.n_nodes = (int)nodes.size();
+    m.forest.n_leaves = (int)leaves.size();
+    h->models.push_back(m);
+    if (model_index) *model_index = (int)h->models.size() - 1;
+    return PCM_OK;
+}
+
+extern "C" int pcm_set_novelty(pcm_handle* h, int model_index, const double* mean, const double* component,
+                               int n_features) {
+    if (!h || !mean || !component) return fail(PCM_E_INVALID, "pcm_set_novelty: NULL argument");
+    if (model_index < 0 || model_index >= (int)h->models.size())
+        return fail(PCM_E_INVALID, "pcm_set_novelty: model %d does not exist", model_index);
+    if (n_features != h->geom.F) return fail(PCM_E_INVALID, "pcm_set_novelty: n_features %d != F %d", n_features, h->geom.F);
+    CUDA_TRY(cudaSetDevice(h->device));
+    Model& m = h->models[model_index];
+    const int F = h->geom.F;
+    std::vector<double> buf(3 * (size_t)F);
+    double mdc = 0.0;
+    for (int f = 0; f < F; ++f) {
+        buf[f] = component[f];
+        buf[F + f] = component[f] / 255.0;
+        buf[2 * F + f] = mean[f];
+        mdc += mean[f] * component[f];
+    }
+    if (!m.d_pca) CUDA_TRY(cudaMalloc(&m.d_pca, buf.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(m.d_pca, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    m.pca.comp = static_cast<const double*>(m.d_pca);
+    m.pca.comp255 = m.pca.comp + F;
+    m.pca.mean = m.pca.comp + 2 * F;
+    m.pca.mean_dot_comp = mdc;
+    m.has_pca = true;
+    return PCM_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// API: per-frame hot path
+// ---------------------------------------------------------------------------------
+extern "C" int pcm_crop_rect(const int bbox[4], int H, int W, int rect_out[4]) {
+    if (!bbox || !rect_out) return fail(PCM_E_INVALID, "pcm_crop_rect: NULL argument");
+    const int e = 20;   // enlarge_bbox, pixel_classification.py:49
+    const long long x = std::max(bbox[0] - e, 0), y = std::max(bbox[1] - e, 0);
+    const long long w = std::min((long long)bbox[0] + bbox[2] + e, (long long)W) - bbox[0] + e;
+    const long long hh = std::min((long long)bbox[1] + bbox[3] + e, (long long)H) - bbox[1] + e;
+    // numpy slice a[start:start+len] with start >= 0: a negative stop counts from the end
+    auto clamp = [](long long start, long long len, long long size, int& o0, int& o1) {
+        long long stop = start + len;
+        if (stop < 0) stop = std::max(size + stop, 0LL);
+        o0 = (int)std::min(start, size);
+        o1 = (int)std::min(std::max(stop, 0LL), size);
+        if (o1 < o0) o1 = o0;
+    };
+    int x0, x1, y0, y1;
+    clamp(x, w, W, x0, x1);
+    clamp(y, hh, H, y0, y1);
+    rect_out[0] = x0; rect_out[1] = y0; rect_out[2] = x1 - x0; rect_out[3] = y1 - y0;
+    return PCM_OK;
+}
+
+static int validate_update(pcm_handle* h, int H, int W, const int rect[4], int n_labels, const pcm_update_params* p) {
+    if (!h->features_set) return fail(PCM_E_STATE, "update: call pcm_set_features first");
+    if (!rect || !p) return fail(PCM_E_INVALID, "update: NULL argument");
+    if (H <= 0 || W <= 0) return fail(PCM_E_INVALID, "update: bad frame size %dx%d", W, H);
+    if (rect[2] <= 0 || rect[3] <= 0 || rect[0] < 0 || rect[1] < 0 || rect[0] + rect[2] > W || rect[1] + rect[3] > H)
+        return fail(PCM_E_INVALID, "update: crop rect {%d,%d,%d,%d} is empty or outside the %dx%d frame", rect[0],
+                    rect[1], rect[2], rect[3], W, H);
+    if ((long long)rect[2] * rect[3] > (1LL << 30)) return fail(PCM_E_LIMIT, "update: crop too large");
+    if (n_labels < 1) return fail(PCM_E_INVALID, "update: n_labels %d", n_labels);
+    const int M = (int)h->models.size();
+    if (p->model_cur < 0 || p->model_cur >= M) return fail(PCM_E_INVALID, "update: model_cur %d of %d", p->model_cur, M);
+    if (p->model_next >= M || p->model_next < -1) return fail(PCM_E_INVALID, "update: model_next %d of %d", p->model_next, M);
+    if (p->novelty) {
+        if (!h->models[p->model_cur].has_pca) return fail(PCM_E_STATE, "update: novelty on but model %d has no PCA", p->model_cur);
+        if (p->model_next >= 0 && !h->models[p->model_next].has_pca)
+            return fail(PCM_E_STATE, "update: novelty on but model %d has no PCA", p->model_next);
+    }
+    if (p->dilation_kernel < 1 || p->dilation_kernel > DIL_MAXK)
+        return fail(PCM_E_LIMIT, "update: dilation_kernel %d outside [1,%d]", p->dilation_kernel, DIL_MAXK);
+    return PCM_OK;
+}
+
+// Enqueue K1..K3 for one crop.  All pointers are device pointers.
+static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, int64_t stride, const int rect[4],
+                          const int32_t* d_labels, int S, const float* d_priors, const pcm_update_params* p,
+                          uint8_t* d_mask, int64_t mask_stride, int mask_cx, int mask_cy, bool want_pre) {
+    const int cx = rect[0], cy = rect[1], cw = rect[2], ch = rect[3];
+    const size_t npx = (size_t)cw * ch;
+    cudaStream_t st = h->stream;
+    CUDA_TRY(h->p1.reserve(npx * sizeof(double)));
+    if (p->novelty) CUDA_TRY(h->sa.reserve(npx * sizeof(double)));
+    const SegLayout sl = seg_layout(S);
+    CUDA_TRY(h->seg.reserve(sl.total));
+    CUDA_TRY(h->rmin.reserve(sizeof(int) * (size_t)S));
+    CUDA_TRY(h->rmax.reserve(sizeof(int) * (size_t)S));
+    CUDA_TRY(h->decision.reserve((size_t)S));
+    CUDA_TRY(h->scores.reserve(sizeof(float) * (size_t)S));
+    CUDA_TRY(h->flagged.reserve(sizeof(int) * (size_t)S));
+    if (want_pre) CUDA_TRY(h->pre.reserve(npx));
+
+    // ---- K1 -----------------------------------------------------------------------
+    ScoreArgs a{};
+    a.frame = d_frame;
+    a.frame_lo = d_frame;
+    a.frame_hi = d_frame + (size_t)(H - 1) * stride + (size_t)W * 3;
+    a.stride = stride;
+    a.cx = cx; a.cy = cy; a.cw = cw; a.ch = ch;
+    a.tiles_x = (cw + TILE_W - 1) / TILE_W;
+    a.tiles_y = (ch + TILE_H - 1) / TILE_H;
+    a.g = h->geom;
+    a.tables = h->d_tables;
+    const Model& m0 = h->models[p->model_cur];
+    a.f0 = m0.forest;
+    a.blend = p->model_next >= 0;
+    if (a.blend) a.f1 = h->models[p->model_next].forest;
+    a.w0 = p->w_cur; a.w1 = p->w_next;
+    a.novelty = p->novelty != 0;
+    if (a.novelty) {
+        a.pca0 = m0.pca;
+        if (a.blend) a.pca1 = h->models[p->model_next].pca;
+    }
+    a.p1_out = h->p1.as<double>();
+    a.sa_out = a.novelty ? h->sa.as<double>() : nullptr;
+
+    ScoreSmem ls = score_smem_layout(a.g, a.f0, a.f1, a.blend, a.novelty, true);
+    const bool forest_smem = (int)ls.total <= h->max_smem_optin;
+    if (!forest_smem) ls = score_smem_layout(a.g, a.f0, a.f1, a.blend, a.novelty, false);
+    if ((int)ls.total > h->max_smem_optin)
+        return fail(PCM_E_LIMIT, "update: tile needs %u B of shared memory (> %d)", ls.total, h->max_smem_optin);
+    int occ = 0;
+    if (forest_smem) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, score_kernel<true>, NTHREADS, ls.total));
+    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, score_kernel<false>, NTHREADS, ls.total));
+    occ = std::max(occ, 1);
+    const int n_tiles = a.tiles_x * a.tiles_y;
+    const int grid = std::min(n_tiles, h->sm_count * occ);
+    {
+        KernelTimer kt(h, 0);
+        if (forest_smem) score_kernel<true><<<grid, NTHREADS, ls.total, st>>>(a);
+        else score_kernel<false><<<grid, NTHREADS, ls.total, st>>>(a);
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+
+    // ---- K2 / K2b / K2c --------------------------------------------------------------
+    char* seg = h->seg.as<char>();
+    CUDA_TRY(cudaMemsetAsync(seg, 0, sl.total, st));
+    CUDA_TRY(cudaMemsetAsync(h->rmin.p, 0x7f, sizeof(int) * (size_t)S, st));
+    CUDA_TRY(cudaMemsetAsync(h->rmax.p, 0xff, sizeof(int) * (size_t)S, st));
+    SegArgs sa{};
+    sa.p1 = a.p1_out;
+    sa.sa = a.sa_out;
+    sa.labels = d_labels;
+    sa.n_px = (int)npx; sa.cw = cw; sa.n_labels = S;
+    sa.thr = p->outlier_threshold;
+    sa.sum = reinterpret_cast<double*>(seg + sl.sum);
+    sa.asum = reinterpret_cast<double*>(seg + sl.asum);
+    sa.area = reinterpret_cast<int*>(seg + sl.area);
+    sa.rmin = h->rmin.as<int>();
+    sa.rmax = h->rmax.as<int>();
+    sa.err = reinterpret_cast<int*>(seg + sl.err);
+    {
+        const int blocks = (int)std::min<size_t>((npx + 255) / 256, (size_t)h->sm_count * 8);
+        {
+            KernelTimer kt(h, 1);
+            segment_reduce_kernel<<<blocks, 256, 0, st>>>(sa);
+        }
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+    }
+    DecideArgs da{};
+    da.sum = sa.sum; da.asum = sa.asum; da.area = sa.area;
+    da.priors = d_priors;
+    da.n_labels = S;
+    da.prior_weight = p->prior_weight;
+    da.decision = h->decision.as<uint8_t>();
+    da.scores = h->scores.as<float>();
+    da.flagged = h->flagged.as<int>();
+    da.n_flagged = reinterpret_cast<int*>(seg + sl.nflag);
+    {
+        KernelTimer kt(h, 2);
+        segment_decide_kernel<<<(S + 255) / 256, 256, 0, st>>>(da);
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    ResolveArgs ra{};
+    ra.p1 = sa.p1; ra.sa = sa.sa; ra.labels = d_labels; ra.cw = cw; ra.thr = sa.thr;
+    ra.area = sa.area; ra.rmin = sa.rmin; ra.rmax = sa.rmax;
+    ra.priors = d_priors; ra.prior_weight = p->prior_weight;
+    ra.flagged = da.flagged; ra.n_flagged = da.n_flagged;
+    ra.decision = da.decision; ra.scores = da.scores;
+    {
+        KernelTimer kt(h, 3);
+        segment_resolve_kernel<<<std::min(S, h->sm_count), 256, 0, st>>>(ra);
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+
+    // ---- K3 -------------------------------------------------------------------------
+    DilateArgs dl{};
+    dl.labels = d_labels;
+    dl.decision = da.decision;
+    dl.cw = cw; dl.ch = ch; dl.k = p->dilation_kernel; dl.n_labels = S;
+    dl.mask = d_mask;
+    dl.mask_stride = mask_stride;
+    dl.cx = mask_cx; dl.cy = mask_cy;
+    dl.pre = want_pre ? h->pre.as<uint8_t>() : nullptr;
+    dim3 dg((cw + DIL_TW - 1) / DIL_TW, (ch + DIL_TH - 1) / DIL_TH);
+    {
+        KernelTimer kt(h, 4);
+        mask_dilate_kernel<<<dg, 256, 0, st>>>(dl);
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+
+    h->last_cw = cw; h->last_ch = ch; h->last_S = S;
+    h->last_novelty = a.novelty;
+    h->last_valid = true;
+    return PCM_OK;
+}
+
+extern "C" int pcm_update_device(pcm_handle* h, const uint8_t* d_frame, int H, int W, int64_t stride, const int rect[4],
+                                 const int32_t* d_labels, int n_labels, const float* d_priors,
+                                 const pcm_update_params* params, uint8_t* d_mask, int64_t mask_row_stride) {
+    if (!h || !d_frame || !d_labels || !d_mask) return fail(PCM_E_INVALID, "pcm_update_device: NULL argument");
+    int rc = validate_update(h, H, W, rect, n_labels, params);
+    if (rc) return rc;
+    if (stride < (int64_t)W * 3) return fail(PCM_E_INVALID, "pcm_update_device: stride %lld < 3*W", (long long)stride);
+    CUDA_TRY(cudaSetDevice(h->device));
+    return enqueue_update(h, d_frame, H, W, stride, rect, d_labels, n_labels, d_priors, params, d_mask,
+                          mask_row_stride, rect[0], rect[1], true);
+}
+
+extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int64_t stride, const int rect[4],
+                          const int32_t* labels, int n_labels, const float* priors, const pcm_update_params* params,
+                          uint8_t* mask, int64_t mask_row_stride, int64_t mask_pixel_stride) {
+    if (!h || !frame || !labels || !mask) return fail(PCM_E_INVALID, "pcm_update: NULL argument");
+    int rc = validate_update(h, H, W, rect, n_labels, params);
+    if (rc) return rc;
+    if (stride < (int64_t)W * 3) return fail(PCM_E_INVALID, "pcm_update: stride %lld < 3*W", (long long)stride);
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int cx = rect[0], cy = rect[1], cw = rect[2], ch = rect[3];
+    const size_t npx = (size_t)cw * ch, row_bytes = (size_t)cw * 3;
+    cudaStream_t st = h->stream;
+    // host -> pinned -> device: only the crop travels
+    CUDA_TRY(h->h_frame.reserve(npx * 3));
+    CUDA_TRY(h->frame.reserve(npx * 3));
+    CUDA_TRY(h->h_labels.reserve(npx * sizeof(int32_t)));
+    CUDA_TRY(h->labels.reserve(npx * sizeof(int32_t)));
+    CUDA_TRY(h->h_mask.reserve(npx));
+    CUDA_TRY(h->mask.reserve(npx));
+    CUDA_TRY(h->h_small.reserve(64));
+    CUDA_TRY(cudaStreamSynchronize(st));   // staging buffers are reused between calls
+    uint8_t* hf = h->h_frame.as<uint8_t>();
+    for (int r = 0; r < ch; ++r)
+        memcpy(hf + (size_t)r * row_bytes, frame + (size_t)(cy + r) * stride + (size_t)cx * 3, row_bytes);
+    CUDA_TRY(cudaMemcpyAsync(h->frame.p, hf, npx * 3, cudaMemcpyHostToDevice, st));
+    memcpy(h->h_labels.p, labels, npx * sizeof(int32_t));
+    CUDA_TRY(cudaMemcpyAsync(h->labels.p, h->h_labels.p, npx * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    const float* d_priors = nullptr;
+    if (priors) {
+        CUDA_TRY(h->h_priors.reserve(sizeof(float) * (size_t)n_labels));
+        CUDA_TRY(h->priors.reserve(sizeof(float) * (size_t)n_labels));
+        memcpy(h->h_priors.p, priors, sizeof(float) * (size_t)n_labels);
+        CUDA_TRY(cudaMemcpyAsync(h->priors.p, h->h_priors.p, sizeof(float) * (size_t)n_labels, cudaMemcpyHostToDevice, st));
+        d_priors = h->priors.as<float>();
+    }
+    const int crop_rect[4] = {0, 0, cw, ch};
+    rc = enqueue_update(h, h->frame.as<uint8_t>(), ch, cw, (int64_t)row_bytes, crop_rect, h->labels.as<int32_t>(),
+                        n_labels, d_priors, params, h->mask.as<uint8_t>(), cw, 0, 0, true);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->h_mask.p, h->mask.p, npx, cudaMemcpyDeviceToHost, st));
+    rc = check_label_error(h, true);
+    if (rc) return rc;
+    // scatter the dense crop into the caller's (possibly interleaved) mask
+    const uint8_t* hm = h->h_mask.as<uint8_t>();
+    for (int r = 0; r < ch; ++r) {
+        uint8_t* dst = mask + (size_t)(cy + r) * mask_row_stride + (size_t)cx * mask_pixel_stride;
+        const uint8_t* src = hm + (size_t)r * cw;
+        if (mask_pixel_stride == 1) memcpy(dst, src, cw);
+        else
+            for (int c = 0; c < cw; ++c) dst[(size_t)c * mask_pixel_stride] = src[c];
+    }
+    return PCM_OK;
+}
+
+extern "C" int pcm_iou_device(pcm_handle* h, const uint8_t* d_mask, int64_t mask_row_stride, const uint8_t* d_truth,
+                              int64_t truth_row_stride, int truth_channels, int height, int width, int64_t* d_counts) {
+    if (!h || !d_mask || !d_truth || !d_counts) return fail(PCM_E_INVALID, "pcm_iou_device: NULL argument");
+    if (truth_channels != 1 && truth_channels != 3) return fail(PCM_E_INVALID, "pcm_iou_device: truth_channels %d", truth_channels);
+    if (height <= 0 || width <= 0) return fail(PCM_E_INVALID, "pcm_iou_device: bad size");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const long long chunks = (long long)height * ((width + 31) / 32);
+    const int blocks = (int)std::min<long long>((chunks + 7) / 8, (long long)h->sm_count * 8);
+    {
+        KernelTimer kt(h, 5);
+        iou_kernel<<<std::max(blocks, 1), 256, 0, h->stream>>>(d_mask, mask_row_stride, d_truth, truth_row_stride,
+                                                              truth_channels, height, width,
+                                                              reinterpret_cast<unsigned long long*>(d_counts));
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return PCM_OK;
+}
+
+extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stride, int64_t mask_pixel_stride,
+                       const uint8_t* truth, int64_t truth_row_stride, int truth_channels, int height, int width,
+                       int64_t counts[2]) {
+    if (!h || !mask || !truth || !counts) return fail(PCM_E_INVALID, "pcm_iou: NULL argument");
+    if (truth_channels != 1 && truth_channels != 3) return fail(PCM_E_INVALID, "pcm_iou: truth_channels %d", truth_channels);
+    if (height <= 0 || width <= 0) return fail(PCM_E_INVALID, "pcm_iou: bad size");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const size_t npx = (size_t)height * width, tbytes = npx * truth_channels;
+    CUDA_TRY(h->h_mask.reserve(npx));
+    CUDA_TRY(h->mask.reserve(npx));
+    CUDA_TRY(h->h_frame.reserve(tbytes));
+    CUDA_TRY(h->frame.reserve(tbytes));
+    CUDA_TRY(h->counts.reserve(2 * sizeof(int64_t)));
+    CUDA_TRY(h->h_small.reserve(64));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    uint8_t* hm = h->h_mask.as<uint8_t>();
+    for (int r = 0; r < height; ++r) {
+        const uint8_t* src = mask + (size_t)r * mask_row_stride;
+        uint8_t* dst = hm + (size_t)r * width;
+        if (mask_pixel_stride == 1) memcpy(dst, src, width);
+        else
+            for (int c = 0; c < width; ++c) dst[c] = src[(size_t)c * mask_pixel_stride];
+    }
+    uint8_t* ht = h->h_frame.as<uint8_t>();
+    for (int r = 0; r < height; ++r)
+        memcpy(ht + (size_t)r * width * truth_channels, truth + (size_t)r * truth_row_stride, (size_t)width * truth_channels);
+    CUDA_TRY(cudaMemcpyAsync(h->mask.p, hm, npx, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->frame.p, ht, tbytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(h->counts.p, 0, 2 * sizeof(int64_t), st));
+    int rc = pcm_iou_device(h, h->mask.as<uint8_t>(), width, h->frame.as<uint8_t>(), (int64_t)width * truth_channels,
+                            truth_channels, height, width, h->counts.as<int64_t>());
+    if (rc) return rc;
+    int64_t* hc = h->h_small.as<int64_t>() + 2;
+    CUDA_TRY(cudaMemcpyAsync(hc, h->counts.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    counts[0] = hc[0];
+    counts[1] = hc[1];
+    h->last_valid = false;   // frame / mask scratch was reused
+    return PCM_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// API: parity taps
+// ---------------------------------------------------------------------------------
+extern "C" int pcm_convert(pcm_handle* h, const uint8_t* bgr, int height, int width, int64_t stride, int space,
+                           uint8_t* out, int64_t out_stride) {
+    if (!h || !bgr || !out) return fail(PCM_E_INVALID, "pcm_convert: NULL argument");
+    if (space < 0 || space > 2) return fail(PCM_E_INVALID, "pcm_convert: bad space %d", space);
+    if (height <= 0 || width <= 0) return fail(PCM_E_INVALID, "pcm_convert: bad size");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)height * width * 3;
+    DevBuf in, o;
+    CUDA_TRY(in.reserve(bytes));
+    CUDA_TRY(o.reserve(bytes));
+    CUDA_TRY(cudaMemcpy2DAsync(in.p, (size_t)width * 3, bgr, stride, (size_t)width * 3, height, cudaMemcpyHostToDevice, h->stream));
+    const int blocks = (int)std::min<size_t>(((size_t)height * width + 255) / 256, (size_t)h->sm_count * 16);
+    convert_kernel<<<blocks, 256, 0, h->stream>>>(in.as<uint8_t>(), (long long)width * 3, height, width, space,
+                                                  h->d_tables, o.as<uint8_t>(), (long long)width * 3);
+    cudaError_t e = cudaGetLastError();
+    h->launches++;
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(out, out_stride, o.p, (size_t)width * 3, (size_t)width * 3, height, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    in.release();
+    o.release();
+    if (e != cudaSuccess) return fail(PCM_E_CUDA, "pcm_convert: %s", cudaGetErrorString(e));
+    return PCM_OK;
+}
+
+extern "C" int pcm_gather_features(pcm_handle* h, const uint8_t* frame, int H, int W, int64_t stride, const int rect[4],
+                                   int16_t* X) {
+    if (!h || !frame || !rect || !X) return fail(PCM_E_INVALID, "pcm_gather_features: NULL argument");
+    if (!h->features_set) return fail(PCM_E_STATE, "pcm_gather_features: call pcm_set_features first");
+    if (rect[2] <= 0 || rect[3] <= 0 || rect[0] < 0 || rect[1] < 0 || rect[0] + rect[2] > W || rect[1] + rect[3] > H)
+        return fail(PCM_E_INVALID, "pcm_gather_features: rect outside the frame");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int cw = rect[2], ch = rect[3];
+    const size_t npx = (size_t)cw * ch, xbytes = npx * h->geom.F * sizeof(int16_t);
+    DevBuf in, o;
+    CUDA_TRY(in.reserve(npx * 3));
+    CUDA_TRY(o.reserve(xbytes));
+    CUDA_TRY(cudaMemcpy2DAsync(in.p, (size_t)cw * 3, frame + (size_t)rect[1] * stride + (size_t)rect[0] * 3, stride,
+                               (size_t)cw * 3, ch, cudaMemcpyHostToDevice, h->stream));
+    const size_t work = npx * h->geom.K;
+    const int blocks = (int)std::min<size_t>((work + 255) / 256, (size_t)h->sm_count * 16);
+    gather_kernel<<<blocks, 256, 0, h->stream>>>(in.as<uint8_t>(), (long long)cw * 3, 0, 0, cw, ch, h->geom, h->d_tables,
+                                                 o.as<int16_t>());
+    cudaError_t e = cudaGetLastError();
+    h->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(X, o.p, xbytes, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    in.release();
+    o.release();
+    if (e != cudaSuccess) return fail(PCM_E_CUDA, "pcm_gather_features: %s", cudaGetErrorString(e));
+    return PCM_OK;
+}
+
+extern "C" int pcm_debug_last(pcm_handle* h, double* p1, double* sa, float* scores, int64_t* areas, uint8_t* pre,
+                              int32_t* n_exact) {
+    if (!h) return fail(PCM_E_INVALID, "pcm_debug_last: NULL handle");
+    if (!h->last_valid) return fail(PCM_E_STATE, "pcm_debug_last: no update to report");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const size_t npx = (size_t)h->last_cw * h->last_ch;
+    const int S = h->last_S;
+    const SegLayout sl = seg_layout(S);
+    if (p1) CUDA_TRY(cudaMemcpy(p1, h->p1.p, npx * sizeof(double), cudaMemcpyDeviceToHost));
+    if (sa) {
+        if (h->last_novelty) CUDA_TRY(cudaMemcpy(sa, h->sa.p, npx * sizeof(double), cudaMemcpyDeviceToHost));
+        else memset(sa, 0, npx * sizeof(double));
+    }
+    if (scores) CUDA_TRY(cudaMemcpy(scores, h->scores.p, sizeof(float) * (size_t)S, cudaMemcpyDeviceToHost));
+    if (areas) {
+        std::vector<int> tmp(S);
+        CUDA_TRY(cudaMemcpy(tmp.data(), h->seg.as<char>() + sl.area, sizeof(int) * (size_t)S, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < S; ++i) areas[i] = tmp[i];
+    }
+    if (pre) CUDA_TRY(cudaMemcpy(pre, h->pre.p, npx, cudaMemcpyDeviceToHost));
+    if (n_exact) {
+        int v = 0;
+        CUDA_TRY(cudaMemcpy(&v, h->seg.as<char>() + sl.nflag, sizeof(int), cudaMemcpyDeviceToHost));
+        *n_exact = v;
+    }
+    return PCM_OK;
+}
+
+extern "C" int pcm_debug_tables(pcm_handle* h, uint16_t* gamma, uint16_t* cbrt_tab, int32_t* sdiv, int32_t* hdiv) {
+    if (!h) return fail(PCM_E_INVALID, "pcm_debug_tables: NULL handle");
+    ColorTables t;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpy(&t, h->d_tables, sizeof t, cudaMemcpyDeviceToHost));
+    if (gamma) memcpy(gamma, t.gamma, sizeof t.gamma);
+    if (cbrt_tab) memcpy(cbrt_tab, t.cbrt_tab, sizeof(uint16_t) * LAB_CBRT_SIZE);
+    if (sdiv) memcpy(sdiv, t.sdiv, sizeof t.sdiv);
+    if (hdiv) memcpy(hdiv, t.hdiv, sizeof t.hdiv);
+    return PCM_OK;
+}
+
+extern "C" int64_t pcm_launch_count(const pcm_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int pcm_profile_enable(pcm_handle* h, int on) {
+    if (!h) return fail(PCM_E_INVALID, "pcm_profile_enable: NULL handle");
+    h->profiling = on != 0;
+    return PCM_OK;
+}
+
+extern "C" int pcm_profile_read(pcm_handle* h, double* ms_sum, int64_t* count, int n, int reset) {
+    if (!h) return fail(PCM_E_INVALID, "pcm_profile_read: NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (auto& t : h->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { h->prof_ms[t.id] += ms; h->prof_n[t.id]++; }
+        h->free_events.push_back(t.a);
+        h->free_events.push_back(t.b);
+    }
+    h->pending.clear();
+    for (int i = 0; i < n && i < PCM_NUM_KERNELS; ++i) {
+        if (ms_sum) ms_sum[i] = h->prof_ms[i];
+        if (count) count[i] = h->prof_n[i];
+    }
+    if (reset)
+        for (int i = 0; i < PCM_NUM_KERNELS; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+    return PCM_OK;
+}

@@ -1,0 +1,124 @@
+"""B200-native PixelClassification masker behind the reference's plugin API.
+
+Interface and state machine follow the reference class
+PixelClassificationNonRigidMasker (maskers/pixel_classification.py:24-228):
+same constructor keywords, `addModel(...) -> bbox_roni`, `update(bbox, frame,
+mask, color) -> None | model index`, same public attributes (`index`, `models`,
+`novelty_det`, `current_model`, `prevFrame`, `prevForegroundMask`).
+
+What differs is where the per-frame work runs: colour conversion, star-tap
+features, forest scoring, PCA novelty error, temporal blend, per-superpixel
+decision and dilation are CUDA kernels in libpcm_b200.so, reached through the C
+ABI of include/pcm_b200.h (pcm/capi.py).  There is no CPU fallback for that path.
+Training (`addModel`) stays with scikit-learn on the host, as in the reference;
+its feature rows come from the same device code (pcm_gather_features).
+"""
+import copy
+
+import cv2 as cv
+import numpy as np
+from sklearn.decomposition import PCA
+from sklearn.ensemble import RandomForestClassifier
+from sklearn.metrics import f1_score
+
+from pcm import capi
+from pcm.providers import make_segment_provider
+from pcm.priors import SiftPrior
+from .masker import Masker
+
+
+class PixelClassificationNonRigidMasker(Masker):
+    def __init__(self, poly_roi=None, update_mask=None, segment_fn=None, prior_fn=None, device=0, **args):
+        Masker.__init__(self, **args)
+        self.poly_roi = copy.deepcopy(poly_roi)
+        self.index = 0
+        self.models = []
+        self.novelty_det = []
+        self.current_model = 0
+        self.multi_selection = self.config.get("multi_selection")
+
+        params = self.config["params"]
+        tokens = params["features"].split()
+        self.n_neighbors = int(tokens[0])
+        self.spaces = tokens[1].split("_")
+        self.native = capi.Handle(device)
+        self.native.set_features(self.n_neighbors, self.spaces)
+        # providers for the two stages that are not part of the hot path
+        self.segment_fn = segment_fn or make_segment_provider(params["over_segmentation"])
+        self.prior_fn = prior_fn or SiftPrior()
+        self.prevForegroundMask = None
+
+    # -- training (reference :166-228) -------------------------------------------
+    def _rows(self, frame, rect):
+        """Feature rows of a rectangle as float64 X/255 (reference :54-55, :192-196)."""
+        return self.native.gather_features(frame, rect).astype(np.float64) / 255
+
+    def addModel(self, frame, poly_roi, bbox, n_frame, bbox_roni=None, show_prob_map=False):
+        if bbox_roni is None:
+            raise ValueError("bbox_roni is required (the reference opens a GUI selector here, :287)")
+        x, y, w, h = [int(v) for v in bbox]
+        roi = np.zeros((h, w), np.uint8)
+        cv.fillPoly(roi, np.array([[(p[0] - x, p[1] - y) for p in poly_roi]], dtype=np.int32), 255)
+        X = self._rows(frame, (x, y, w, h))
+        labels = (roi.reshape(-1) > 0).astype(np.int64)
+        Xn = self._rows(frame, tuple(int(v) for v in bbox_roni))
+        X = np.concatenate([X, Xn], axis=0)
+        labels = np.concatenate([labels, np.zeros(len(Xn), np.int64)])
+
+        params = self.config["params"]
+        clf = RandomForestClassifier(random_state=42, n_estimators=params["n_estimators"],
+                                     max_depth=params["max_depth"]).fit(X, labels)
+        print("F1 score classifier for frame {}= {}".format(n_frame, round(f1_score(labels, clf.predict(X)), 2)))
+        if params["novelty_detection"]:
+            pca = PCA(n_components=params["n_components"]).fit(X[labels == 1])
+            if pca.components_.shape[0] != 1:
+                raise ValueError("the native novelty path supports n_components == 1 (config.yaml:27)")
+            residual = np.sum(np.sqrt(np.power(X - pca.inverse_transform(pca.transform(X)), 2)), axis=1)
+            threshold = np.percentile(residual, 90)
+        else:
+            pca, threshold = None, 0.0
+
+        m = self.native.add_forest(n_frame, clf)
+        if pca is not None:
+            self.native.set_novelty(m, pca.mean_, pca.components_[0])
+        self.models.append({"n_frame": n_frame, "model": clf})
+        self.novelty_det.append({"n_frame": n_frame, "model": pca, "threshold": threshold})
+        return bbox_roni
+
+    # -- per-frame hot path (reference :45-126) --------------------------------------
+    def update(self, bbox, frame, mask, color=None):
+        x, y, w, h = capi.crop_rect(bbox, frame.shape[0], frame.shape[1])
+        if w <= 0 or h <= 0:
+            raise ValueError("empty crop for bbox %r" % (bbox,))
+        ys, xs = slice(y, y + h), slice(x, x + w)
+        crop = frame[ys, xs]
+        params = self.config["params"]
+        cur = self.current_model
+
+        segments = np.ascontiguousarray(self.segment_fn(crop), np.int32)
+        n_labels = int(segments.max()) + 1
+        priors = None
+        if self.index != 0 and params["prior_weight"] != 0.0:
+            priors = self.prior_fn(self.prevFrame, self.prevForegroundMask, crop, segments, n_labels)
+
+        blend = bool(self.multi_selection) and len(self.models) > cur + 1
+        w_cur, w_next = 1.0, 0.0
+        if blend:
+            span = self.models[cur + 1]["n_frame"] - self.models[cur]["n_frame"]
+            tmp = self.index - self.models[cur]["n_frame"]
+            w_cur, w_next = 1 - (tmp / span), tmp / span
+        p = capi.Handle.make_params(cur, cur + 1 if blend else -1, w_cur, w_next,
+                                    novelty=params["novelty_detection"],
+                                    dilation_kernel=params["dilation_kernel"],
+                                    outlier_threshold=self.novelty_det[cur]["threshold"],
+                                    prior_weight=params["prior_weight"])
+        self.native.update(frame, (x, y, w, h), segments, n_labels, priors, p, mask, channel=2)
+
+        self.index += 1
+        self.prevFrame = crop
+        self.prevForegroundMask = mask[ys, xs, 2]
+        if blend and self.index >= self.models[cur + 1]["n_frame"]:
+            self.current_model += 1
+            print("\n \n CHANGE OF MODEL \n \n")
+            return self.current_model   # tells the caller to re-initialise the tracker
+        return None

@@ -1,0 +1,282 @@
+"""ctypes binding of libpcm_b200.so (include/pcm_b200.h) -- the same pattern the
+reference uses for its own native component (prim/__init__.py:7-38).
+
+There is no CPU fallback: if the library or a CUDA device is missing, creating a
+`Handle` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+SPACE_IDS = {"rgb": 0, "hsv": 1, "lab": 2}
+
+_lib = None
+
+
+class PcmError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "pcm_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class UpdateParams(C.Structure):
+    _fields_ = [("model_cur", C.c_int32), ("model_next", C.c_int32),
+                ("w_cur", C.c_double), ("w_next", C.c_double),
+                ("novelty", C.c_int32), ("dilation_kernel", C.c_int32),
+                ("outlier_threshold", C.c_double), ("prior_weight", C.c_double)]
+
+
+def library_path():
+    return _build.LIB
+
+
+def load_library():
+    """dlopen the in-tree library (building it first if nvcc is available and the
+    sources are newer).  Raises if it cannot be loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _build.needs_build():
+        _build.build()
+    lib = C.CDLL(_build.LIB)
+    P, I, L, D = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    sig = {
+        "pcm_abi_version": (I, []),
+        "pcm_last_error": (C.c_char_p, []),
+        "pcm_create": (I, [I, C.POINTER(P)]),
+        "pcm_destroy": (None, [P]),
+        "pcm_set_stream": (I, [P, P]),
+        "pcm_synchronize": (I, [P]),
+        "pcm_set_features": (I, [P, I, I, P]),
+        "pcm_num_features": (I, [P]),
+        "pcm_add_model": (I, [P, I, I, P, P, P, P, P, P, C.POINTER(I)]),
+        "pcm_set_novelty": (I, [P, I, P, P, I]),
+        "pcm_num_models": (I, [P]),
+        "pcm_crop_rect": (I, [P, I, I, P]),
+        "pcm_update": (I, [P, P, I, I, L, P, P, I, P, C.POINTER(UpdateParams), P, L, L]),
+        "pcm_update_device": (I, [P, P, I, I, L, P, P, I, P, C.POINTER(UpdateParams), P, L]),
+        "pcm_iou": (I, [P, P, L, L, P, L, I, I, I, P]),
+        "pcm_iou_device": (I, [P, P, L, P, L, I, I, I, P]),
+        "pcm_convert": (I, [P, P, I, I, L, I, P, L]),
+        "pcm_gather_features": (I, [P, P, I, I, L, P, P]),
+        "pcm_debug_last": (I, [P, P, P, P, P, P, P]),
+        "pcm_debug_tables": (I, [P, P, P, P, P]),
+        "pcm_launch_count": (L, [P]),
+        "pcm_profile_enable": (I, [P, I]),
+        "pcm_profile_read": (I, [P, P, P, I, I]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pcm_abi_version() != 1:
+        raise RuntimeError("libpcm_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_synchronize",
+    "pcm_set_features", "pcm_num_features", "pcm_add_model", "pcm_set_novelty", "pcm_num_models", "pcm_crop_rect",
+    "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_convert", "pcm_gather_features",
+    "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_profile_enable", "pcm_profile_read",
+]
+
+KERNEL_NAMES = ["score", "segment_reduce", "segment_decide", "segment_resolve", "mask_dilate", "iou"]
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def crop_rect(bbox, frame_h, frame_w):
+    """(x, y, w, h) of the crop the reference slices (pixel_classification.py:49-51)."""
+    lib = load_library()
+    b = (C.c_int * 4)(*[int(v) for v in bbox])
+    out = (C.c_int * 4)()
+    rc = lib.pcm_crop_rect(b, int(frame_h), int(frame_w), out)
+    if rc:
+        raise PcmError(rc, lib.pcm_last_error().decode())
+    return tuple(out)
+
+
+class Handle:
+    """One native masker context (one per tracked target)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        self._check(self.lib.pcm_create(int(device), C.byref(self._h)))
+        self.device = device
+
+    def _check(self, rc):
+        if rc:
+            raise PcmError(rc, self.lib.pcm_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.pcm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration ------------------------------------------------------
+    def set_features(self, n_neighbors, spaces):
+        ids = (C.c_int * len(spaces))(*[SPACE_IDS[s] for s in spaces])
+        self._check(self.lib.pcm_set_features(self._h, int(n_neighbors), len(spaces), ids))
+
+    @property
+    def num_features(self):
+        return self.lib.pcm_num_features(self._h)
+
+    @property
+    def num_models(self):
+        return self.lib.pcm_num_models(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.pcm_launch_count(self._h))
+
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.pcm_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def synchronize(self):
+        self._check(self.lib.pcm_synchronize(self._h))
+
+    def add_model_arrays(self, n_frame, tree_arrays):
+        """tree_arrays: list of (feature, threshold_f64, left, right, value1) per tree."""
+        offs = np.cumsum([0] + [len(t[0]) for t in tree_arrays]).astype(np.int64)
+        feature = np.ascontiguousarray(np.concatenate([t[0] for t in tree_arrays]), np.int32)
+        thr = np.ascontiguousarray(np.concatenate([t[1] for t in tree_arrays]), np.float64)
+        left = np.ascontiguousarray(np.concatenate([t[2] for t in tree_arrays]), np.int32)
+        right = np.ascontiguousarray(np.concatenate([t[3] for t in tree_arrays]), np.int32)
+        val = np.ascontiguousarray(np.concatenate([t[4] for t in tree_arrays]), np.float64)
+        idx = C.c_int(-1)
+        self._check(self.lib.pcm_add_model(self._h, int(n_frame), len(tree_arrays), _ptr(offs), _ptr(feature),
+                                           _ptr(thr), _ptr(left), _ptr(right), _ptr(val), C.byref(idx)))
+        return idx.value
+
+    def add_forest(self, n_frame, clf):
+        """Export a fitted sklearn RandomForestClassifier (binary, classes {0,1})."""
+        if list(clf.classes_) != [0, 1]:
+            raise ValueError("forest must be a binary {0,1} classifier (the reference indexes probs[:,1])")
+        arrays = []
+        for est in clf.estimators_:
+            t = est.tree_
+            arrays.append((t.feature, t.threshold, t.children_left, t.children_right, t.value[:, 0, 1]))
+        return self.add_model_arrays(n_frame, arrays)
+
+    def set_novelty(self, model_index, mean, component):
+        mean = np.ascontiguousarray(mean, np.float64).reshape(-1)
+        comp = np.ascontiguousarray(component, np.float64).reshape(-1)
+        self._check(self.lib.pcm_set_novelty(self._h, int(model_index), _ptr(mean), _ptr(comp), len(mean)))
+
+    # -- hot path -------------------------------------------------------------
+    @staticmethod
+    def make_params(model_cur, model_next=-1, w_cur=1.0, w_next=0.0, novelty=False, dilation_kernel=7,
+                    outlier_threshold=0.0, prior_weight=0.0):
+        return UpdateParams(int(model_cur), int(model_next), float(w_cur), float(w_next), int(bool(novelty)),
+                            int(dilation_kernel), float(outlier_threshold), float(prior_weight))
+
+    def update(self, frame, rect, labels, n_labels, priors, params, mask, channel=2):
+        """Host-buffer update: writes channel `channel` of `mask` (HxWxC u8) inside `rect`."""
+        if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3 or frame.strides[2] != 1 \
+                or frame.strides[1] != 3:
+            frame = np.ascontiguousarray(frame, np.uint8)
+        if mask.dtype != np.uint8 or mask.strides[-1] != 1 and mask.ndim == 3:
+            raise ValueError("mask must be a uint8 array with unit channel stride")
+        labels = np.ascontiguousarray(labels, np.int32)
+        if labels.size != rect[2] * rect[3]:
+            raise ValueError("labels has %d elements, crop has %d" % (labels.size, rect[2] * rect[3]))
+        pr = None if priors is None else np.ascontiguousarray(priors, np.float32)
+        if pr is not None and pr.size != n_labels:
+            raise ValueError("priors must have n_labels entries")
+        r = (C.c_int * 4)(*[int(v) for v in rect])
+        if mask.ndim == 3:
+            mptr = C.c_void_p(mask.ctypes.data + channel * mask.strides[2])
+            row, pix = mask.strides[0], mask.strides[1]
+        else:
+            mptr, row, pix = C.c_void_p(mask.ctypes.data), mask.strides[0], mask.strides[1]
+        self._check(self.lib.pcm_update(self._h, _ptr(frame), frame.shape[0], frame.shape[1], frame.strides[0], r,
+                                        _ptr(labels), int(n_labels), _ptr(pr), C.byref(params), mptr, row, pix))
+
+    def update_device(self, d_frame, frame_h, frame_w, stride, rect, d_labels, n_labels, d_priors, params, d_mask,
+                      mask_stride):
+        """Device-pointer update (integers are raw device addresses); asynchronous."""
+        r = (C.c_int * 4)(*[int(v) for v in rect])
+        self._check(self.lib.pcm_update_device(self._h, C.c_void_p(d_frame), int(frame_h), int(frame_w), int(stride), r,
+                                               C.c_void_p(d_labels), int(n_labels),
+                                               C.c_void_p(d_priors) if d_priors else None, C.byref(params),
+                                               C.c_void_p(d_mask), int(mask_stride)))
+
+    def iou_counts(self, mask, truth):
+        """(intersection, union) of mask != 0 and truth != 0; truth HxW gray or HxWx3 BGR."""
+        if mask.ndim != 2 or mask.dtype != np.uint8:
+            raise ValueError("mask must be HxW uint8")
+        tch = 1 if truth.ndim == 2 else truth.shape[2]
+        if truth.dtype != np.uint8 or truth.strides[1] != tch or (truth.ndim == 3 and truth.strides[2] != 1):
+            truth = np.ascontiguousarray(truth, np.uint8)
+        if truth.shape[:2] != mask.shape:
+            raise ValueError("mask / truth shapes differ")
+        out = np.zeros(2, np.int64)
+        self._check(self.lib.pcm_iou(self._h, C.c_void_p(mask.ctypes.data), mask.strides[0], mask.strides[1],
+                                     _ptr(truth), truth.strides[0], tch, mask.shape[0], mask.shape[1], _ptr(out)))
+        return int(out[0]), int(out[1])
+
+    def iou_device(self, d_mask, mask_stride, d_truth, truth_stride, truth_channels, h, w, d_counts):
+        self._check(self.lib.pcm_iou_device(self._h, C.c_void_p(d_mask), int(mask_stride), C.c_void_p(d_truth),
+                                            int(truth_stride), int(truth_channels), int(h), int(w),
+                                            C.c_void_p(d_counts)))
+
+    # -- parity taps ------------------------------------------------------------
+    def convert(self, bgr, space):
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        out = np.empty_like(bgr)
+        self._check(self.lib.pcm_convert(self._h, _ptr(bgr), bgr.shape[0], bgr.shape[1], bgr.strides[0],
+                                         SPACE_IDS[space], _ptr(out), out.strides[0]))
+        return out
+
+    def gather_features(self, frame, rect):
+        frame = np.ascontiguousarray(frame, np.uint8)
+        X = np.empty((rect[2] * rect[3], self.num_features), np.int16)
+        r = (C.c_int * 4)(*[int(v) for v in rect])
+        self._check(self.lib.pcm_gather_features(self._h, _ptr(frame), frame.shape[0], frame.shape[1],
+                                                 frame.strides[0], r, _ptr(X)))
+        return X
+
+    def debug_last(self, crop_h, crop_w, n_labels):
+        n = crop_h * crop_w
+        p1 = np.empty(n, np.float64)
+        sa = np.empty(n, np.float64)
+        scores = np.empty(n_labels, np.float32)
+        areas = np.empty(n_labels, np.int64)
+        pre = np.empty((crop_h, crop_w), np.uint8)
+        nx = C.c_int32(0)
+        self._check(self.lib.pcm_debug_last(self._h, _ptr(p1), _ptr(sa), _ptr(scores), _ptr(areas), _ptr(pre),
+                                            C.byref(nx)))
+        return dict(p1=p1, sa=sa, scores=scores, areas=areas, pre=pre, n_exact=nx.value)
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.pcm_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self, reset=False):
+        """{kernel name: (total ms, launches)} measured with CUDA events on the handle's stream."""
+        ms = np.zeros(len(KERNEL_NAMES), np.float64)
+        cnt = np.zeros(len(KERNEL_NAMES), np.int64)
+        self._check(self.lib.pcm_profile_read(self._h, _ptr(ms), _ptr(cnt), len(KERNEL_NAMES), int(bool(reset))))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNEL_NAMES)}
+
+    def tables(self):
+        gamma = np.empty(256, np.uint16)
+        cb = np.empty(2041, np.uint16)
+        sdiv = np.empty(256, np.int32)
+        hdiv = np.empty(256, np.int32)
+        self._check(self.lib.pcm_debug_tables(self._h, _ptr(gamma), _ptr(cb), _ptr(sdiv), _ptr(hdiv)))
+        return gamma, cb, sdiv, hdiv

@@ -188,6 +188,23 @@ def get_features_int(frames, n):
     return X.reshape(h * w, -1)
 
 
+def features_at(frames, n, rows, cols):
+    """Rows of get_features_int for selected pixels only (large frames)."""
+    h, w = frames[0].shape[:2]
+    rows = np.asarray(rows)
+    cols = np.asarray(cols)
+    taps = star_taps(n)
+    K = len(taps)
+    X = np.full((len(rows), len(frames) * K * 3), -1, np.int16)
+    for q, fr in enumerate(frames):
+        for k, (dr, dc) in enumerate(taps):
+            r, c = rows + dr, cols + dc
+            ok = (r >= 0) & (r < h) & (c >= 0) & (c < w)
+            col = q * K * 3 + k * 3
+            X[ok, col:col + 3] = fr[r[ok], c[ok], :]
+    return X
+
+
 # --------------------------------------------------------------------------
 # forest scoring (reference: pixel_classification.py:80-95 -> sklearn
 # RandomForestClassifier.predict_proba; SURVEY §8 a-5)
@@ -312,6 +329,18 @@ def saliency_scores(p1, sa, segments, outlier_threshold, priors, prior_weight):
     with np.errstate(divide="ignore", invalid="ignore"):
         s = (acc.astype(np.float64) / areas) * (1 - w) + priors.astype(np.float32).astype(np.float64) * w
     return s.astype(np.float32), areas
+
+
+def saliency_scores_fast(p1, segments):
+    """float64 per-label means (novelty off, no prior): NOT the reference's float32
+    accumulation -- only for large-size property tests, which exclude labels whose
+    score is within 1e-4 of 0.5."""
+    seg = segments.reshape(-1)
+    S = int(seg.max()) + 1
+    areas = np.bincount(seg, minlength=S)
+    sums = np.bincount(seg, weights=p1, minlength=S)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (sums / areas).astype(np.float32), areas
 
 
 def saliency_mask(scores, segments):

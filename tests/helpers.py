@@ -87,3 +87,20 @@ def polygons():
     import yaml
     with open(os.path.join(PKG, "polygons.yaml")) as f:
         return yaml.full_load(f)
+
+
+def native_masker_from_golden(g, device=0, **kw):
+    """The product masker with its models injected from the golden tree arrays
+    (no sklearn fitting): isolates the per-frame hot path."""
+    from maskers import getMaskerByName
+    from pcm.providers import make_segment_provider
+    m = getMaskerByName("PC", debug=False, frame=g.frames[0], config=g.config, poly_roi=None, update_mask=False,
+                        segment_fn=make_segment_provider(g.meta["segments"]), device=device, **kw)
+    for s in range(g.n_models):
+        idx = m.native.add_model_arrays(g.model_frames()[s], g.tree_arrays(s))
+        pca = g.pca(s)
+        if pca is not None:
+            m.native.set_novelty(idx, pca[0], pca[1][0])
+        m.models.append({"n_frame": g.model_frames()[s], "model": None})
+        m.novelty_det.append({"n_frame": g.model_frames()[s], "model": None, "threshold": g.novelty_threshold(s)})
+    return m

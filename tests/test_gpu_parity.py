@@ -1,0 +1,315 @@
+"""Parity of the CUDA path (through the C ABI, libpcm_b200.so) against the oracle
+and the golden vectors of the unmodified reference.  Needs a GPU: `pytest -m gpu`.
+
+Bars: integer / byte / label work bit-exact; P(fg) float64 bit-exact; novelty
+error within 1e-5 relative (north_star tolerance); masks identical except labels
+whose score is within that tolerance of 0.5 (none occur in these cases unless
+stated)."""
+import os
+
+import cv2 as cv
+import numpy as np
+import pytest
+
+import pcm_oracle as orc
+from helpers import GOLDEN, SEQ_NAMES, GoldenSeq, native_masker_from_golden, polygons, sha1
+
+pytestmark = pytest.mark.gpu
+
+NOVELTY_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def handle():
+    from pcm import capi
+    h = capi.Handle(0)
+    yield h
+    h.close()
+
+
+def all_colours():
+    v = np.arange(1 << 24, dtype=np.uint32)
+    return np.stack([v & 255, (v >> 8) & 255, (v >> 16) & 255], -1).astype(np.uint8).reshape(4096, 4096, 3)
+
+
+def test_native_library_is_loaded():
+    from pcm import capi
+    lib = capi.load_library()
+    assert os.path.basename(capi.library_path()) == "libpcm_b200.so"
+    assert lib.pcm_abi_version() == 1
+
+
+def test_tables_equal_oracle(handle):
+    gamma, cb, sdiv, hdiv = handle.tables()
+    og, ocb = orc.lab_tables()
+    osd, ohd = orc.hsv_tables()
+    assert np.array_equal(gamma, og) and np.array_equal(cb, ocb)
+    assert np.array_equal(sdiv, osd) and np.array_equal(hdiv, ohd)
+
+
+@pytest.mark.parametrize("space", ["hsv", "lab"])
+def test_convert_all_colours(handle, space):
+    img = all_colours()
+    want = orc.bgr2hsv(img) if space == "hsv" else orc.bgr2lab(img)
+    got = handle.convert(img, space)
+    assert np.count_nonzero(got != want) == 0
+
+
+def test_gather_features_matches_reference_golden():
+    from pcm import capi
+    z = np.load(os.path.join(GOLDEN, "stages.npz"))
+    for ci in range(int(z["feat_n"])):
+        crop = z["feat%d_crop" % ci]
+        n, spaces = orc.parse_features(str(z["feat%d_features" % ci]))
+        h = capi.Handle(0)
+        h.set_features(n, spaces)
+        X = h.gather_features(crop, (0, 0, crop.shape[1], crop.shape[0]))
+        assert np.array_equal(X, z["feat%d_X" % ci]), ci
+        h.close()
+
+
+def test_iou_matches_reference_golden(handle):
+    z = np.load(os.path.join(GOLDEN, "stages.npz"))
+    for bi in range(int(z["iou_n"])):
+        m, t = z["iou%d_mask" % bi], z["iou%d_truth" % bi]
+        inter, union = handle.iou_counts(m, t)
+        assert (inter, union) == orc.iou_counts(m, t)
+        with np.errstate(all="ignore"):
+            got = np.float64(inter) / np.float64(union)
+        want = z["iou%d_value" % bi]
+        assert got == want or (np.isnan(got) and np.isnan(want))
+
+
+def test_iou_bgr_truth_and_strided_mask(handle):
+    rng = np.random.default_rng(5)
+    mask3 = np.zeros((123, 77, 3), np.uint8)
+    mask3[..., 2] = (rng.random((123, 77)) < 0.3) * 255
+    truth = rng.integers(0, 3, (123, 77, 3)).astype(np.uint8) * (rng.random((123, 77, 1)) < 0.5)
+    truth = truth.astype(np.uint8)
+    got = handle.iou_counts(mask3[..., 2], truth)
+    assert got == orc.iou_counts(mask3[..., 2], orc.bgr2gray(truth))
+    assert got == orc.iou_counts(mask3[..., 2], cv.cvtColor(truth, cv.COLOR_BGR2GRAY))
+
+
+@pytest.mark.parametrize("name", SEQ_NAMES)
+def test_update_sequence_matches_reference(name):
+    """Whole sequences through the plugin API: return protocol, mask bytes and IoU
+    counts per frame equal the reference's; stage dumps equal on the dumped frames."""
+    g = GoldenSeq(name)
+    if not g.frames_match():
+        pytest.skip("video decoder output differs from the one the goldens were made with")
+    m = native_masker_from_golden(g)
+    z = g.z
+    for i in range(g.meta["n_frames"]):
+        mask = np.zeros_like(g.frames[i])
+        ret = m.update(bbox=tuple(int(v) for v in z["bbox"][i]), frame=g.frames[i], mask=mask, color=(0, 0, 255))
+        assert (-1 if ret is None else ret) == int(z["ret"][i]), "return protocol, frame %d" % i
+        assert not mask[:, :, :2].any()
+        if i in g.meta["dump"]:
+            x, y, w, h = [int(v) for v in z["f%d_rect" % i]]
+            S = int(z["f%d_segments" % i].max()) + 1
+            d = m.native.debug_last(h, w, S)
+            assert np.array_equal(d["p1"], z["f%d_p1" % i]), "P(fg) must be bit-equal, frame %d" % i
+            if g.params["novelty_detection"]:
+                np.testing.assert_allclose(d["sa"], z["f%d_sa" % i].reshape(-1), rtol=NOVELTY_RTOL, atol=0)
+            assert np.array_equal(d["areas"], np.bincount(z["f%d_segments" % i].reshape(-1), minlength=S))
+            assert np.array_equal(d["pre"], z["f%d_pre" % i]), "pre-dilation map, frame %d" % i
+            assert np.array_equal(mask[y:y + h, x:x + w, 2], z["f%d_post" % i])
+        assert sha1(mask[:, :, 2]) == str(z["mask_sha1"][i]), "mask differs at frame %d" % i
+        tg = cv.cvtColor(g.truth[i], cv.COLOR_BGR2GRAY)
+        assert m.native.iou_counts(mask[:, :, 2], tg) == (int(z["inter"][i]), int(z["union"][i]))
+        assert m.native.iou_counts(mask[:, :, 2], g.truth[i]) == (int(z["inter"][i]), int(z["union"][i]))
+
+
+def test_addmodel_trains_the_reference_forest():
+    """addModel with device-gathered feature rows + sklearn reproduces the reference's trees."""
+    g = GoldenSeq("soldier_default")
+    from maskers import getMaskerByName
+    poly = polygons()[g.meta["video"]]
+    pts, ronis = poly["pts"][0], poly["bboxes_roni"][0]
+    m = getMaskerByName("PC", debug=False, frame=g.frames[0], config=g.config, poly_roi=pts[0], update_mask=False)
+    fn = g.model_frames()[0]
+    assert m.addModel(frame=g.frames[fn], poly_roi=pts[0], bbox=cv.boundingRect(np.array(pts[0])),
+                      bbox_roni=ronis[0], n_frame=fn) == ronis[0]
+    got = orc.sklearn_tree_arrays(m.models[0]["model"])
+    for a, b in zip(got, g.tree_arrays(0)):
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)
+
+
+def _random_forest_arrays(rng, n_trees, depth, F):
+    """Random complete-ish trees in sklearn array form."""
+    trees = []
+    for _ in range(n_trees):
+        feature, thr, left, right, val = [], [], [], [], []
+
+        def build(d):
+            i = len(feature)
+            feature.append(0); thr.append(0.0); left.append(-1); right.append(-1); val.append(rng.random())
+            if d < depth and rng.random() < 0.85:
+                feature[i] = int(rng.integers(0, F))
+                # thresholds between -1/255 and 1, incl. the "outside crop" split
+                thr[i] = float(rng.choice([(-0.5) / 255, (rng.integers(0, 255) + 0.5) / 255]))
+                left[i] = build(d + 1)
+                right[i] = build(d + 1)
+            return i
+        build(0)
+        trees.append((np.array(feature, np.int32), np.array(thr), np.array(left, np.int32),
+                      np.array(right, np.int32), np.array(val)))
+    return trees
+
+
+@pytest.mark.parametrize("features,shape", [("8 hsv_lab", (150, 211)), ("6 lab", (33, 70)), ("2 rgb", (5, 3)),
+                                            ("3 rgb_hsv_lab", (64, 64)), ("16 hsv", (40, 90))])
+def test_random_forests_bit_exact(features, shape):
+    """Synthetic forests with many 'outside the crop' splits (threshold -1) on random
+    crops inside a larger frame: P(fg) bit-equal to the oracle's integer traversal."""
+    from pcm import capi
+    rng = np.random.default_rng(hash(features) % 1000)
+    n, spaces = orc.parse_features(features)
+    F = 3 * (1 + 8 * n) * len(spaces)
+    frame = rng.integers(0, 256, (shape[0] + 30, shape[1] + 41, 3), dtype=np.uint8)
+    rect = (17, 9, shape[1], shape[0])
+    crop = frame[rect[1]:rect[1] + rect[3], rect[0]:rect[0] + rect[2]]
+    trees0 = _random_forest_arrays(rng, 7, 6, F)
+    trees1 = _random_forest_arrays(rng, 5, 9, F)
+    h = capi.Handle(0)
+    h.set_features(n, spaces)
+    h.add_model_arrays(0, trees0)
+    h.add_model_arrays(10, trees1)
+    X = orc.get_features_int(orc.build_planes(crop, spaces), n)
+    p0 = orc.forest_p1(orc.forest_from_arrays(trees0, F), X)
+    p1 = orc.forest_p1(orc.forest_from_arrays(trees1, F), X)
+    labels = np.zeros(shape, np.int32)
+    mask = np.zeros(frame.shape, np.uint8)
+    for (cur, nxt, w0, w1, want) in [(0, -1, 1.0, 0.0, p0), (1, -1, 1.0, 0.0, p1),
+                                      (0, 1, 0.7, 0.3, orc.blend(p0, p1, 0.3)),
+                                      (0, 1, 1 - 0.9, 0.9, (p0 * (1 - 0.9) + p1 * 0.9) / ((1 - 0.9) + 0.9))]:
+        prm = capi.Handle.make_params(cur, nxt, w0, w1)
+        h.update(frame, rect, labels, 1, None, prm, mask)
+        d = h.debug_last(shape[0], shape[1], 1)
+        assert np.array_equal(d["p1"], want), (features, cur, nxt)
+    h.close()
+
+
+def test_guard_band_labels_take_exact_path():
+    """Labels whose score sits on the 0.5 boundary are re-evaluated with the
+    reference's sequential float32 accumulation; the mask equals the oracle's."""
+    from pcm import capi
+    rng = np.random.default_rng(11)
+    hgt, wid = 96, 160
+    frame = rng.integers(0, 256, (hgt, wid, 3), dtype=np.uint8)
+    n, spaces = 2, ["rgb"]
+    F = 3 * 17
+    # one stump on the centre pixel's blue channel: leaf values straddle 0.5 by ~1e-8
+    lo, hi = 0.5 - 3e-9, 0.5 + 3e-9
+    trees = [(np.array([0, -2, -2], np.int32), np.array([127.5 / 255, -2.0, -2.0]),
+              np.array([1, -1, -1], np.int32), np.array([2, -1, -1], np.int32), np.array([0.5, lo, hi]))]
+    h = capi.Handle(0)
+    h.set_features(n, spaces)
+    h.add_model_arrays(0, trees)
+    from pcm.providers import voronoi_segments
+    seg = voronoi_segments(frame, 60, seed=3)
+    S = int(seg.max()) + 1
+    mask = np.zeros((hgt, wid, 3), np.uint8)
+    rect = (0, 0, wid, hgt)
+    prm = capi.Handle.make_params(0, dilation_kernel=1)
+    h.update(frame, rect, seg, S, None, prm, mask)
+    d = h.debug_last(hgt, wid, S)
+    X = orc.get_features_int([frame], n)
+    p1 = orc.forest_p1(orc.forest_from_arrays(trees, F), X)
+    assert np.array_equal(d["p1"], p1)
+    scores, areas = orc.saliency_scores(p1, np.zeros(hgt * wid), seg, 0.0, np.full(S, -1, np.float32), 0.0)
+    assert d["n_exact"] == S, "every label is inside the guard band here"
+    assert np.array_equal(d["scores"], scores)
+    assert np.array_equal(mask[..., 2], orc.saliency_mask(scores, seg))
+    h.close()
+
+
+def test_priors_and_prior_weight():
+    from pcm import capi
+    rng = np.random.default_rng(12)
+    hgt, wid = 70, 90
+    frame = rng.integers(0, 256, (hgt, wid, 3), dtype=np.uint8)
+    F = 3 * 9
+    trees = _random_forest_arrays(rng, 6, 4, F)
+    h = capi.Handle(0)
+    h.set_features(1, ["rgb"])
+    h.add_model_arrays(0, trees)
+    from pcm.providers import grid_segments
+    seg = grid_segments(frame, 6)
+    S = int(seg.max()) + 1
+    priors = rng.choice(np.array([-1, 1], np.float32), S)
+    mask = np.zeros((hgt, wid, 3), np.uint8)
+    prm = capi.Handle.make_params(0, dilation_kernel=3, prior_weight=0.1)
+    h.update(frame, (0, 0, wid, hgt), seg, S, priors, prm, mask)
+    p1 = orc.forest_p1(orc.forest_from_arrays(trees, F), orc.get_features_int([frame], 1))
+    scores, _ = orc.saliency_scores(p1, np.zeros(hgt * wid), seg, 0.0, priors, 0.1)
+    assert np.array_equal(mask[..., 2], orc.dilate(orc.saliency_mask(scores, seg), 3))
+    h.close()
+
+
+def test_label_out_of_range_is_an_error():
+    from pcm import capi
+    rng = np.random.default_rng(2)
+    frame = rng.integers(0, 256, (40, 40, 3), dtype=np.uint8)
+    h = capi.Handle(0)
+    h.set_features(1, ["rgb"])
+    h.add_model_arrays(0, _random_forest_arrays(rng, 2, 2, 27))
+    seg = np.zeros((40, 40), np.int32)
+    seg[3, 4] = 7
+    with pytest.raises(capi.PcmError):
+        h.update(frame, (0, 0, 40, 40), seg, 2, None, capi.Handle.make_params(0), np.zeros((40, 40, 3), np.uint8))
+    h.close()
+
+
+def test_full_hd_frame_properties():
+    """BASELINE config[1] size (1920x1080 crop = full frame): P(fg) at 20k random
+    pixels bit-equal to the oracle, dilation / mask / IoU equal to the oracle,
+    and tiling invariance (a sub-crop away from the border reproduces the same
+    interior probabilities)."""
+    from pcm import capi
+    from pcm.synthetic import SyntheticSequence
+    from pcm.providers import grid_segments
+    rng = np.random.default_rng(21)
+    seq = SyntheticSequence(1920, 1080, 4, seed=0)
+    frame = seq.frame(1)
+    n, spaces = 8, ["hsv", "lab"]
+    F = 390
+    trees = _random_forest_arrays(rng, 20, 5, F)
+    h = capi.Handle(0)
+    h.set_features(n, spaces)
+    h.add_model_arrays(0, trees)
+    rect = capi.crop_rect((20, 20, 1880, 1040), 1080, 1920)
+    assert rect == (0, 0, 1920, 1080)
+    seg = grid_segments(frame, 16)
+    S = int(seg.max()) + 1
+    mask = np.zeros_like(frame)
+    h.update(frame, rect, seg, S, None, capi.Handle.make_params(0, dilation_kernel=7), mask)
+    d = h.debug_last(1080, 1920, S)
+    forest = orc.forest_from_arrays(trees, F)
+    planes = orc.build_planes(frame, spaces)
+    # random pixels, plus the four corners and edges (crop-border sentinel)
+    rr = np.concatenate([rng.integers(0, 1080, 20000), [0, 0, 1079, 1079, 5, 1075]])
+    cc = np.concatenate([rng.integers(0, 1920, 20000), [0, 1919, 0, 1919, 1915, 3]])
+    X = orc.features_at(planes, n, rr, cc)
+    assert np.array_equal(d["p1"].reshape(1080, 1920)[rr, cc], orc.forest_p1(forest, X))
+    # decision + dilation + IoU on the device's own probabilities
+    scores, areas = orc.saliency_scores_fast(d["p1"], seg)
+    near = np.abs(scores.astype(np.float64) - 0.5) < 1e-4
+    pre = orc.saliency_mask(scores, seg)
+    ok = ~near[seg]
+    assert np.array_equal(d["pre"][ok], pre[ok])
+    assert np.array_equal(mask[..., 2], orc.dilate(d["pre"], 7))
+    truth = seq.truth(1)
+    assert h.iou_counts(mask[..., 2], truth) == orc.iou_counts(mask[..., 2], truth)
+    # tiling invariance: interior of a sub-crop (>= n px from its border) is unchanged
+    sub = (333, 217, 700, 500)
+    seg2 = grid_segments(frame[sub[1]:sub[1] + sub[3], sub[0]:sub[0] + sub[2]], 16)
+    mask2 = np.zeros_like(frame)
+    h.update(frame, sub, seg2, int(seg2.max()) + 1, None, capi.Handle.make_params(0), mask2)
+    d2 = h.debug_last(sub[3], sub[2], int(seg2.max()) + 1)
+    a = d["p1"].reshape(1080, 1920)[sub[1] + n:sub[1] + sub[3] - n, sub[0] + n:sub[0] + sub[2] - n]
+    b = d2["p1"].reshape(sub[3], sub[2])[n:-n, n:-n]
+    assert np.array_equal(a, b)
+    h.close()
