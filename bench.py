@@ -189,7 +189,7 @@ def sklearn_models(seq):
 
 def run_reference(args, rank, world):
     if rank != 0:
-        return
+        return None
     from pcm.synthetic import SyntheticSequence
     seq = SyntheticSequence(WIDTH, HEIGHT, SEQ_FRAMES, seed=0)
     log("[reference] training 3 forests with the CPU port ...")
@@ -218,7 +218,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cores_available": os.cpu_count(),
     }
-    print(json.dumps(out), flush=True)
+    return out
 
 
 def workload_config():
@@ -338,7 +338,7 @@ def run_b200(args, rank, world, local_rank):
     mean_iou = float(np.mean(counts[args.warmup:, 0] / counts[args.warmup:, 1]))
 
     # ---- end to end through the plugin API with host buffers -------------------------------
-    h.set_stream(None)
+    h.use_own_stream()
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
     mask_h = np.zeros_like(frames_h[0])
 
@@ -383,6 +383,7 @@ def run_b200(args, rank, world, local_rank):
                          "frames/s by pixel count; the reference path is single-threaded" % (reps, sw, sh, tt),
                "host_cores_available": os.cpu_count()}
 
+    out = None
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -391,10 +392,10 @@ def run_b200(args, rank, world, local_rank):
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "mean_iou_vs_truth": mean_iou, "impl": "b200",
         }
-        print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    return out
 
 
 def main():
@@ -411,10 +412,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-    else:
-        run_b200(args, rank, world, local_rank)
+    # stdout carries exactly ONE JSON line; everything else (sklearn / masker prints) -> stderr
+    real_stdout = sys.stdout
+    sys.stdout = sys.stderr
+    try:
+        if args.impl == "reference":
+            out = run_reference(args, rank, world)
+        else:
+            out = run_b200(args, rank, world, local_rank)
+    finally:
+        sys.stdout = real_stdout
+    if out is not None:
+        print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":

@@ -55,9 +55,11 @@ const char* pcm_last_error(void);
 int pcm_create(int device, pcm_handle** out);
 void pcm_destroy(pcm_handle* h);
 
-/* Use an existing CUDA stream (cudaStream_t passed as void*) instead of the
- * handle's own non-blocking stream; NULL restores the own stream. */
+/* Enqueue on an existing CUDA stream (cudaStream_t passed as void*; NULL is the
+ * legacy default stream) instead of the handle's own non-blocking stream;
+ * pcm_use_own_stream switches back. */
 int pcm_set_stream(pcm_handle* h, void* cuda_stream);
+int pcm_use_own_stream(pcm_handle* h);
 int pcm_synchronize(pcm_handle* h);
 
 /* ---- configuration (config.yaml `params.features`, :300-308) ---------- */
@@ -79,7 +81,7 @@ int pcm_num_features(const pcm_handle* h);
  *   value1[i]     class-1 fraction at node i              (tree_.value[i,0,1])
  * Thresholds are collapsed to integers here (x_f32 <= thr  <=>  v <= t), so
  * scoring is bit-exact against predict_proba (:80,:82).
- * Limits: <= 32767 internal nodes and <= 32768 leaves per tree.
+ * Limit: <= 8192 nodes (internal + leaves) per tree, i.e. any tree of depth <= 12.
  * Returns the model index in *model_index. */
 int pcm_add_model(pcm_handle* h, int n_frame, int n_trees, const int64_t* tree_offsets,
                   const int32_t* feature, const double* threshold,

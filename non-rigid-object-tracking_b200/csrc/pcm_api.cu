@@ -221,9 +221,10 @@ static int int_threshold(double thr) {
 }
 
 struct EncTree {
-    std::vector<uint2> nodes;
+    std::vector<uint2> nodes;     // internal nodes, then one self-looping pseudo-node per leaf
     std::vector<double> leaves;
-    unsigned root = 0;
+    unsigned root = 0;            // byte offset of the root entry
+    int n_int = 0;
     int depth = 0;
 };
 
@@ -238,6 +239,7 @@ struct Encoder {
     std::vector<int> tint;       // integer threshold per node
     std::vector<int> node_id;    // new index of kept internal nodes, -1 otherwise
     std::vector<int> leaf_id;
+    int n_int = 0;
     EncTree out;
     std::string err;
 
@@ -247,9 +249,10 @@ struct Encoder {
         while (left[i] != -1 && tint[i] < -1) i = right[i];
         return i;
     }
+    // byte offset of the entry a child reference resolves to
     unsigned ref_of(int i) const {
         i = skip(i);
-        return left[i] == -1 ? (0x8000u | (unsigned)leaf_id[i]) : (unsigned)node_id[i];
+        return 8u * (unsigned)(left[i] == -1 ? n_int + leaf_id[i] : node_id[i]);
     }
     bool run() {
         tint.assign(n, 0);
@@ -264,7 +267,7 @@ struct Encoder {
         // iterative DFS from the root, numbering reachable kept nodes / leaves in preorder
         std::vector<std::pair<int, int>> stack;   // (node, depth = internal nodes above)
         stack.push_back({skip(0), 0});
-        int n_int = 0, n_leaf = 0, depth = 0;
+        int n_leaf = 0, depth = 0;
         std::vector<int> order;
         while (!stack.empty()) {
             auto [i, d] = stack.back();
@@ -280,11 +283,15 @@ struct Encoder {
             stack.push_back({skip(right[i]), d + 1});
             stack.push_back({skip(left[i]), d + 1});
         }
-        if (n_int > 32767 || n_leaf > 32768) { err = "tree too large (limit 32767 internal nodes / 32768 leaves)"; return false; }
-        out.nodes.assign((size_t)n_int + 1, make_uint2(0xff000000u, 0x80008000u));   // +1 pad node
+        if (n_int + n_leaf > 8192) { err = "tree too large (limit 8192 nodes incl. leaves)"; return false; }
+        out.nodes.assign((size_t)n_int + n_leaf, make_uint2(0, 0));
         out.leaves.assign(n_leaf, 0.0);
         for (int i = 0; i < n; ++i)
-            if (leaf_id[i] >= 0) out.leaves[leaf_id[i]] = value1[i];
+            if (leaf_id[i] >= 0) {
+                out.leaves[leaf_id[i]] = value1[i];
+                const unsigned self = 8u * (unsigned)(n_int + leaf_id[i]);
+                out.nodes[n_int + leaf_id[i]] = make_uint2(0xff000000u, self | (self << 16));
+            }
         const int vplane = 3 * g.n_spaces;
         for (int i : order) {
             const int f = feature[i];
@@ -299,6 +306,7 @@ struct Encoder {
             out.nodes[node_id[i]] = make_uint2(((unsigned)thr << 24) | off, ref_of(left[i]) | (ref_of(right[i]) << 16));
         }
         out.root = ref_of(0);
+        out.n_int = n_int;
         out.depth = depth;
         return true;
     }
@@ -348,7 +356,7 @@ extern "C" int pcm_create(int device, pcm_handle** out) {
 extern "C" void pcm_destroy(pcm_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->stream);
     for (auto& m : h->models) free_model(m);
     for (DevBuf* b : {&h->frame, &h->labels, &h->priors, &h->p1, &h->sa, &h->seg, &h->rmin, &h->rmax, &h->decision,
                       &h->scores, &h->flagged, &h->mask, &h->pre, &h->counts})
@@ -363,7 +371,13 @@ extern "C" void pcm_destroy(pcm_handle* h) {
 
 extern "C" int pcm_set_stream(pcm_handle* h, void* cuda_stream) {
     if (!h) return fail(PCM_E_INVALID, "pcm_set_stream: NULL handle");
-    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return PCM_OK;
+}
+
+extern "C" int pcm_use_own_stream(pcm_handle* h) {
+    if (!h) return fail(PCM_E_INVALID, "pcm_use_own_stream: NULL handle");
+    h->stream = h->own_stream;
     return PCM_OK;
 }
 
@@ -421,7 +435,9 @@ extern "C" int pcm_add_model(pcm_handle* h, int n_frame, int n_trees, const int6
         if (e <= b) return fail(PCM_E_INVALID, "pcm_add_model: tree %d is empty", t);
         Encoder enc{h->geom, feature + b, threshold + b, left + b, right + b, value1 + b, (int)(e - b)};
         if (!enc.run()) return fail(PCM_E_LIMIT, "pcm_add_model: tree %d: %s", t, enc.err.c_str());
-        trees.push_back(make_int4((int)nodes.size(), (int)leaves.size(), (int)enc.out.root, enc.out.depth));
+        // leaf value of entry offset o lives at leaves + 8*leaf_base + (o - 8*n_int)
+        trees.push_back(make_int4(8 * (int)nodes.size(), 8 * ((int)leaves.size() - enc.out.n_int), (int)enc.out.root,
+                                  enc.out.depth));
         nodes.insert(nodes.end(), enc.out.nodes.begin(), enc.out.nodes.end());
         leaves.insert(leaves.end(), enc.out.leaves.begin(), enc.out.leaves.end());
         max_depth = std::max(max_depth, enc.out.depth);

@@ -18,11 +18,15 @@ namespace pcm {
 
 // ------------------------------------------------------------------------------
 // packed forest (built on the host by encode_forest in pcm_api.cu)
+//   Every tree owns a contiguous run of 8-byte entries: its internal nodes followed
+//   by one self-looping pseudo-node per leaf, so that the traversal is branch-free
+//   and a thread that has reached a leaf simply stays there.
 //   node.x = thr << 24 | tap byte offset inside the plane tile (24 bits)
-//   node.y = left ref | right ref << 16;  ref = 0x8000 | leaf index  or  node index,
-//            both relative to the tree's base
-//   trees[t] = {node base, leaf base, root ref, depth (= max #internal nodes on a path)}
-// A tap value v (u8, 0 outside the crop) goes LEFT iff v <= thr  <=>  !((v << 24) > node.x).
+//   node.y = left | right << 16, BYTE offsets of the children from the tree's base
+//   leaf pseudo-node: x = 0xff000000 (never goes right), y = self | self << 16
+//   trees[t] = {node base (bytes), leaf-value base (bytes, biased so that
+//               value address = base + entry offset), root offset, depth}
+// A tap value v (u8, 0 outside the crop) goes RIGHT iff v > thr  <=>  (v << 24) > node.x.
 // The crop-border sentinel -1 of the reference (:263) is handled by the encoder:
 // nodes with integer threshold -1 test the validity plane instead (0 outside the crop).
 // ------------------------------------------------------------------------------
@@ -69,29 +73,30 @@ __device__ __forceinline__ uint32_t ldg_word_checked(const uint8_t* wp, const ui
 
 // One forest over the thread's PIX_PER_THREAD pixels; leaf fractions are added in
 // estimator order (sklearn ensemble/_forest.py: all_proba += prediction).
-__device__ __forceinline__ void traverse_forest(const uint2* __restrict__ nodes, const double* __restrict__ leaves,
+// Branch-free: PIX_PER_THREAD independent pointer chases are interleaved by the
+// compiler, which is what hides the two dependent shared-memory loads per visit.
+__device__ __forceinline__ void traverse_forest(const uint8_t* __restrict__ nodes, const uint8_t* __restrict__ leaves,
                                                 const int4* __restrict__ trees, int n_trees,
-                                                const uint8_t* __restrict__ pixbase, int RS, unsigned active,
+                                                const uint8_t* __restrict__ pixbase, int RS,
                                                 double (&acc)[PIX_PER_THREAD]) {
     for (int t = 0; t < n_trees; ++t) {
         const int4 ti = trees[t];
-        const uint2* nb = nodes + ti.x;
-        const double* lb = leaves + ti.y;
+        const uint8_t* nb = nodes + ti.x;
+        const uint8_t* lb = leaves + ti.y;
         unsigned ref[PIX_PER_THREAD];
 #pragma unroll
-        for (int g = 0; g < PIX_PER_THREAD; ++g) ref[g] = ((active >> g) & 1u) ? (unsigned)ti.z : 0x8000u;
+        for (int g = 0; g < PIX_PER_THREAD; ++g) ref[g] = (unsigned)ti.z;
         for (int lvl = 0; lvl < ti.w; ++lvl) {
 #pragma unroll
             for (int g = 0; g < PIX_PER_THREAD; ++g) {
-                if (!(ref[g] & 0x8000u)) {
-                    const uint2 nd = nb[ref[g]];
-                    const unsigned v = pixbase[g * RS + (nd.x & 0xffffffu)];
-                    ref[g] = ((v << 24) > nd.x) ? (nd.y >> 16) : (nd.y & 0xffffu);
-                }
+                const uint2 nd = *reinterpret_cast<const uint2*>(nb + ref[g]);
+                const unsigned v = pixbase[g * RS + (nd.x & 0xffffffu)];
+                ref[g] = __byte_perm(nd.y, 0u, ((v << 24) > nd.x) ? 0x4432u : 0x4410u);
             }
         }
 #pragma unroll
-        for (int g = 0; g < PIX_PER_THREAD; ++g) acc[g] = __dadd_rn(acc[g], lb[ref[g] & 0x7fffu]);
+        for (int g = 0; g < PIX_PER_THREAD; ++g)
+            acc[g] = __dadd_rn(acc[g], *reinterpret_cast<const double*>(lb + ref[g]));
     }
 }
 
@@ -207,21 +212,25 @@ __global__ void __launch_bounds__(NTHREADS) score_kernel(const ScoreArgs a) {
         star_tap(k, dr, dc);
         sp[k] = (dr + g.n) * g.RS + (dc + g.n);
     }
-    const uint2* f0n = a.f0.nodes;  const double* f0l = a.f0.leaves;  const int4* f0t = a.f0.trees;
-    const uint2* f1n = a.f1.nodes;  const double* f1l = a.f1.leaves;  const int4* f1t = a.f1.trees;
+    const uint8_t* f0n = reinterpret_cast<const uint8_t*>(a.f0.nodes);
+    const uint8_t* f0l = reinterpret_cast<const uint8_t*>(a.f0.leaves);
+    const int4* f0t = a.f0.trees;
+    const uint8_t* f1n = reinterpret_cast<const uint8_t*>(a.f1.nodes);
+    const uint8_t* f1l = reinterpret_cast<const uint8_t*>(a.f1.leaves);
+    const int4* f1t = a.f1.trees;
     if (FOREST_SMEM) {
         copy_to_smem(reinterpret_cast<uint2*>(smem + L.f0_nodes), a.f0.nodes, a.f0.n_nodes);
         copy_to_smem(reinterpret_cast<double*>(smem + L.f0_leaves), a.f0.leaves, a.f0.n_leaves);
         copy_to_smem(reinterpret_cast<int4*>(smem + L.f0_trees), a.f0.trees, a.f0.n_trees);
-        f0n = reinterpret_cast<const uint2*>(smem + L.f0_nodes);
-        f0l = reinterpret_cast<const double*>(smem + L.f0_leaves);
+        f0n = smem + L.f0_nodes;
+        f0l = smem + L.f0_leaves;
         f0t = reinterpret_cast<const int4*>(smem + L.f0_trees);
         if (a.blend) {
             copy_to_smem(reinterpret_cast<uint2*>(smem + L.f1_nodes), a.f1.nodes, a.f1.n_nodes);
             copy_to_smem(reinterpret_cast<double*>(smem + L.f1_leaves), a.f1.leaves, a.f1.n_leaves);
             copy_to_smem(reinterpret_cast<int4*>(smem + L.f1_trees), a.f1.trees, a.f1.n_trees);
-            f1n = reinterpret_cast<const uint2*>(smem + L.f1_nodes);
-            f1l = reinterpret_cast<const double*>(smem + L.f1_leaves);
+            f1n = smem + L.f1_nodes;
+            f1l = smem + L.f1_leaves;
             f1t = reinterpret_cast<const int4*>(smem + L.f1_trees);
         }
     }
@@ -302,7 +311,7 @@ __global__ void __launch_bounds__(NTHREADS) score_kernel(const ScoreArgs a) {
         double p[PIX_PER_THREAD];
 #pragma unroll
         for (int i = 0; i < PIX_PER_THREAD; ++i) p[i] = 0.0;
-        traverse_forest(f0n, f0l, f0t, a.f0.n_trees, pixbase, g.RS, active, p);
+        traverse_forest(f0n, f0l, f0t, a.f0.n_trees, pixbase, g.RS, p);
         const double T0 = (double)a.f0.n_trees;
 #pragma unroll
         for (int i = 0; i < PIX_PER_THREAD; ++i) p[i] = __ddiv_rn(p[i], T0);
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(NTHREADS) score_kernel(const ScoreArgs a) {
             double q[PIX_PER_THREAD];
 #pragma unroll
             for (int i = 0; i < PIX_PER_THREAD; ++i) q[i] = 0.0;
-            traverse_forest(f1n, f1l, f1t, a.f1.n_trees, pixbase, g.RS, active, q);
+            traverse_forest(f1n, f1l, f1t, a.f1.n_trees, pixbase, g.RS, q);
             const double T1 = (double)a.f1.n_trees;
 #pragma unroll
             for (int i = 0; i < PIX_PER_THREAD; ++i) p[i] = blend2(p[i], __ddiv_rn(q[i], T1), a.w0, a.w1);

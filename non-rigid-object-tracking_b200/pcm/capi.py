@@ -49,6 +49,7 @@ def load_library():
         "pcm_create": (I, [I, C.POINTER(P)]),
         "pcm_destroy": (None, [P]),
         "pcm_set_stream": (I, [P, P]),
+        "pcm_use_own_stream": (I, [P]),
         "pcm_synchronize": (I, [P]),
         "pcm_set_features": (I, [P, I, I, P]),
         "pcm_num_features": (I, [P]),
@@ -79,7 +80,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_synchronize",
+    "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_use_own_stream", "pcm_synchronize",
     "pcm_set_features", "pcm_num_features", "pcm_add_model", "pcm_set_novelty", "pcm_num_models", "pcm_crop_rect",
     "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_convert", "pcm_gather_features",
     "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_profile_enable", "pcm_profile_read",
@@ -145,7 +146,11 @@ class Handle:
         return int(self.lib.pcm_launch_count(self._h))
 
     def set_stream(self, cuda_stream):
-        self._check(self.lib.pcm_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+        """Enqueue on this cudaStream_t (integer handle; 0 = legacy default stream)."""
+        self._check(self.lib.pcm_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def use_own_stream(self):
+        self._check(self.lib.pcm_use_own_stream(self._h))
 
     def synchronize(self):
         self._check(self.lib.pcm_synchronize(self._h))
