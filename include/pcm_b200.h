@@ -81,7 +81,6 @@ int pcm_num_features(const pcm_handle* h);
  *   value1[i]     class-1 fraction at node i              (tree_.value[i,0,1])
  * Thresholds are collapsed to integers here (x_f32 <= thr  <=>  v <= t), so
  * scoring is bit-exact against predict_proba (:80,:82).
- * Limit: <= 8192 nodes (internal + leaves) per tree, i.e. any tree of depth <= 12.
  * Returns the model index in *model_index. */
 int pcm_add_model(pcm_handle* h, int n_frame, int n_trees, const int64_t* tree_offsets,
                   const int32_t* feature, const double* threshold,
@@ -179,12 +178,13 @@ int pcm_debug_tables(pcm_handle* h, uint16_t* gamma, uint16_t* cbrt_tab, int32_t
 int64_t pcm_launch_count(const pcm_handle* h);
 
 /* Per-kernel device timing (CUDA events on the handle's stream around every
- * launch while enabled).  Kernel ids: 0 score (fused convert+features+forest),
- * 1 segment_reduce, 2 segment_decide, 3 segment_resolve, 4 mask_dilate, 5 iou.
+ * launch while enabled).  Kernel ids: 0 score (fused star features + forests),
+ * 1 segment_reduce, 2 segment_decide, 3 segment_resolve, 4 mask_dilate, 5 iou,
+ * 6 planes (colour conversion to planar tiles).
  * pcm_profile_read synchronises the stream, adds the finished launches to the
- * running totals and returns them (ms_sum[i], count[i] for i < n <= 6);
+ * running totals and returns them (ms_sum[i], count[i] for i < n <= PCM_NUM_KERNELS);
  * reset != 0 clears the totals afterwards. */
-#define PCM_NUM_KERNELS 6
+#define PCM_NUM_KERNELS 7
 int pcm_profile_enable(pcm_handle* h, int on);
 int pcm_profile_read(pcm_handle* h, double* ms_sum, int64_t* count, int n, int reset);
 

@@ -6,11 +6,14 @@
 #include "../../include/pcm_b200.h"
 #include "pcm_kernels.cuh"
 
+#include <cudaTypedefs.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -83,6 +86,7 @@ struct Model {
     void* d_nodes = nullptr;
     void* d_leaves = nullptr;
     void* d_trees = nullptr;
+    TopNodes top{};               // root + its children of the first MAX_TOP_TREES trees
     bool has_pca = false;
     DevPCA pca{};
     void* d_pca = nullptr;        // comp | comp255 | mean, 3F doubles
@@ -97,6 +101,7 @@ struct pcm_handle {
     cudaStream_t stream = nullptr;
     ColorTables* d_tables = nullptr;
     ColorTables h_tables;
+    PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;   // driver entry point (no libcuda link)
     bool features_set = false;
     Geom geom{};
     std::vector<Model> models;
@@ -111,7 +116,7 @@ struct pcm_handle {
     int64_t prof_n[PCM_NUM_KERNELS] = {0};
 
     // per-update scratch (device)
-    DevBuf frame, labels, priors, p1, sa, seg, rmin, rmax, decision, scores, flagged, mask, pre, counts;
+    DevBuf frame, labels, priors, planes, sched, p1, sa, seg, rmin, rmax, decision, scores, flagged, mask, pre, counts;
     // pinned staging (host)
     PinBuf h_frame, h_labels, h_priors, h_mask, h_small;
 
@@ -136,6 +141,24 @@ static SegLayout seg_layout(int S) {
     l.total = l.err + sizeof(int);
     return l;
 }
+
+// PCM_DEBUG_SYNC=1: synchronise after every launch so that a device fault is
+// attributed to the kernel that caused it.
+static bool debug_sync_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PCM_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+#define CHECK_LAUNCH(h, name)                                                                   \
+    do {                                                                                        \
+        CUDA_TRY(cudaGetLastError());                                                           \
+        (h)->launches++;                                                                        \
+        if (debug_sync_enabled()) {                                                             \
+            cudaError_t e2__ = cudaStreamSynchronize((h)->stream);                              \
+            if (e2__ != cudaSuccess)                                                            \
+                return fail(PCM_E_CUDA, "kernel %s faulted: %s", name, cudaGetErrorString(e2__)); \
+        }                                                                                       \
+    } while (0)
 
 // ---------------------------------------------------------------------------------
 // per-kernel timing
@@ -198,11 +221,10 @@ static Geom make_geom(int n, int n_spaces, const int* ids) {
     g.K = 1 + 8 * n;
     g.F = 3 * g.K * n_spaces;
     g.n_planes = 3 * n_spaces + 1;
-    g.PW = TILE_W + 2 * n;
+    g.HX = 16;
     g.PH = TILE_H + 2 * n;
-    g.RS = (g.PW + 3) & ~3;
+    g.RS = TILE_W + 2 * g.HX;
     g.PS = g.RS * g.PH;
-    g.RAWS = ((g.PW * 3 + 3 + 3) & ~3) + 4;
     return g;
 }
 
@@ -221,10 +243,9 @@ static int int_threshold(double thr) {
 }
 
 struct EncTree {
-    std::vector<uint2> nodes;     // internal nodes, then one self-looping pseudo-node per leaf
-    std::vector<double> leaves;
-    unsigned root = 0;            // byte offset of the root entry
-    int n_int = 0;
+    std::vector<uint2> nodes;     // entries (see pcm_kernels.cuh): y = entry INDEX of the left child here
+    std::vector<double> values;   // parallel: class-1 fraction of leaf entries
+    int n_leaf = 0;
     int depth = 0;
 };
 
@@ -237,9 +258,6 @@ struct Encoder {
     const double* value1;
     int n;                       // nodes in this tree
     std::vector<int> tint;       // integer threshold per node
-    std::vector<int> node_id;    // new index of kept internal nodes, -1 otherwise
-    std::vector<int> leaf_id;
-    int n_int = 0;
     EncTree out;
     std::string err;
 
@@ -249,51 +267,33 @@ struct Encoder {
         while (left[i] != -1 && tint[i] < -1) i = right[i];
         return i;
     }
-    // byte offset of the entry a child reference resolves to
-    unsigned ref_of(int i) const {
-        i = skip(i);
-        return 8u * (unsigned)(left[i] == -1 ? n_int + leaf_id[i] : node_id[i]);
-    }
     bool run() {
         tint.assign(n, 0);
-        node_id.assign(n, -1);
-        leaf_id.assign(n, -1);
         for (int i = 0; i < n; ++i) {
             if (left[i] == -1) continue;
             if (left[i] < 0 || left[i] >= n || right[i] < 0 || right[i] >= n) { err = "child index out of range"; return false; }
             if (feature[i] < 0 || feature[i] >= g.F) { err = "feature index out of range"; return false; }
             tint[i] = int_threshold(threshold[i]);
         }
-        // iterative DFS from the root, numbering reachable kept nodes / leaves in preorder
-        std::vector<std::pair<int, int>> stack;   // (node, depth = internal nodes above)
-        stack.push_back({skip(0), 0});
-        int n_leaf = 0, depth = 0;
-        std::vector<int> order;
-        while (!stack.empty()) {
-            auto [i, d] = stack.back();
-            stack.pop_back();
+        // breadth-first: the root is entry 0, the two children of a node are adjacent entries
+        struct Item { int node, entry, depth; };
+        std::vector<Item> queue;
+        queue.push_back({skip(0), 0, 0});
+        out.nodes.assign(1, make_uint2(0, 0));
+        out.values.assign(1, 0.0);
+        const int vplane = 3 * g.n_spaces;
+        size_t visited = 0;
+        for (size_t qi = 0; qi < queue.size(); ++qi) {
+            const Item it = queue[qi];
+            if (++visited > (size_t)n + 1) { err = "tree is not a tree"; return false; }
+            const int i = it.node;
             if (left[i] == -1) {
-                if (leaf_id[i] < 0) leaf_id[i] = n_leaf++;
-                depth = std::max(depth, d);
+                out.nodes[it.entry] = make_uint2(0x0000ffffu, (unsigned)it.entry);
+                out.values[it.entry] = value1[i];
+                out.n_leaf++;
+                out.depth = std::max(out.depth, it.depth);
                 continue;
             }
-            if (node_id[i] >= 0) { err = "tree is not a tree"; return false; }
-            node_id[i] = n_int++;
-            order.push_back(i);
-            stack.push_back({skip(right[i]), d + 1});
-            stack.push_back({skip(left[i]), d + 1});
-        }
-        if (n_int + n_leaf > 8192) { err = "tree too large (limit 8192 nodes incl. leaves)"; return false; }
-        out.nodes.assign((size_t)n_int + n_leaf, make_uint2(0, 0));
-        out.leaves.assign(n_leaf, 0.0);
-        for (int i = 0; i < n; ++i)
-            if (leaf_id[i] >= 0) {
-                out.leaves[leaf_id[i]] = value1[i];
-                const unsigned self = 8u * (unsigned)(n_int + leaf_id[i]);
-                out.nodes[n_int + leaf_id[i]] = make_uint2(0xff000000u, self | (self << 16));
-            }
-        const int vplane = 3 * g.n_spaces;
-        for (int i : order) {
             const int f = feature[i];
             const int q = f / (3 * g.K), rem = f % (3 * g.K), k = rem / 3, ch = rem % 3;
             int dr, dc;
@@ -301,13 +301,15 @@ struct Encoder {
             int plane = 3 * q + ch;
             int thr = tint[i];
             if (thr == -1) { plane = vplane; thr = 0; }   // "tap is outside the crop"
-            const unsigned off = (unsigned)(plane * g.PS + (dr + g.n) * g.RS + (dc + g.n));
-            if (off >= (1u << 24)) { err = "tap offset overflow"; return false; }
-            out.nodes[node_id[i]] = make_uint2(((unsigned)thr << 24) | off, ref_of(left[i]) | (ref_of(right[i]) << 16));
+            const unsigned off = (unsigned)(plane * g.PS + (dr + g.n) * g.RS + (dc + g.HX));
+            if (off >= (1u << 16)) { err = "tap offset overflow"; return false; }
+            const int child = (int)out.nodes.size();
+            out.nodes.resize(child + 2, make_uint2(0, 0));
+            out.values.resize(child + 2, 0.0);
+            out.nodes[it.entry] = make_uint2((off << 16) | (unsigned)thr, (unsigned)child);
+            queue.push_back({skip(left[i]), child, it.depth + 1});
+            queue.push_back({skip(right[i]), child + 1, it.depth + 1});
         }
-        out.root = ref_of(0);
-        out.n_int = n_int;
-        out.depth = depth;
         return true;
     }
 };
@@ -344,6 +346,14 @@ extern "C" int pcm_create(int device, pcm_handle** out) {
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_TRY(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn)
+            return fail(PCM_E_CUDA, "pcm_create: driver does not provide cuTensorMapEncodeTiled");
+        h->encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
     build_tables(h->h_tables);
     CUDA_TRY(cudaMalloc(&h->d_tables, sizeof(ColorTables)));
     CUDA_TRY(cudaMemcpy(h->d_tables, &h->h_tables, sizeof(ColorTables), cudaMemcpyHostToDevice));
@@ -358,7 +368,7 @@ extern "C" void pcm_destroy(pcm_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto& m : h->models) free_model(m);
-    for (DevBuf* b : {&h->frame, &h->labels, &h->priors, &h->p1, &h->sa, &h->seg, &h->rmin, &h->rmax, &h->decision,
+    for (DevBuf* b : {&h->frame, &h->labels, &h->priors, &h->planes, &h->sched, &h->p1, &h->sa, &h->seg, &h->rmin, &h->rmax, &h->decision,
                       &h->scores, &h->flagged, &h->mask, &h->pre, &h->counts})
         b->release();
     for (PinBuf* b : {&h->h_frame, &h->h_labels, &h->h_priors, &h->h_mask, &h->h_small}) b->release();
@@ -429,19 +439,23 @@ extern "C" int pcm_add_model(pcm_handle* h, int n_frame, int n_trees, const int6
     std::vector<uint2> nodes;
     std::vector<double> leaves;
     std::vector<int4> trees;
-    int max_depth = 0;
+    int max_depth = 0, n_leaf = 0;
     for (int t = 0; t < n_trees; ++t) {
         const int64_t b = tree_offsets[t], e = tree_offsets[t + 1];
         if (e <= b) return fail(PCM_E_INVALID, "pcm_add_model: tree %d is empty", t);
         Encoder enc{h->geom, feature + b, threshold + b, left + b, right + b, value1 + b, (int)(e - b)};
         if (!enc.run()) return fail(PCM_E_LIMIT, "pcm_add_model: tree %d: %s", t, enc.err.c_str());
-        // leaf value of entry offset o lives at leaves + 8*leaf_base + (o - 8*n_int)
-        trees.push_back(make_int4(8 * (int)nodes.size(), 8 * ((int)leaves.size() - enc.out.n_int), (int)enc.out.root,
-                                  enc.out.depth));
-        nodes.insert(nodes.end(), enc.out.nodes.begin(), enc.out.nodes.end());
-        leaves.insert(leaves.end(), enc.out.leaves.begin(), enc.out.leaves.end());
+        const unsigned base = (unsigned)nodes.size();       // entry index of this tree's root
+        trees.push_back(make_int4((int)(8u * base), enc.out.depth, 0, 0));
+        for (uint2 nd : enc.out.nodes) {
+            nd.y = 8u * (nd.y + base);                      // forest-relative byte offset
+            nodes.push_back(nd);
+        }
+        leaves.insert(leaves.end(), enc.out.values.begin(), enc.out.values.end());
         max_depth = std::max(max_depth, enc.out.depth);
+        n_leaf += enc.out.n_leaf;
     }
+    if (nodes.size() > (1u << 27)) return fail(PCM_E_LIMIT, "pcm_add_model: forest too large");
     Model m;
     m.n_frame = n_frame;
     m.max_depth = max_depth;
@@ -456,7 +470,14 @@ extern "C" int pcm_add_model(pcm_handle* h, int n_frame, int n_trees, const int6
     m.forest.trees = static_cast<const int4*>(m.d_trees);
     m.forest.n_trees = n_trees;
     m.forest.n_nodes = (int)nodes.size();
-    m.forest.n_leaves = (int)leaves.size();
+    m.forest.n_leaves = n_leaf;
+    for (int t = 0; t < n_trees && t < MAX_TOP_TREES; ++t) {
+        const uint2 root = nodes[trees[t].x / 8];
+        const bool root_is_leaf = root.y == (unsigned)trees[t].x;     // pseudo-node: y = self
+        m.top.n[t][0] = root;
+        m.top.n[t][1] = root_is_leaf ? root : nodes[root.y / 8];
+        m.top.n[t][2] = root_is_leaf ? root : nodes[root.y / 8 + 1];
+    }
     h->models.push_back(m);
     if (model_index) *model_index = (int)h->models.size() - 1;
     return PCM_OK;
@@ -550,24 +571,64 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     CUDA_TRY(h->rmax.reserve(sizeof(int) * (size_t)S));
     CUDA_TRY(h->decision.reserve((size_t)S));
     CUDA_TRY(h->scores.reserve(sizeof(float) * (size_t)S));
-    CUDA_TRY(h->flagged.reserve(sizeof(int) * (size_t)S));
     if (want_pre) CUDA_TRY(h->pre.reserve(npx));
 
-    // ---- K1 -----------------------------------------------------------------------
+    // ---- K0: BGR crop -> planar colour planes (+ validity plane) ------------------------
+    const Geom& g = h->geom;
+    const long long pitch = ((long long)cw + 127) / 128 * 128;
+    const long long plane_stride = pitch * ch;
+    CUDA_TRY(h->planes.reserve((size_t)plane_stride * g.n_planes));
+    CUDA_TRY(h->sched.reserve(64));
+    PlanesArgs pa{};
+    pa.frame = d_frame;
+    pa.stride = stride;
+    pa.cx = cx; pa.cy = cy; pa.cw = cw; pa.ch = ch;
+    pa.g = g;
+    pa.tables = h->d_tables;
+    pa.planes = h->planes.as<uint8_t>();
+    pa.pitch = pitch;
+    pa.plane_stride = plane_stride;
+    pa.tile_counter = h->sched.as<unsigned>();
+    char* seg = h->seg.as<char>();
+    pa.n_labels = S;
+    pa.sum = reinterpret_cast<double*>(seg + sl.sum);
+    pa.asum = reinterpret_cast<double*>(seg + sl.asum);
+    pa.area = reinterpret_cast<int*>(seg + sl.area);
+    pa.rmin = h->rmin.as<int>();
+    pa.rmax = h->rmax.as<int>();
+    pa.n_flagged = reinterpret_cast<int*>(seg + sl.nflag);
+    pa.err = reinterpret_cast<int*>(seg + sl.err);
+    {
+        const long long groups = (long long)ch * ((cw + 3) / 4);
+        const int blocks = (int)std::min<long long>((groups + 255) / 256, (long long)h->sm_count * 16);
+        KernelTimer kt(h, 6);
+        planes_kernel<<<std::max(blocks, 1), 256, 0, st>>>(pa);
+    }
+    CHECK_LAUNCH(h, "planes_kernel");
+
+    // ---- K1: TMA-tiled star features + forest(s) [+ novelty] -> P(fg) ------------------------
+    CUtensorMap tmap;
+    {
+        const cuuint64_t gdim[3] = {(cuuint64_t)cw, (cuuint64_t)ch, (cuuint64_t)g.n_planes};
+        const cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)plane_stride};
+        const cuuint32_t box[3] = {(cuuint32_t)g.RS, (cuuint32_t)g.PH, (cuuint32_t)g.n_planes};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = h->encode_tiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->planes.p, gdim, gstr, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(PCM_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d crop", (int)r, cw, ch);
+    }
     ScoreArgs a{};
-    a.frame = d_frame;
-    a.frame_lo = d_frame;
-    a.frame_hi = d_frame + (size_t)(H - 1) * stride + (size_t)W * 3;
-    a.stride = stride;
-    a.cx = cx; a.cy = cy; a.cw = cw; a.ch = ch;
+    a.cw = cw; a.ch = ch;
     a.tiles_x = (cw + TILE_W - 1) / TILE_W;
     a.tiles_y = (ch + TILE_H - 1) / TILE_H;
-    a.g = h->geom;
-    a.tables = h->d_tables;
+    a.g = g;
+    a.tile_counter = h->sched.as<unsigned>();
     const Model& m0 = h->models[p->model_cur];
     a.f0 = m0.forest;
+    a.top0 = m0.top;
     a.blend = p->model_next >= 0;
-    if (a.blend) a.f1 = h->models[p->model_next].forest;
+    if (a.blend) { a.f1 = h->models[p->model_next].forest; a.top1 = h->models[p->model_next].top; }
     a.w0 = p->w_cur; a.w1 = p->w_next;
     a.novelty = p->novelty != 0;
     if (a.novelty) {
@@ -576,7 +637,13 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     }
     a.p1_out = h->p1.as<double>();
     a.sa_out = a.novelty ? h->sa.as<double>() : nullptr;
+    a.seg.labels = d_labels;
+    a.seg.n_labels = S;
+    a.seg.thr = p->outlier_threshold;
+    a.seg.sum = pa.sum; a.seg.asum = pa.asum; a.seg.area = pa.area;
+    a.seg.rmin = pa.rmin; a.seg.rmax = pa.rmax; a.seg.err = pa.err;
 
+    // forests live in shared memory when two CTAs per SM still fit, else they are read through L1
     ScoreSmem ls = score_smem_layout(a.g, a.f0, a.f1, a.blend, a.novelty, true);
     const bool forest_smem = (int)ls.total <= h->max_smem_optin;
     if (!forest_smem) ls = score_smem_layout(a.g, a.f0, a.f1, a.blend, a.novelty, false);
@@ -590,65 +657,26 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     const int grid = std::min(n_tiles, h->sm_count * occ);
     {
         KernelTimer kt(h, 0);
-        if (forest_smem) score_kernel<true><<<grid, NTHREADS, ls.total, st>>>(a);
-        else score_kernel<false><<<grid, NTHREADS, ls.total, st>>>(a);
+        if (forest_smem) score_kernel<true><<<grid, NTHREADS, ls.total, st>>>(tmap, a);
+        else score_kernel<false><<<grid, NTHREADS, ls.total, st>>>(tmap, a);
     }
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
+    CHECK_LAUNCH(h, forest_smem ? "score_kernel<smem>" : "score_kernel<global>");
 
-    // ---- K2 / K2b / K2c --------------------------------------------------------------
-    char* seg = h->seg.as<char>();
-    CUDA_TRY(cudaMemsetAsync(seg, 0, sl.total, st));
-    CUDA_TRY(cudaMemsetAsync(h->rmin.p, 0x7f, sizeof(int) * (size_t)S, st));
-    CUDA_TRY(cudaMemsetAsync(h->rmax.p, 0xff, sizeof(int) * (size_t)S, st));
-    SegArgs sa{};
-    sa.p1 = a.p1_out;
-    sa.sa = a.sa_out;
-    sa.labels = d_labels;
-    sa.n_px = (int)npx; sa.cw = cw; sa.n_labels = S;
-    sa.thr = p->outlier_threshold;
-    sa.sum = reinterpret_cast<double*>(seg + sl.sum);
-    sa.asum = reinterpret_cast<double*>(seg + sl.asum);
-    sa.area = reinterpret_cast<int*>(seg + sl.area);
-    sa.rmin = h->rmin.as<int>();
-    sa.rmax = h->rmax.as<int>();
-    sa.err = reinterpret_cast<int*>(seg + sl.err);
-    {
-        const int blocks = (int)std::min<size_t>((npx + 255) / 256, (size_t)h->sm_count * 8);
-        {
-            KernelTimer kt(h, 1);
-            segment_reduce_kernel<<<blocks, 256, 0, st>>>(sa);
-        }
-        CUDA_TRY(cudaGetLastError());
-        h->launches++;
-    }
+    // ---- K2: per-label decision (+ exact path) ------------------------------------------------
     DecideArgs da{};
-    da.sum = sa.sum; da.asum = sa.asum; da.area = sa.area;
+    da.p1 = a.p1_out; da.sa = a.sa_out; da.labels = d_labels; da.cw = cw; da.thr = p->outlier_threshold;
+    da.sum = pa.sum; da.asum = pa.asum; da.area = pa.area; da.rmin = pa.rmin; da.rmax = pa.rmax;
     da.priors = d_priors;
     da.n_labels = S;
     da.prior_weight = p->prior_weight;
     da.decision = h->decision.as<uint8_t>();
     da.scores = h->scores.as<float>();
-    da.flagged = h->flagged.as<int>();
     da.n_flagged = reinterpret_cast<int*>(seg + sl.nflag);
     {
         KernelTimer kt(h, 2);
         segment_decide_kernel<<<(S + 255) / 256, 256, 0, st>>>(da);
     }
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    ResolveArgs ra{};
-    ra.p1 = sa.p1; ra.sa = sa.sa; ra.labels = d_labels; ra.cw = cw; ra.thr = sa.thr;
-    ra.area = sa.area; ra.rmin = sa.rmin; ra.rmax = sa.rmax;
-    ra.priors = d_priors; ra.prior_weight = p->prior_weight;
-    ra.flagged = da.flagged; ra.n_flagged = da.n_flagged;
-    ra.decision = da.decision; ra.scores = da.scores;
-    {
-        KernelTimer kt(h, 3);
-        segment_resolve_kernel<<<std::min(S, h->sm_count), 256, 0, st>>>(ra);
-    }
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
+    CHECK_LAUNCH(h, "segment_decide_kernel");
 
     // ---- K3 -------------------------------------------------------------------------
     DilateArgs dl{};
@@ -664,8 +692,7 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
         KernelTimer kt(h, 4);
         mask_dilate_kernel<<<dg, 256, 0, st>>>(dl);
     }
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
+    CHECK_LAUNCH(h, "mask_dilate_kernel");
 
     h->last_cw = cw; h->last_ch = ch; h->last_S = S;
     h->last_novelty = a.novelty;

@@ -39,10 +39,11 @@ struct Geom {
     int K;            // 1 + 8 n taps
     int F;            // 3 K Q features
     int n_planes;     // 3 Q + 1 (last plane = in-crop validity)
-    int PW, PH;       // tile + halo extents
-    int RS;           // plane row stride (bytes)
-    int PS;           // plane stride (bytes)
-    int RAWS;         // raw BGR staging row stride (bytes, multiple of 4)
+    int HX;           // horizontal halo of the smem tile: 16, because the TMA box must start on a
+                      // 16-byte boundary of the row (measured: any other x faults on sm_100a)
+    int PH;           // tile rows incl. vertical halo: TILE_H + 2 n
+    int RS;           // plane row stride in the smem tile (bytes) = TMA box width = TILE_W + 2 HX
+    int PS;           // plane stride in the smem tile (bytes)
 };
 
 __host__ __device__ inline void star_tap(int k, int& dr, int& dc) {

@@ -1,40 +1,55 @@
 // pcm_kernels.cuh -- CUDA kernels of the PC masker hot path (sm_100a).
 //
-//  K1 score_kernel        BGR crop -> HSV/LAB planes (smem) -> star taps -> forest(s)
+//  K0 planes_kernel       BGR crop -> planar HSV/LAB/BGR planes + validity plane (cvtColor :294-309)
+//  K1 score_kernel        TMA tiles of those planes (smem, halo) -> star taps -> forest(s)
 //                         [-> PCA novelty error] [-> temporal blend] -> P(fg) f64 [, err f64]
 //                         replaces cvtColor + getFeatures + X/255 + predict_proba + PCA
 //                         (reference maskers/pixel_classification.py:53-63, :80-95)
-//  K2 segment_reduce      per-label sums / areas (np.unique :97 + first loop of
+//                         epilogue: per-label sums / areas (np.unique :97 + first loop of
 //                         compileSaliencyMap :235-238), warp-aggregated atomics
-//  K2b segment_decide     per-label score and decision (:240-242) + guard band
-//  K2c segment_resolve    exact sequential-float32 re-evaluation of guard-band labels
+//  K2 segment_decide      per-label score and decision (:240-242); labels inside the guard
+//                         band are re-evaluated exactly (sequential float32, raster order)
 //  K3 mask_dilate         decision -> 0/255 map (:242-246) fused with cv.dilate (:112)
 //  K5 iou_kernel          computeBenchmark counts (benchmark.py:8-14)
 //  + convert_kernel / gather_kernel: parity taps (pcm_convert, pcm_gather_features)
 #pragma once
 #include "pcm_device.cuh"
+#include <cuda.h>
 
 namespace pcm {
 
 // ------------------------------------------------------------------------------
-// packed forest (built on the host by encode_forest in pcm_api.cu)
-//   Every tree owns a contiguous run of 8-byte entries: its internal nodes followed
-//   by one self-looping pseudo-node per leaf, so that the traversal is branch-free
-//   and a thread that has reached a leaf simply stays there.
-//   node.x = thr << 24 | tap byte offset inside the plane tile (24 bits)
-//   node.y = left | right << 16, BYTE offsets of the children from the tree's base
-//   leaf pseudo-node: x = 0xff000000 (never goes right), y = self | self << 16
-//   trees[t] = {node base (bytes), leaf-value base (bytes, biased so that
-//               value address = base + entry offset), root offset, depth}
-// A tap value v (u8, 0 outside the crop) goes RIGHT iff v > thr  <=>  (v << 24) > node.x.
+// packed forest (built on the host by Encoder in pcm_api.cu)
+//   Every tree owns a contiguous run of 8-byte entries: internal nodes and one
+//   self-looping pseudo-node per leaf, laid out so that the two children of a node are
+//   ADJACENT entries (left, then right).  The traversal is branch-free and a thread that
+//   has reached a leaf simply stays there.
+//     entry.x = tap << 16 | thr   tap: byte offset of the tested value inside the plane
+//                                 tile; thr: the value v (u8, 0 outside the crop) goes
+//                                 RIGHT iff v > thr
+//     entry.y = byte offset of the LEFT child's entry from the start of the forest's
+//               entry array (right child = +8); relocated to an absolute shared-memory
+//               address when the forest is staged in shared memory
+//     leaf pseudo-node: x = 0x0000ffff (never right), y = self
+//   values[i] = class-1 fraction of entry i (leaf entries; 0 elsewhere), parallel array
+//   trees[t] = {root entry offset (bytes), depth, -, -}
 // The crop-border sentinel -1 of the reference (:263) is handled by the encoder:
 // nodes with integer threshold -1 test the validity plane instead (0 outside the crop).
 // ------------------------------------------------------------------------------
 struct DevForest {
-    const uint2* nodes;
-    const double* leaves;
+    const uint2* nodes;      // [n_nodes] entries
+    const double* leaves;    // [n_nodes] values, parallel to nodes
     const int4* trees;
     int n_trees, n_nodes, n_leaves;
+};
+
+// Root and its two children of the first MAX_TOP_TREES trees, passed in the kernel
+// parameter (constant) bank: the first two levels of a tree are evaluated from
+// warp-uniform operands, without touching the shared-memory pipe for node fetches
+// (entry.y here is still forest-relative).
+constexpr int MAX_TOP_TREES = 48;
+struct TopNodes {
+    uint2 n[MAX_TOP_TREES][3];   // {root, left child, right child}
 };
 
 struct DevPCA {
@@ -44,59 +59,247 @@ struct DevPCA {
     double mean_dot_comp;    // mean_ . components_[0]
 };
 
-struct ScoreArgs {
-    const uint8_t* frame;            // BGR, rows `stride` bytes apart
-    const uint8_t* frame_lo;         // first / one-past-last readable byte of the frame
-    const uint8_t* frame_hi;
+// ---- K0: BGR crop -> planar colour planes + validity plane ------------------------------
+// planes[p][r][c], p = 3*q + channel in `features` token order, last plane = 1 (inside the
+// crop).  Rows are `pitch` bytes apart (multiple of 16 so that TMA can tile the tensor);
+// the tile loads of K1 zero-fill everything outside [0,cw) x [0,ch).
+struct PlanesArgs {
+    const uint8_t* frame;
     long long stride;
-    int cx, cy, cw, ch;              // crop rectangle (frame coords)
-    int tiles_x, tiles_y;
+    int cx, cy, cw, ch;
     Geom g;
     const ColorTables* tables;
+    uint8_t* planes;
+    long long pitch;          // bytes between rows
+    long long plane_stride;   // bytes between planes
+    unsigned* tile_counter;   // reset here for K1's dynamic tile scheduler
+    // per-label accumulators of K2, reset here (saves three memset launches per frame)
+    int n_labels;
+    double* sum;
+    double* asum;
+    int* area;
+    int* rmin;
+    int* rmax;
+    int* n_flagged;
+    int* err;
+};
+
+__global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
+    __shared__ ColorTables tab;
+    for (int i = threadIdx.x; i < (int)(sizeof(ColorTables) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(&tab)[i] = reinterpret_cast<const uint32_t*>(a.tables)[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *a.tile_counter = 0; *a.n_flagged = 0; *a.err = 0; }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_labels; i += gridDim.x * blockDim.x) {
+        a.sum[i] = 0.0; a.asum[i] = 0.0; a.area[i] = 0; a.rmin[i] = 0x7fffffff; a.rmax[i] = -1;
+    }
+    __syncthreads();
+    const int groups_per_row = (a.cw + 3) >> 2;
+    const long long n_groups = (long long)a.ch * groups_per_row;
+    const int nch = 3 * a.g.n_spaces;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_groups;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / groups_per_row);
+        const int c0 = (int)(i - (long long)r * groups_per_row) * 4;
+        const uint8_t* src = a.frame + (long long)(a.cy + r) * a.stride + (long long)(a.cx + c0) * 3;
+        uint32_t out[3 * MAX_SPACES + 1];
+#pragma unroll
+        for (int p = 0; p < 3 * MAX_SPACES + 1; ++p) out[p] = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (c0 + j < a.cw) {
+                const int b = __ldg(src + 3 * j), gg = __ldg(src + 3 * j + 1), rr = __ldg(src + 3 * j + 2);
+#pragma unroll
+                for (int q = 0; q < MAX_SPACES; ++q) {
+                    if (q < a.g.n_spaces) {
+                        int v0, v1, v2;
+                        const int sid = a.g.space_id[q];
+                        if (sid == 1) bgr2hsv_px(b, gg, rr, tab.sdiv, tab.hdiv, v0, v1, v2);
+                        else if (sid == 2) bgr2lab_px(b, gg, rr, tab.gamma, tab.cbrt_tab, v0, v1, v2);
+                        else { v0 = b; v1 = gg; v2 = rr; }
+                        out[3 * q + 0] |= (uint32_t)v0 << (8 * j);
+                        out[3 * q + 1] |= (uint32_t)v1 << (8 * j);
+                        out[3 * q + 2] |= (uint32_t)v2 << (8 * j);
+                    }
+                }
+                out[3 * MAX_SPACES] |= 1u << (8 * j);
+            }
+        }
+        uint8_t* dst = a.planes + (long long)r * a.pitch + c0;
+#pragma unroll
+        for (int p = 0; p < 3 * MAX_SPACES; ++p)
+            if (p < nch) *reinterpret_cast<uint32_t*>(dst + p * a.plane_stride) = out[p];
+        *reinterpret_cast<uint32_t*>(dst + nch * a.plane_stride) = out[3 * MAX_SPACES];
+    }
+}
+
+// ---- PTX helpers: mbarrier, TMA tile load, shared-memory loads --------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+// TMA: one 3-D box {x, y, plane} of the planar crop tensor -> dense [plane][row][col] tile
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int x, int y, int z, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+
+// ---- per-label accumulation (np.unique :97 + first loop of compileSaliencyMap :235-238) ----
+// d = p1 - (max(sa, thr) - thr) per pixel (:237); per label: sum d, sum |d|, area, first /
+// last row.  Runs in K1's epilogue: the 32 lanes of a warp hold 32 consecutive pixels of one
+// row; lanes with equal labels are combined with shuffles so that a warp issues one set of
+// atomics per distinct label.
+struct SegAcc {
+    const int32_t* labels;     // [ch*cw]
+    int n_labels;
+    double thr;                // outlier_threshold
+    double* sum;               // [S]
+    double* asum;              // [S]
+    int* area;                 // [S]
+    int* rmin;                 // [S] init INT_MAX
+    int* rmax;                 // [S] init -1
+    int* err;                  // set to 1 on an out-of-range label
+};
+
+__device__ __forceinline__ double contribution(double p1, double sa, double thr) {
+    return __dsub_rn(p1, __dsub_rn(fmax(sa, thr), thr));
+}
+
+// lab < 0: lane does not take part.  `row` is warp-uniform.
+__device__ __forceinline__ void segment_accumulate(const SegAcc& s, int lab, double d, int row) {
+    const int lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(0xffffffffu, lab >= 0);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int L = __shfl_sync(0xffffffffu, lab, leader);
+        const bool mine = (lab == L);
+        const unsigned members = __ballot_sync(0xffffffffu, mine);
+        double sm = mine ? d : 0.0, as = mine ? fabs(d) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sm += __shfl_xor_sync(0xffffffffu, sm, o);
+            as += __shfl_xor_sync(0xffffffffu, as, o);
+        }
+        if (lane == leader) {
+            atomicAdd(s.sum + L, sm);
+            atomicAdd(s.asum + L, as);
+            atomicAdd(s.area + L, __popc(members));
+            atomicMin(s.rmin + L, row);
+            atomicMax(s.rmax + L, row);
+        }
+        todo &= ~members;
+    }
+}
+
+struct ScoreArgs {
+    int cw, ch;                      // crop size
+    int tiles_x, tiles_y;
+    Geom g;
+    unsigned* tile_counter;          // dynamic tile scheduler (zeroed by K0)
     DevForest f0, f1;
+    TopNodes top0, top1;             // first two levels of f0 / f1 (constant bank)
     int blend;                       // 0/1: f1 (and pca1) valid
     double w0, w1;                   // np.average weights
     int novelty;                     // 0/1
     DevPCA pca0, pca1;
     double* p1_out;                  // [ch*cw]
     double* sa_out;                  // [ch*cw] (novelty only)
+    SegAcc seg;                      // per-label accumulators (epilogue)
 };
-
-__device__ __forceinline__ uint32_t ldg_word_checked(const uint8_t* wp, const uint8_t* lo, const uint8_t* hi) {
-    if (wp >= lo && wp + 4 <= hi) return __ldg(reinterpret_cast<const uint32_t*>(wp));
-    uint32_t w = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (wp + i >= lo && wp + i < hi) w |= (uint32_t)__ldg(wp + i) << (8 * i);
-    return w;
-}
 
 // One forest over the thread's PIX_PER_THREAD pixels; leaf fractions are added in
 // estimator order (sklearn ensemble/_forest.py: all_proba += prediction).
-// Branch-free: PIX_PER_THREAD independent pointer chases are interleaved by the
-// compiler, which is what hides the two dependent shared-memory loads per visit.
-__device__ __forceinline__ void traverse_forest(const uint8_t* __restrict__ nodes, const uint8_t* __restrict__ leaves,
-                                                const int4* __restrict__ trees, int n_trees,
-                                                const uint8_t* __restrict__ pixbase, int RS,
+// Branch-free: the PIX_PER_THREAD pointer chases are issued level by level so that
+// their dependent shared-memory loads overlap.  SM = forest staged in shared memory
+// (node links are absolute shared addresses); otherwise nodes/leaves are read through L1.
+template <bool SM>
+__device__ __forceinline__ void traverse_forest(const uint32_t nodes_s, const uint32_t vdelta_s,
+                                                const uint8_t* __restrict__ nodes_g,
+                                                const uint8_t* __restrict__ leaves_g,
+                                                const int4* __restrict__ trees, int n_trees, const TopNodes& top,
+                                                const uint32_t (&pix)[PIX_PER_THREAD],
                                                 double (&acc)[PIX_PER_THREAD]) {
+    const uint32_t base = SM ? nodes_s : 0u;
     for (int t = 0; t < n_trees; ++t) {
         const int4 ti = trees[t];
-        const uint8_t* nb = nodes + ti.x;
-        const uint8_t* lb = leaves + ti.y;
-        unsigned ref[PIX_PER_THREAD];
+        uint32_t ref[PIX_PER_THREAD];
+        int lvl = 0;
+        if (t < MAX_TOP_TREES) {
+            // levels 0 and 1 from warp-uniform operands (constant bank)
+            const uint2 e0 = top.n[t][0], eL = top.n[t][1], eR = top.n[t][2];
+            uint32_t v[PIX_PER_THREAD], x1[PIX_PER_THREAD];
 #pragma unroll
-        for (int g = 0; g < PIX_PER_THREAD; ++g) ref[g] = (unsigned)ti.z;
-        for (int lvl = 0; lvl < ti.w; ++lvl) {
+            for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = lds_u8(pix[g] + (e0.x >> 16));
 #pragma unroll
             for (int g = 0; g < PIX_PER_THREAD; ++g) {
-                const uint2 nd = *reinterpret_cast<const uint2*>(nb + ref[g]);
-                const unsigned v = pixbase[g * RS + (nd.x & 0xffffffu)];
-                ref[g] = __byte_perm(nd.y, 0u, ((v << 24) > nd.x) ? 0x4432u : 0x4410u);
+                const bool right = v[g] > (e0.x & 0xffffu);
+                x1[g] = right ? eR.x : eL.x;
+                ref[g] = (right ? eR.y : eL.y) + base;
+            }
+#pragma unroll
+            for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = lds_u8(pix[g] + (x1[g] >> 16));
+#pragma unroll
+            for (int g = 0; g < PIX_PER_THREAD; ++g) {
+                asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 8;\n\t}"
+                    : "+r"(ref[g]) : "r"(v[g]), "r"(x1[g] & 0xffffu));
+            }
+            lvl = 2;
+        } else {
+#pragma unroll
+            for (int g = 0; g < PIX_PER_THREAD; ++g) ref[g] = (uint32_t)ti.x + base;
+        }
+        for (; lvl < ti.y; ++lvl) {
+            uint2 nd[PIX_PER_THREAD];
+            uint32_t v[PIX_PER_THREAD];
+#pragma unroll
+            for (int g = 0; g < PIX_PER_THREAD; ++g)
+                nd[g] = SM ? lds_v2(ref[g]) : __ldg(reinterpret_cast<const uint2*>(nodes_g + ref[g]));
+#pragma unroll
+            for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = lds_u8(pix[g] + (nd[g].x >> 16));
+#pragma unroll
+            for (int g = 0; g < PIX_PER_THREAD; ++g) {
+                // ref = left child, + 8 (the adjacent right child) iff v > thr: one predicated add
+                uint32_t nxt = nd[g].y;
+                asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 8;\n\t}"
+                    : "+r"(nxt) : "r"(v[g]), "r"(nd[g].x & 0xffffu));
+                ref[g] = nxt;
             }
         }
 #pragma unroll
-        for (int g = 0; g < PIX_PER_THREAD; ++g)
-            acc[g] = __dadd_rn(acc[g], *reinterpret_cast<const double*>(lb + ref[g]));
+        for (int g = 0; g < PIX_PER_THREAD; ++g) {
+            const double leaf = SM ? lds_f64(ref[g] + vdelta_s)
+                                   : __ldg(reinterpret_cast<const double*>(leaves_g + ref[g]));
+            acc[g] = __dadd_rn(acc[g], leaf);
+        }
     }
 }
 
@@ -104,8 +307,8 @@ __device__ __forceinline__ void traverse_forest(const uint8_t* __restrict__ node
 //   t = sum_f x_f c_f - mean.c ;  err = sum_f |x_f - (t c_f + mean_f)|,  x_f = v_f / 255, v_f = -1 off-crop
 __device__ __forceinline__ void novelty_error(const double* __restrict__ comp, const double* __restrict__ comp255,
                                               const double* __restrict__ mean, const double mdc,
-                                              const int* __restrict__ sp,
-                                              const Geom& g, const uint8_t* __restrict__ pixbase,
+                                              const int* __restrict__ sp, const Geom& g,
+                                              const uint32_t (&pix)[PIX_PER_THREAD],
                                               double (&err)[PIX_PER_THREAD]) {
     const int nch = 3 * g.n_spaces;
     const int vplane = nch * g.PS;
@@ -117,22 +320,22 @@ __device__ __forceinline__ void novelty_error(const double* __restrict__ comp, c
             const int so = sp[k];
             unsigned ok = 0;
 #pragma unroll
-            for (int i = 0; i < PIX_PER_THREAD; ++i) ok |= (unsigned)(pixbase[i * g.RS + vplane + so] != 0) << i;
+            for (int i = 0; i < PIX_PER_THREAD; ++i) ok |= (unsigned)(lds_u8(pix[i] + vplane + so) != 0) << i;
             for (int p = 0; p < nch; ++p) {
                 const int f = (p / 3) * 3 * g.K + 3 * k + (p % 3);
-                const uint8_t* src = pixbase + p * g.PS + so;
+                const uint32_t off = (uint32_t)(p * g.PS + so);
                 if (pass == 0) {
                     const double c255 = comp255[f];
 #pragma unroll
                     for (int i = 0; i < PIX_PER_THREAD; ++i) {
-                        const double v = ((ok >> i) & 1u) ? u8_to_double(src[i * g.RS]) : -1.0;
+                        const double v = ((ok >> i) & 1u) ? u8_to_double(lds_u8(pix[i] + off)) : -1.0;
                         t[i] = fma(v, c255, t[i]);
                     }
                 } else {
                     const double c = comp[f], mu = mean[f];
 #pragma unroll
                     for (int i = 0; i < PIX_PER_THREAD; ++i) {
-                        const double v = ((ok >> i) & 1u) ? u8_to_double(src[i * g.RS]) : -1.0;
+                        const double v = ((ok >> i) & 1u) ? u8_to_double(lds_u8(pix[i] + off)) : -1.0;
                         err[i] += fabs(fma(v, 1.0 / 255.0, -fma(t[i], c, mu)));
                     }
                 }
@@ -150,9 +353,10 @@ __device__ __forceinline__ double blend2(double a, double b, double w0, double w
     return __ddiv_rn(__dadd_rn(__dmul_rn(a, w0), __dmul_rn(b, w1)), __dadd_rn(w0, w1));
 }
 
+constexpr int N_TILE_BUF = 2;
+
 struct ScoreSmem {
-    uint32_t planes, raw, tables, sp, f0_nodes, f0_leaves, f0_trees, f1_nodes, f1_leaves, f1_trees,
-        pca0, pca1, total;
+    uint32_t tiles, bars, sched, sp, f0_nodes, f0_leaves, f0_trees, f1_nodes, f1_leaves, f1_trees, pca0, pca1, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
@@ -162,19 +366,20 @@ __host__ __device__ inline ScoreSmem score_smem_layout(const Geom& g, const DevF
                                                        bool blend, bool novelty, bool forest_smem) {
     ScoreSmem s;
     uint32_t o = 0;
-    s.planes = o; o = align_up(o + g.n_planes * g.PS, 16);
-    s.raw = o;    o = align_up(o + g.PH * g.RAWS, 16);
-    s.tables = o; o = align_up(o + (uint32_t)sizeof(ColorTables), 16);
+    s.tiles = o;  o = align_up(o + N_TILE_BUF * align_up(g.n_planes * g.PS, 128), 128);
+    s.bars = o;   o += 8 * N_TILE_BUF;
+    s.sched = o;  o = align_up(o + 4 * N_TILE_BUF, 16);
     s.sp = o;     o = align_up(o + 4 * g.K, 16);
-    s.f0_nodes = s.f0_leaves = s.f0_trees = s.f1_nodes = s.f1_leaves = s.f1_trees = 0;
+    s.f0_nodes = s.f0_leaves = s.f1_nodes = s.f1_leaves = 0;
+    s.f0_trees = o;  o = align_up(o + 16 * f0.n_trees, 16);
+    s.f1_trees = o;
+    if (blend) o = align_up(o + 16 * f1.n_trees, 16);
     if (forest_smem) {
         s.f0_nodes = o;  o = align_up(o + 8 * f0.n_nodes, 16);
-        s.f0_leaves = o; o = align_up(o + 8 * f0.n_leaves, 16);
-        s.f0_trees = o;  o = align_up(o + 16 * f0.n_trees, 16);
+        s.f0_leaves = o; o = align_up(o + 8 * f0.n_nodes, 16);
         if (blend) {
             s.f1_nodes = o;  o = align_up(o + 8 * f1.n_nodes, 16);
-            s.f1_leaves = o; o = align_up(o + 8 * f1.n_leaves, 16);
-            s.f1_trees = o;  o = align_up(o + 16 * f1.n_trees, 16);
+            s.f1_leaves = o; o = align_up(o + 8 * f1.n_nodes, 16);
         }
     }
     s.pca0 = s.pca1 = 0;
@@ -191,47 +396,67 @@ __device__ __forceinline__ void copy_to_smem(T* dst, const T* __restrict__ src, 
     for (int i = threadIdx.x; i < n; i += NTHREADS) dst[i] = src[i];
 }
 
+// stage a forest's nodes in shared memory, turning child offsets into absolute shared addresses
+__device__ __forceinline__ void stage_nodes(uint8_t* dst, const uint2* __restrict__ src, int n) {
+    const uint32_t base = smem_u32(dst);
+    for (int i = threadIdx.x; i < n; i += NTHREADS) {
+        uint2 nd = src[i];
+        nd.y += base;
+        reinterpret_cast<uint2*>(dst)[i] = nd;
+    }
+}
+
 // K1 -----------------------------------------------------------------------------
+// Persistent CTAs; tiles are handed out by an atomic counter and arrive through a
+// two-stage TMA pipeline (the box of tile i+1 is in flight while tile i is scored).
 template <bool FOREST_SMEM>
-__global__ void __launch_bounds__(NTHREADS) score_kernel(const ScoreArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
+__global__ void __launch_bounds__(NTHREADS, 2) score_kernel(const __grid_constant__ CUtensorMap tmap, const ScoreArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
     const Geom& g = a.g;
     const ScoreSmem L = score_smem_layout(g, a.f0, a.f1, a.blend != 0, a.novelty != 0, FOREST_SMEM);
-    uint8_t* planes = smem + L.planes;
-    uint8_t* raw = smem + L.raw;
-    ColorTables* tab = reinterpret_cast<ColorTables*>(smem + L.tables);
+    const uint32_t tile_bytes = align_up(g.n_planes * g.PS, 128);
+    const uint32_t tiles_s = smem_u32(smem + L.tiles);
+    const uint32_t bars_s = smem_u32(smem + L.bars);
+    volatile int* sched = reinterpret_cast<volatile int*>(smem + L.sched);
     int* sp = reinterpret_cast<int*>(smem + L.sp);
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_tiles = a.tiles_x * a.tiles_y;
+    const uint32_t box_bytes = (uint32_t)(g.n_planes * g.PS);
 
-    // ---- once per CTA: tables, tap offsets, forests, PCA vectors -> smem ------------
-    copy_to_smem(reinterpret_cast<uint32_t*>(tab), reinterpret_cast<const uint32_t*>(a.tables),
-                 (int)(sizeof(ColorTables) / 4));
+    auto issue = [&](int buf) {   // thread 0: claim the next tile and start its TMA load
+        const int t = (int)atomicAdd(a.tile_counter, 1u);
+        sched[buf] = t;
+        if (t < n_tiles) {
+            const uint32_t bar = bars_s + 8 * buf;
+            mbar_expect_tx(bar, box_bytes);
+            tma_load_3d(tiles_s + buf * tile_bytes, &tmap, (t % a.tiles_x) * TILE_W - g.HX,
+                        (t / a.tiles_x) * TILE_H - g.n, 0, bar);
+        }
+    };
+
+    if (tid == 0) {
+        for (int b = 0; b < N_TILE_BUF; ++b) mbar_init(bars_s + 8 * b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(0);
+    }
+
+    // ---- once per CTA: tap offsets, forests, PCA vectors -> smem (overlaps the first TMA) ----
     for (int k = tid; k < g.K; k += NTHREADS) {
         int dr, dc;
         star_tap(k, dr, dc);
-        sp[k] = (dr + g.n) * g.RS + (dc + g.n);
+        sp[k] = (dr + g.n) * g.RS + (dc + g.HX);
     }
-    const uint8_t* f0n = reinterpret_cast<const uint8_t*>(a.f0.nodes);
-    const uint8_t* f0l = reinterpret_cast<const uint8_t*>(a.f0.leaves);
-    const int4* f0t = a.f0.trees;
-    const uint8_t* f1n = reinterpret_cast<const uint8_t*>(a.f1.nodes);
-    const uint8_t* f1l = reinterpret_cast<const uint8_t*>(a.f1.leaves);
-    const int4* f1t = a.f1.trees;
+    copy_to_smem(reinterpret_cast<int4*>(smem + L.f0_trees), a.f0.trees, a.f0.n_trees);
+    if (a.blend) copy_to_smem(reinterpret_cast<int4*>(smem + L.f1_trees), a.f1.trees, a.f1.n_trees);
+    const int4* f0t = reinterpret_cast<const int4*>(smem + L.f0_trees);
+    const int4* f1t = reinterpret_cast<const int4*>(smem + L.f1_trees);
     if (FOREST_SMEM) {
-        copy_to_smem(reinterpret_cast<uint2*>(smem + L.f0_nodes), a.f0.nodes, a.f0.n_nodes);
-        copy_to_smem(reinterpret_cast<double*>(smem + L.f0_leaves), a.f0.leaves, a.f0.n_leaves);
-        copy_to_smem(reinterpret_cast<int4*>(smem + L.f0_trees), a.f0.trees, a.f0.n_trees);
-        f0n = smem + L.f0_nodes;
-        f0l = smem + L.f0_leaves;
-        f0t = reinterpret_cast<const int4*>(smem + L.f0_trees);
+        stage_nodes(smem + L.f0_nodes, a.f0.nodes, a.f0.n_nodes);
+        copy_to_smem(reinterpret_cast<double*>(smem + L.f0_leaves), a.f0.leaves, a.f0.n_nodes);
         if (a.blend) {
-            copy_to_smem(reinterpret_cast<uint2*>(smem + L.f1_nodes), a.f1.nodes, a.f1.n_nodes);
-            copy_to_smem(reinterpret_cast<double*>(smem + L.f1_leaves), a.f1.leaves, a.f1.n_leaves);
-            copy_to_smem(reinterpret_cast<int4*>(smem + L.f1_trees), a.f1.trees, a.f1.n_trees);
-            f1n = smem + L.f1_nodes;
-            f1l = smem + L.f1_leaves;
-            f1t = reinterpret_cast<const int4*>(smem + L.f1_trees);
+            stage_nodes(smem + L.f1_nodes, a.f1.nodes, a.f1.n_nodes);
+            copy_to_smem(reinterpret_cast<double*>(smem + L.f1_leaves), a.f1.leaves, a.f1.n_nodes);
         }
     }
     const double *p0c = nullptr, *p0c255 = nullptr, *p0m = nullptr, *p1c = nullptr, *p1c255 = nullptr, *p1m = nullptr;
@@ -251,67 +476,33 @@ __global__ void __launch_bounds__(NTHREADS) score_kernel(const ScoreArgs a) {
     }
     __syncthreads();
 
-    const int n_tiles = a.tiles_x * a.tiles_y;
-    const int nch = 3 * g.n_spaces;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int tx0 = (tile % a.tiles_x) * TILE_W;
-        const int ty0 = (tile / a.tiles_x) * TILE_H;
-        const int lo = max(tx0 - g.n, 0);
-        const int hi = min(tx0 - g.n + g.PW, a.cw);
+    const uint32_t f0n_s = smem_u32(smem + L.f0_nodes), f0l_s = smem_u32(smem + L.f0_leaves);
+    const uint32_t f1n_s = smem_u32(smem + L.f1_nodes), f1l_s = smem_u32(smem + L.f1_leaves);
+    const uint8_t* f0n_g = reinterpret_cast<const uint8_t*>(a.f0.nodes);
+    const uint8_t* f0l_g = reinterpret_cast<const uint8_t*>(a.f0.leaves);
+    const uint8_t* f1n_g = reinterpret_cast<const uint8_t*>(a.f1.nodes);
+    const uint8_t* f1l_g = reinterpret_cast<const uint8_t*>(a.f1.leaves);
 
-        // ---- stage 1: warp w stages and converts plane rows w, w+8, ... ----------------
-        for (int r = warp; r < g.PH; r += NTHREADS / 32) {
-            const int gy = ty0 - g.n + r;
-            const bool rowok = (gy >= 0) && (gy < a.ch) && (hi > lo);
-            int m = 0;
-            uint8_t* rawrow = raw + r * g.RAWS;
-            if (rowok) {
-                const uint8_t* a0 = a.frame + (long long)(a.cy + gy) * a.stride + (long long)(a.cx + lo) * 3;
-                m = (int)(reinterpret_cast<uintptr_t>(a0) & 3);
-                const uint8_t* A0 = a0 - m;
-                const int nwords = (m + (hi - lo) * 3 + 3) >> 2;
-                for (int j = lane; j < nwords; j += 32)
-                    reinterpret_cast<uint32_t*>(rawrow)[j] = ldg_word_checked(A0 + 4 * j, a.frame_lo, a.frame_hi);
-            }
-            __syncwarp();
-            for (int c = lane; c < g.PW; c += 32) {
-                const int gx = tx0 - g.n + c;
-                uint8_t* dst = planes + r * g.RS + c;
-                if (rowok && gx >= lo && gx < hi) {
-                    const uint8_t* px = rawrow + m + (gx - lo) * 3;
-                    const int b = px[0], gg = px[1], rr = px[2];
-                    for (int q = 0; q < g.n_spaces; ++q) {
-                        int c0, c1, c2;
-                        const int sid = g.space_id[q];
-                        if (sid == 1) bgr2hsv_px(b, gg, rr, tab->sdiv, tab->hdiv, c0, c1, c2);
-                        else if (sid == 2) bgr2lab_px(b, gg, rr, tab->gamma, tab->cbrt_tab, c0, c1, c2);
-                        else { c0 = b; c1 = gg; c2 = rr; }
-                        dst[(3 * q + 0) * g.PS] = (uint8_t)c0;
-                        dst[(3 * q + 1) * g.PS] = (uint8_t)c1;
-                        dst[(3 * q + 2) * g.PS] = (uint8_t)c2;
-                    }
-                    dst[nch * g.PS] = 1;
-                } else {
-                    for (int p = 0; p <= nch; ++p) dst[p * g.PS] = 0;
-                }
-            }
-        }
-        __syncthreads();
+    const int col = (warp & 1) * 32 + lane;
+    const int row0 = (warp >> 1) * PIX_PER_THREAD;
+    uint32_t phase = 0;   // bit b = parity to wait for on buffer b
+    for (int buf = 0;; buf ^= 1) {
+        const int tile = sched[buf];
+        if (tile >= n_tiles) break;
+        if (tid == 0) issue(buf ^ 1);            // buffer buf^1 was released by the barrier below
+        mbar_wait(bars_s + 8 * buf, (phase >> buf) & 1u);
+        phase ^= 1u << buf;
 
-        // ---- stage 2: forests (+ novelty) for 8 rows of one column per thread -----------
-        const int col = (warp & 1) * 32 + lane;
-        const int row0 = (warp >> 1) * PIX_PER_THREAD;
+        const int tx0 = (tile % a.tiles_x) * TILE_W, ty0 = (tile / a.tiles_x) * TILE_H;
         const int ox = tx0 + col;
-        unsigned active = 0;
+        uint32_t pix[PIX_PER_THREAD];
 #pragma unroll
-        for (int i = 0; i < PIX_PER_THREAD; ++i)
-            active |= (unsigned)((ox < a.cw) && (ty0 + row0 + i < a.ch)) << i;
-        const uint8_t* pixbase = planes + row0 * g.RS + col;
+        for (int i = 0; i < PIX_PER_THREAD; ++i) pix[i] = tiles_s + buf * tile_bytes + (row0 + i) * g.RS + col;
 
         double p[PIX_PER_THREAD];
 #pragma unroll
         for (int i = 0; i < PIX_PER_THREAD; ++i) p[i] = 0.0;
-        traverse_forest(f0n, f0l, f0t, a.f0.n_trees, pixbase, g.RS, p);
+        traverse_forest<FOREST_SMEM>(f0n_s, f0l_s - f0n_s, f0n_g, f0l_g, f0t, a.f0.n_trees, a.top0, pix, p);
         const double T0 = (double)a.f0.n_trees;
 #pragma unroll
         for (int i = 0; i < PIX_PER_THREAD; ++i) p[i] = __ddiv_rn(p[i], T0);
@@ -319,195 +510,113 @@ __global__ void __launch_bounds__(NTHREADS) score_kernel(const ScoreArgs a) {
             double q[PIX_PER_THREAD];
 #pragma unroll
             for (int i = 0; i < PIX_PER_THREAD; ++i) q[i] = 0.0;
-            traverse_forest(f1n, f1l, f1t, a.f1.n_trees, pixbase, g.RS, q);
+            traverse_forest<FOREST_SMEM>(f1n_s, f1l_s - f1n_s, f1n_g, f1l_g, f1t, a.f1.n_trees, a.top1, pix, q);
             const double T1 = (double)a.f1.n_trees;
 #pragma unroll
             for (int i = 0; i < PIX_PER_THREAD; ++i) p[i] = blend2(p[i], __ddiv_rn(q[i], T1), a.w0, a.w1);
         }
+        double e[PIX_PER_THREAD];
 #pragma unroll
-        for (int i = 0; i < PIX_PER_THREAD; ++i)
-            if ((active >> i) & 1u) a.p1_out[(size_t)(ty0 + row0 + i) * a.cw + ox] = p[i];
-
+        for (int i = 0; i < PIX_PER_THREAD; ++i) e[i] = 0.0;
         if (a.novelty) {
-            double e[PIX_PER_THREAD];
-#pragma unroll
-            for (int i = 0; i < PIX_PER_THREAD; ++i) e[i] = 0.0;
-            novelty_error(p0c, p0c255, p0m, a.pca0.mean_dot_comp, sp, g, pixbase, e);
+            novelty_error(p0c, p0c255, p0m, a.pca0.mean_dot_comp, sp, g, pix, e);
             if (a.blend) {
                 double e1[PIX_PER_THREAD];
 #pragma unroll
                 for (int i = 0; i < PIX_PER_THREAD; ++i) e1[i] = 0.0;
-                novelty_error(p1c, p1c255, p1m, a.pca1.mean_dot_comp, sp, g, pixbase, e1);
+                novelty_error(p1c, p1c255, p1m, a.pca1.mean_dot_comp, sp, g, pix, e1);
 #pragma unroll
                 for (int i = 0; i < PIX_PER_THREAD; ++i) e[i] = blend2(e[i], e1[i], a.w0, a.w1);
             }
+        }
+        // ---- epilogue: P(fg) [, err] to HBM and the per-label sums (K2 fused here) --------------
 #pragma unroll
-            for (int i = 0; i < PIX_PER_THREAD; ++i)
-                if ((active >> i) & 1u) a.sa_out[(size_t)(ty0 + row0 + i) * a.cw + ox] = e[i];
-        }
-        __syncthreads();   // planes / raw are rewritten by the next tile
-    }
-}
-
-// K2 -----------------------------------------------------------------------------
-// d = p1 - (max(sa, thr) - thr) per pixel (:237); per label: sum d, sum |d|, area,
-// first/last row.  One pixel per lane; lanes with equal labels are combined with
-// shuffles so that a warp issues one set of atomics per distinct label.
-struct SegArgs {
-    const double* p1;
-    const double* sa;          // nullptr when novelty is off (sa == 0, thr == 0)
-    const int32_t* labels;
-    int n_px, cw, n_labels;
-    double thr;
-    double* sum;               // [S]
-    double* asum;              // [S]
-    int* area;                 // [S]
-    int* rmin;                 // [S] init INT_MAX
-    int* rmax;                 // [S] init -1
-    int* err;                  // set to 1 on an out-of-range label
-};
-
-__device__ __forceinline__ double contribution(double p1, double sa, double thr) {
-    return __dsub_rn(p1, __dsub_rn(fmax(sa, thr), thr));
-}
-
-__global__ void __launch_bounds__(256) segment_reduce_kernel(const SegArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int n_warps_total = (gridDim.x * blockDim.x) >> 5;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    for (int base = warp_global * 32; base < a.n_px; base += n_warps_total * 32) {
-        const int idx = base + lane;
-        const bool in = idx < a.n_px;
-        int lab = -1;
-        double d = 0.0;
-        int row = 0;
-        if (in) {
-            lab = a.labels[idx];
-            if (lab < 0 || lab >= a.n_labels) { *a.err = 1; lab = -1; }
-            else {
-                d = contribution(a.p1[idx], a.sa ? a.sa[idx] : 0.0, a.thr);
-                row = idx / a.cw;
+        for (int i = 0; i < PIX_PER_THREAD; ++i) {
+            const int oy = ty0 + row0 + i;
+            const bool in = (ox < a.cw) && (oy < a.ch);
+            int lab = -1;
+            if (in) {
+                const size_t o = (size_t)oy * a.cw + ox;
+                a.p1_out[o] = p[i];
+                if (a.novelty) a.sa_out[o] = e[i];
+                lab = a.seg.labels[o];
+                if (lab < 0 || lab >= a.seg.n_labels) { *a.seg.err = 1; lab = -1; }
             }
+            segment_accumulate(a.seg, lab, contribution(p[i], e[i], a.seg.thr), oy);
         }
-        unsigned todo = __ballot_sync(0xffffffffu, lab >= 0);
-        while (todo) {
-            const int leader = __ffs(todo) - 1;
-            const int L = __shfl_sync(0xffffffffu, lab, leader);
-            const bool mine = (lab == L);
-            const unsigned members = __ballot_sync(0xffffffffu, mine);
-            double s = mine ? d : 0.0, as = mine ? fabs(d) : 0.0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-                as += __shfl_xor_sync(0xffffffffu, as, o);
-            }
-            const int r0 = __reduce_min_sync(0xffffffffu, mine ? row : 0x7fffffff);
-            const int r1 = __reduce_max_sync(0xffffffffu, mine ? row : -1);
-            if (lane == leader) {
-                atomicAdd(a.sum + L, s);
-                atomicAdd(a.asum + L, as);
-                atomicAdd(a.area + L, __popc(members));
-                atomicMin(a.rmin + L, r0);
-                atomicMax(a.rmax + L, r1);
-            }
-            todo &= ~members;
-        }
+        __syncthreads();   // tile buffer `buf` may be refilled; sched[buf^1] is visible
     }
 }
 
 // K2b ----------------------------------------------------------------------------
 // score = f32( (acc/area) * (1-w) + prior * w ) > 0.5 (:241-242), acc being the
 // reference's sequential float32 accumulator.  The parallel float64 sum differs from
-// it by at most 2^-24 * sum|d| per unit area; labels whose score is that close to
-// 0.5 are queued for the exact path (K2c), every other label is decided here.
+// it by at most 2^-24 * sum|d| per unit area; a label whose score is that close to
+// 0.5 is re-evaluated EXACTLY by its warp: float32 accumulator, each `+=` evaluated in
+// float64 and rounded to float32, pixels in raster order (:235-238).
 struct DecideArgs {
+    const double* p1;
+    const double* sa;          // nullptr when novelty is off
+    const int32_t* labels;
+    int cw;
+    double thr;
     const double* sum;
     const double* asum;
     const int* area;
+    const int* rmin;
+    const int* rmax;
     const float* priors;       // nullptr -> all -1
     int n_labels;
     double prior_weight;
     uint8_t* decision;         // [S] 0/1
     float* scores;             // [S]
-    int* flagged;              // [S] queue
-    int* n_flagged;
+    int* n_flagged;            // number of labels that took the exact path
 };
 
 __global__ void __launch_bounds__(256) segment_decide_kernel(const DecideArgs a) {
+    const int lane = threadIdx.x & 31;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.n_labels) return;
-    const int area = a.area[s];
-    if (area <= 0) { a.decision[s] = 0; a.scores[s] = 0.f; return; }
     const double w = a.prior_weight;
-    const double prior = a.priors ? (double)a.priors[s] : -1.0;
     const double omw = __dsub_rn(1.0, w);
-    const double sc = __dadd_rn(__dmul_rn(__ddiv_rn(a.sum[s], (double)area), omw), __dmul_rn(prior, w));
-    const double band = 2.0 * 5.9604644775390625e-08 * (a.asum[s] / (double)area) * fabs(omw) + 2.4e-7;
-    if (fabs(sc - 0.5) <= band) {
-        a.flagged[atomicAdd(a.n_flagged, 1)] = s;
-        a.decision[s] = 0;
-    } else {
-        a.decision[s] = sc > 0.5;
-    }
-    a.scores[s] = (float)sc;
-}
-
-// K2c ----------------------------------------------------------------------------
-// Exact compileSaliencyMap accumulation for one label: float32 accumulator, each
-// `+=` evaluated in float64 and rounded to float32, pixels in raster order (:235-238).
-struct ResolveArgs {
-    const double* p1;
-    const double* sa;
-    const int32_t* labels;
-    int cw;
-    double thr;
-    const int* area;
-    const int* rmin;
-    const int* rmax;
-    const float* priors;
-    double prior_weight;
-    const int* flagged;
-    const int* n_flagged;
-    uint8_t* decision;
-    float* scores;
-};
-
-__global__ void __launch_bounds__(256) segment_resolve_kernel(const ResolveArgs a) {
-    __shared__ double buf[256];
-    __shared__ int warp_count[8];
-    const int n = *a.n_flagged;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int q = blockIdx.x; q < n; q += gridDim.x) {
-        const int L = a.flagged[q];
-        const int lo = a.rmin[L] * a.cw, hi = (a.rmax[L] + 1) * a.cw;
-        float acc = 0.f;
-        for (int base = lo; base < hi; base += 256) {
-            const int idx = base + threadIdx.x;
-            const bool mine = (idx < hi) && (a.labels[idx] == L);
-            const unsigned bal = __ballot_sync(0xffffffffu, mine);
-            if (lane == 0) warp_count[warp] = __popc(bal);
-            __syncthreads();
-            int off = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                if (w < warp) off += warp_count[w];
-                total += warp_count[w];
-            }
-            if (mine)
-                buf[off + __popc(bal & ((1u << lane) - 1u))] =
-                    contribution(a.p1[idx], a.sa ? a.sa[idx] : 0.0, a.thr);
-            __syncthreads();
-            if (threadIdx.x == 0)
-                for (int i = 0; i < total; ++i) acc = __double2float_rn(__dadd_rn((double)acc, buf[i]));
-            __syncthreads();
+    bool flagged = false;
+    int area = 0;
+    double prior = -1.0;
+    if (s < a.n_labels) {
+        area = a.area[s];
+        if (area <= 0) { a.decision[s] = 0; a.scores[s] = 0.f; }
+        else {
+            prior = a.priors ? (double)a.priors[s] : -1.0;
+            const double sc = __dadd_rn(__dmul_rn(__ddiv_rn(a.sum[s], (double)area), omw), __dmul_rn(prior, w));
+            const double band = 2.0 * 5.9604644775390625e-08 * (a.asum[s] / (double)area) * fabs(omw) + 2.4e-7;
+            flagged = fabs(sc - 0.5) <= band;
+            a.decision[s] = sc > 0.5;
+            a.scores[s] = (float)sc;
         }
-        if (threadIdx.x == 0) {
-            const double w = a.prior_weight;
-            const double prior = a.priors ? (double)a.priors[L] : -1.0;
-            const float sc = __double2float_rn(__dadd_rn(
-                __dmul_rn(__ddiv_rn((double)acc, (double)a.area[L]), __dsub_rn(1.0, w)), __dmul_rn(prior, w)));
-            a.scores[L] = sc;
-            a.decision[L] = sc > 0.5f;
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, flagged);
+    if (todo && lane == 0) atomicAdd(a.n_flagged, __popc(todo));
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int L = __shfl_sync(0xffffffffu, s, src);
+        const int lo = a.rmin[L] * a.cw, hi = (a.rmax[L] + 1) * a.cw;
+        float acc = 0.f;   // identical in every lane
+        for (int base = lo; base < hi; base += 32) {
+            const int idx = base + lane;
+            const bool mine = (idx < hi) && (a.labels[idx] == L);
+            const double d = mine ? contribution(a.p1[idx], a.sa ? a.sa[idx] : 0.0, a.thr) : 0.0;
+            unsigned m = __ballot_sync(0xffffffffu, mine);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                acc = __double2float_rn(__dadd_rn((double)acc, __shfl_sync(0xffffffffu, d, b)));
+            }
+        }
+        if (lane == src) {
+            const float sc = __double2float_rn(__dadd_rn(__dmul_rn(__ddiv_rn((double)acc, (double)area), omw),
+                                                         __dmul_rn(prior, w)));
+            a.scores[s] = sc;
+            a.decision[s] = sc > 0.5f;
         }
     }
 }

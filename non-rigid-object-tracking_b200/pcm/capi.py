@@ -86,7 +86,7 @@ EXPORTED_SYMBOLS = [
     "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_profile_enable", "pcm_profile_read",
 ]
 
-KERNEL_NAMES = ["score", "segment_reduce", "segment_decide", "segment_resolve", "mask_dilate", "iou"]
+KERNEL_NAMES = ["score", "segment_reduce", "segment_decide", "segment_resolve", "mask_dilate", "iou", "planes"]
 
 
 def _ptr(a):
