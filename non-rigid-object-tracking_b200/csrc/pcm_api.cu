@@ -5,6 +5,7 @@
 // every entry point either runs the CUDA kernels or fails.
 #include "../../include/pcm_b200.h"
 #include "pcm_kernels.cuh"
+#include "pcm_host.h"
 
 #include <cudaTypedefs.h>
 
@@ -732,12 +733,39 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
     CUDA_TRY(h->mask.reserve(npx));
     CUDA_TRY(h->h_small.reserve(64));
     CUDA_TRY(cudaStreamSynchronize(st));   // staging buffers are reused between calls
+    // Row chunks are copied into pinned memory by the host pool and handed to the copy engine
+    // one by one, so the DMA of chunk i overlaps the staging of chunk i+1.
+    HostPool& pool = HostPool::instance();
     uint8_t* hf = h->h_frame.as<uint8_t>();
-    for (int r = 0; r < ch; ++r)
-        memcpy(hf + (size_t)r * row_bytes, frame + (size_t)(cy + r) * stride + (size_t)cx * 3, row_bytes);
-    CUDA_TRY(cudaMemcpyAsync(h->frame.p, hf, npx * 3, cudaMemcpyHostToDevice, st));
-    memcpy(h->h_labels.p, labels, npx * sizeof(int32_t));
-    CUDA_TRY(cudaMemcpyAsync(h->labels.p, h->h_labels.p, npx * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    {
+        const int rows_per_chunk = std::max(1, (int)((1u << 20) / std::max<size_t>(row_bytes, 1)));
+        for (int r0 = 0; r0 < ch; r0 += rows_per_chunk) {
+            const int r1 = std::min(ch, r0 + rows_per_chunk);
+            const int parts = std::min(pool.size(), r1 - r0);
+            pool.parallel_for(parts, [&](int part) {
+                const int a0 = r0 + (int)((long long)(r1 - r0) * part / parts);
+                const int a1 = r0 + (int)((long long)(r1 - r0) * (part + 1) / parts);
+                for (int r = a0; r < a1; ++r)
+                    memcpy(hf + (size_t)r * row_bytes, frame + (size_t)(cy + r) * stride + (size_t)cx * 3, row_bytes);
+            });
+            CUDA_TRY(cudaMemcpyAsync(h->frame.as<uint8_t>() + (size_t)r0 * row_bytes, hf + (size_t)r0 * row_bytes,
+                                     (size_t)(r1 - r0) * row_bytes, cudaMemcpyHostToDevice, st));
+        }
+    }
+    {
+        const size_t total = npx * sizeof(int32_t), chunk = 1u << 20;
+        uint8_t* hl = h->h_labels.as<uint8_t>();
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(labels);
+        for (size_t o = 0; o < total; o += chunk) {
+            const size_t len = std::min(chunk, total - o);
+            const int parts = (int)std::min<size_t>(pool.size(), (len + 65535) / 65536);
+            pool.parallel_for(parts, [&](int part) {
+                const size_t b0 = len * part / parts, b1 = len * (part + 1) / parts;
+                memcpy(hl + o + b0, src + o + b0, b1 - b0);
+            });
+            CUDA_TRY(cudaMemcpyAsync(h->labels.as<uint8_t>() + o, hl + o, len, cudaMemcpyHostToDevice, st));
+        }
+    }
     const float* d_priors = nullptr;
     if (priors) {
         CUDA_TRY(h->h_priors.reserve(sizeof(float) * (size_t)n_labels));
@@ -755,12 +783,18 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
     if (rc) return rc;
     // scatter the dense crop into the caller's (possibly interleaved) mask
     const uint8_t* hm = h->h_mask.as<uint8_t>();
-    for (int r = 0; r < ch; ++r) {
-        uint8_t* dst = mask + (size_t)(cy + r) * mask_row_stride + (size_t)cx * mask_pixel_stride;
-        const uint8_t* src = hm + (size_t)r * cw;
-        if (mask_pixel_stride == 1) memcpy(dst, src, cw);
-        else
-            for (int c = 0; c < cw; ++c) dst[(size_t)c * mask_pixel_stride] = src[c];
+    {
+        const int parts = std::min(pool.size(), std::max(1, (int)(npx >> 16)));
+        pool.parallel_for(parts, [&](int part) {
+            const int a0 = (int)((long long)ch * part / parts), a1 = (int)((long long)ch * (part + 1) / parts);
+            for (int r = a0; r < a1; ++r) {
+                uint8_t* dst = mask + (size_t)(cy + r) * mask_row_stride + (size_t)cx * mask_pixel_stride;
+                const uint8_t* src = hm + (size_t)r * cw;
+                if (mask_pixel_stride == 1) memcpy(dst, src, cw);
+                else
+                    for (int c = 0; c < cw; ++c) dst[(size_t)c * mask_pixel_stride] = src[c];
+            }
+        });
     }
     return PCM_OK;
 }
@@ -771,8 +805,8 @@ extern "C" int pcm_iou_device(pcm_handle* h, const uint8_t* d_mask, int64_t mask
     if (truth_channels != 1 && truth_channels != 3) return fail(PCM_E_INVALID, "pcm_iou_device: truth_channels %d", truth_channels);
     if (height <= 0 || width <= 0) return fail(PCM_E_INVALID, "pcm_iou_device: bad size");
     CUDA_TRY(cudaSetDevice(h->device));
-    const long long chunks = (long long)height * ((width + 31) / 32);
-    const int blocks = (int)std::min<long long>((chunks + 7) / 8, (long long)h->sm_count * 8);
+    const long long work = ((long long)height * width + 15) / 16;
+    const int blocks = (int)std::min<long long>((work + 255) / 256, (long long)h->sm_count * 8);
     {
         KernelTimer kt(h, 5);
         iou_kernel<<<std::max(blocks, 1), 256, 0, h->stream>>>(d_mask, mask_row_stride, d_truth, truth_row_stride,
@@ -800,19 +834,29 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
     CUDA_TRY(h->counts.reserve(2 * sizeof(int64_t)));
     CUDA_TRY(h->h_small.reserve(64));
     CUDA_TRY(cudaStreamSynchronize(st));
+    HostPool& pool = HostPool::instance();
     uint8_t* hm = h->h_mask.as<uint8_t>();
-    for (int r = 0; r < height; ++r) {
-        const uint8_t* src = mask + (size_t)r * mask_row_stride;
-        uint8_t* dst = hm + (size_t)r * width;
-        if (mask_pixel_stride == 1) memcpy(dst, src, width);
-        else
-            for (int c = 0; c < width; ++c) dst[c] = src[(size_t)c * mask_pixel_stride];
-    }
     uint8_t* ht = h->h_frame.as<uint8_t>();
-    for (int r = 0; r < height; ++r)
-        memcpy(ht + (size_t)r * width * truth_channels, truth + (size_t)r * truth_row_stride, (size_t)width * truth_channels);
-    CUDA_TRY(cudaMemcpyAsync(h->mask.p, hm, npx, cudaMemcpyHostToDevice, st));
+    const int parts = std::min(pool.size(), std::max(1, (int)(npx >> 16)));
+    pool.parallel_for(parts, [&](int part) {
+        const int a0 = (int)((long long)height * part / parts), a1 = (int)((long long)height * (part + 1) / parts);
+        for (int r = a0; r < a1; ++r) {
+            memcpy(ht + (size_t)r * width * truth_channels, truth + (size_t)r * truth_row_stride,
+                   (size_t)width * truth_channels);
+        }
+    });
     CUDA_TRY(cudaMemcpyAsync(h->frame.p, ht, tbytes, cudaMemcpyHostToDevice, st));
+    pool.parallel_for(parts, [&](int part) {
+        const int a0 = (int)((long long)height * part / parts), a1 = (int)((long long)height * (part + 1) / parts);
+        for (int r = a0; r < a1; ++r) {
+            const uint8_t* src = mask + (size_t)r * mask_row_stride;
+            uint8_t* dst = hm + (size_t)r * width;
+            if (mask_pixel_stride == 1) memcpy(dst, src, width);
+            else
+                for (int c = 0; c < width; ++c) dst[c] = src[(size_t)c * mask_pixel_stride];
+        }
+    });
+    CUDA_TRY(cudaMemcpyAsync(h->mask.p, hm, npx, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(h->counts.p, 0, 2 * sizeof(int64_t), st));
     int rc = pcm_iou_device(h, h->mask.as<uint8_t>(), width, h->frame.as<uint8_t>(), (int64_t)width * truth_channels,
                             truth_channels, height, width, h->counts.as<int64_t>());

@@ -12,16 +12,25 @@ namespace pcm {
 
 // ---- tile geometry of the fused score kernel ---------------------------------
 constexpr int TILE_W = 64;            // output pixels per tile row
-constexpr int TILE_H = 32;            // output rows per tile
-constexpr int NTHREADS = 256;         // 8 warps: warp = (row group, 32-column half)
-constexpr int PIX_PER_THREAD = 8;     // rows of one column handled by a thread
+#ifndef PCM_TILE_H
+#define PCM_TILE_H 32
+#endif
+constexpr int TILE_H = PCM_TILE_H;    // output rows per tile
+#ifndef PCM_NTHREADS
+#define PCM_NTHREADS 256
+#endif
+#ifndef PCM_MIN_CTAS
+#define PCM_MIN_CTAS 2
+#endif
+constexpr int NTHREADS = PCM_NTHREADS;   // warp = (row group, 32-column half of the tile)
+constexpr int PIX_PER_THREAD = TILE_H / (NTHREADS / 64);   // rows of one column handled by a thread
 constexpr int MAX_NEIGHBORS = 16;
 constexpr int MAX_SPACES = 3;
 constexpr int LAB_CBRT_SIZE = 2041;
 constexpr int LAB_CBRT_PAD = 2048;
 
-static_assert(TILE_W == 64 && TILE_H == 32 && NTHREADS == 256 && PIX_PER_THREAD == 8,
-              "thread mapping below assumes 8 warps x (4 row groups x 2 halves)");
+static_assert(TILE_W == 64 && (NTHREADS / 64) * PIX_PER_THREAD == TILE_H && NTHREADS % 64 == 0,
+              "thread mapping: NTHREADS/64 row groups x 2 column halves, PIX_PER_THREAD rows each");
 
 // Lookup tables built on the host at pcm_create (pcm_api.cu: build_tables).
 struct ColorTables {

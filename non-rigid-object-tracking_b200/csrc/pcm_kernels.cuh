@@ -104,10 +104,22 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
         uint32_t out[3 * MAX_SPACES + 1];
 #pragma unroll
         for (int p = 0; p < 3 * MAX_SPACES + 1; ++p) out[p] = 0;
+        // 4 pixels = 12 bytes: three aligned words when possible, byte loads otherwise
+        uint32_t w3[3] = {0u, 0u, 0u};
+        if (c0 + 3 < a.cw && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) w3[q] = __ldg(reinterpret_cast<const uint32_t*>(src) + q);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 12; ++q)
+                if (c0 + q / 3 < a.cw) w3[q / 4] |= (uint32_t)__ldg(src + q) << (8 * (q % 4));
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (c0 + j < a.cw) {
-                const int b = __ldg(src + 3 * j), gg = __ldg(src + 3 * j + 1), rr = __ldg(src + 3 * j + 2);
+                const int b = (w3[(3 * j) / 4] >> (8 * ((3 * j) % 4))) & 0xff;
+                const int gg = (w3[(3 * j + 1) / 4] >> (8 * ((3 * j + 1) % 4))) & 0xff;
+                const int rr = (w3[(3 * j + 2) / 4] >> (8 * ((3 * j + 2) % 4))) & 0xff;
 #pragma unroll
                 for (int q = 0; q < MAX_SPACES; ++q) {
                     if (q < a.g.n_spaces) {
@@ -353,7 +365,10 @@ __device__ __forceinline__ double blend2(double a, double b, double w0, double w
     return __ddiv_rn(__dadd_rn(__dmul_rn(a, w0), __dmul_rn(b, w1)), __dadd_rn(w0, w1));
 }
 
-constexpr int N_TILE_BUF = 2;
+#ifndef PCM_TILE_BUFS
+#define PCM_TILE_BUFS 2
+#endif
+constexpr int N_TILE_BUF = PCM_TILE_BUFS;   // 2: TMA of tile i+1 overlaps scoring of tile i; 1: rely on co-resident CTAs
 
 struct ScoreSmem {
     uint32_t tiles, bars, sched, sp, f0_nodes, f0_leaves, f0_trees, f1_nodes, f1_leaves, f1_trees, pca0, pca1, total;
@@ -410,7 +425,7 @@ __device__ __forceinline__ void stage_nodes(uint8_t* dst, const uint2* __restric
 // Persistent CTAs; tiles are handed out by an atomic counter and arrive through a
 // two-stage TMA pipeline (the box of tile i+1 is in flight while tile i is scored).
 template <bool FOREST_SMEM>
-__global__ void __launch_bounds__(NTHREADS, 2) score_kernel(const __grid_constant__ CUtensorMap tmap, const ScoreArgs a) {
+__global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __grid_constant__ CUtensorMap tmap, const ScoreArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const Geom& g = a.g;
     const ScoreSmem L = score_smem_layout(g, a.f0, a.f1, a.blend != 0, a.novelty != 0, FOREST_SMEM);
@@ -438,7 +453,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) score_kernel(const __grid_constan
         for (int b = 0; b < N_TILE_BUF; ++b) mbar_init(bars_s + 8 * b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(0);
+        if (N_TILE_BUF > 1) issue(0);
     }
 
     // ---- once per CTA: tap offsets, forests, PCA vectors -> smem (overlaps the first TMA) ----
@@ -486,10 +501,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) score_kernel(const __grid_constan
     const int col = (warp & 1) * 32 + lane;
     const int row0 = (warp >> 1) * PIX_PER_THREAD;
     uint32_t phase = 0;   // bit b = parity to wait for on buffer b
-    for (int buf = 0;; buf ^= 1) {
+    for (int buf = 0;; buf = (N_TILE_BUF > 1) ? (buf ^ 1) : 0) {
+        if (N_TILE_BUF == 1) {
+            if (tid == 0) issue(0);
+            __syncthreads();
+        }
         const int tile = sched[buf];
         if (tile >= n_tiles) break;
-        if (tid == 0) issue(buf ^ 1);            // buffer buf^1 was released by the barrier below
+        if (N_TILE_BUF > 1 && tid == 0) issue(buf ^ 1);   // buffer buf^1 was released by the barrier below
         mbar_wait(bars_s + 8 * buf, (phase >> buf) & 1u);
         phase ^= 1u << buf;
 
@@ -634,71 +653,110 @@ struct DilateArgs {
     uint8_t* pre;              // optional [ch*cw] pre-dilation map
 };
 
-constexpr int DIL_TW = 64, DIL_TH = 32, DIL_MAXK = 33;
+constexpr int DIL_TW = 128, DIL_TH = 16, DIL_MAXK = 33;
 
+// One block = 128 x 16 output pixels.  Stage 1 gathers decision[label] for the tile plus its
+// k-1 halo (all label loads of a thread are issued before the dependent decision loads),
+// stage 2 ORs along rows, stage 3 ORs along columns and writes 4 pixels per thread.
 __global__ void __launch_bounds__(256) mask_dilate_kernel(const DilateArgs a) {
-    __shared__ uint8_t s0[(DIL_TH + DIL_MAXK) * (DIL_TW + DIL_MAXK)];
-    __shared__ uint8_t s1[(DIL_TH + DIL_MAXK) * DIL_TW];
+    __shared__ __align__(16) uint8_t s0[(DIL_TH + DIL_MAXK) * (DIL_TW + DIL_MAXK + 3)];
+    __shared__ __align__(16) uint8_t s1[(DIL_TH + DIL_MAXK) * DIL_TW];
     const int k = a.k, before = k / 2, SW = DIL_TW + k - 1, SH = DIL_TH + k - 1;
     const int tx0 = blockIdx.x * DIL_TW, ty0 = blockIdx.y * DIL_TH;
-    for (int i = threadIdx.x; i < SW * SH; i += blockDim.x) {
-        const int r = i / SW, c = i - r * SW;
-        const int y = ty0 - before + r, x = tx0 - before + c;
-        uint8_t v = 0;
-        if (y >= 0 && y < a.ch && x >= 0 && x < a.cw) {
-            const int lab = a.labels[(size_t)y * a.cw + x];
-            v = (lab >= 0 && lab < a.n_labels) ? a.decision[lab] : 0;
-            if (a.pre && r >= before && r < before + DIL_TH && c >= before && c < before + DIL_TW)
-                a.pre[(size_t)y * a.cw + x] = v ? 255 : 0;
+    constexpr int B = 4;
+    for (int i0 = threadIdx.x; i0 < SW * SH; i0 += B * 256) {
+        int lab[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int i = i0 + j * 256;
+            lab[j] = -1;
+            if (i < SW * SH) {
+                const int r = i / SW, c = i - r * SW;
+                const int y = ty0 - before + r, x = tx0 - before + c;
+                if (y >= 0 && y < a.ch && x >= 0 && x < a.cw) lab[j] = __ldg(a.labels + (size_t)y * a.cw + x);
+            }
         }
-        s0[i] = v;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int i = i0 + j * 256;
+            if (i < SW * SH) {
+                const uint8_t v = (lab[j] >= 0 && lab[j] < a.n_labels) ? __ldg(a.decision + lab[j]) : 0;
+                s0[i] = v;
+                if (a.pre && lab[j] >= 0) {
+                    const int r = i / SW, c = i - r * SW;
+                    if (r >= before && r < before + DIL_TH && c >= before && c < before + DIL_TW)
+                        a.pre[(size_t)(ty0 - before + r) * a.cw + (tx0 - before + c)] = v ? 255 : 0;
+                }
+            }
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < SH * DIL_TW; i += blockDim.x) {
+    for (int i = threadIdx.x; i < SH * DIL_TW; i += 256) {
         const int r = i / DIL_TW, c = i - r * DIL_TW;
         uint8_t v = 0;
         for (int d = 0; d < k; ++d) v |= s0[r * SW + c + d];
         s1[i] = v;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < DIL_TH * DIL_TW; i += blockDim.x) {
-        const int r = i / DIL_TW, c = i - r * DIL_TW;
+    for (int i = threadIdx.x; i < DIL_TH * DIL_TW / 4; i += 256) {
+        const int r = i / (DIL_TW / 4), c = (i - r * (DIL_TW / 4)) * 4;
         const int y = ty0 + r, x = tx0 + c;
-        if (y < a.ch && x < a.cw) {
-            uint8_t v = 0;
-            for (int d = 0; d < k; ++d) v |= s1[(r + d) * DIL_TW + c];
-            a.mask[(size_t)(a.cy + y) * a.mask_stride + (a.cx + x)] = v ? 255 : 0;
-        }
+        if (y >= a.ch || x >= a.cw) continue;
+        uint32_t v = 0;
+        for (int d = 0; d < k; ++d) v |= *reinterpret_cast<const uint32_t*>(s1 + (r + d) * DIL_TW + c);
+        // bytes are 0/1 -> 0/255
+        v = (v & 0x01010101u) * 255u;
+        uint8_t* dst = a.mask + (size_t)(a.cy + y) * a.mask_stride + (a.cx + x);
+        if (x + 3 < a.cw && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) *reinterpret_cast<uint32_t*>(dst) = v;
+        else
+            for (int j = 0; j < 4 && x + j < a.cw; ++j) dst[j] = (uint8_t)(v >> (8 * j));
     }
 }
 
 // K5 -----------------------------------------------------------------------------
 // counts[0] += #(m != 0 && t != 0), counts[1] += #(m != 0 || t != 0) (benchmark.py:12-13);
 // truth either gray or BGR (converted like cv.cvtColor(BGR2GRAY), main.py:285).
+// Gray truth with 16-byte aligned rows is read 16 pixels per thread.
 __global__ void __launch_bounds__(256) iou_kernel(const uint8_t* __restrict__ mask, long long mask_stride,
                                                   const uint8_t* __restrict__ truth, long long truth_stride,
                                                   int truth_channels, int h, int w,
                                                   unsigned long long* __restrict__ counts) {
     unsigned inter = 0, uni = 0;
-    const int chunks_per_row = (w + 31) / 32;
-    const long long n_chunks = (long long)h * chunks_per_row;
-    const int lane = threadIdx.x & 31;
-    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long ch = warp_global; ch < n_chunks; ch += n_warps) {
-        const int r = (int)(ch / chunks_per_row);
-        const int c = (int)(ch - (long long)r * chunks_per_row) * 32 + lane;
-        bool m = false, t = false;
-        if (c < w) {
-            m = mask[(size_t)r * mask_stride + c] != 0;
-            const uint8_t* tp = truth + (size_t)r * truth_stride + (size_t)c * truth_channels;
-            t = (truth_channels == 3) ? (bgr2gray_px(tp[0], tp[1], tp[2]) != 0) : (tp[0] != 0);
+    const bool vec = truth_channels == 1 && (w % 16 == 0) && (mask_stride % 16 == 0) && (truth_stride % 16 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(truth)) & 15) == 0;
+    if (vec) {
+        const int per_row = w / 16;
+        const long long n = (long long)h * per_row;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            const int r = (int)(i / per_row), c = (int)(i - (long long)r * per_row) * 16;
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(mask + (size_t)r * mask_stride + c));
+            const uint4 t = __ldg(reinterpret_cast<const uint4*>(truth + (size_t)r * truth_stride + c));
+            const uint32_t mm[4] = {m.x, m.y, m.z, m.w}, tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t a = __vcmpne4(mm[j], 0u), b = __vcmpne4(tt[j], 0u);   // 0xff per non-zero byte
+                inter += __popc(a & b) >> 3;
+                uni += __popc(a | b) >> 3;
+            }
         }
-        inter += __popc(__ballot_sync(0xffffffffu, m && t));
-        uni += __popc(__ballot_sync(0xffffffffu, m || t));
+    } else {
+        const long long n = (long long)h * w;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            const int r = (int)(i / w), c = (int)(i - (long long)r * w);
+            const bool m = mask[(size_t)r * mask_stride + c] != 0;
+            const uint8_t* tp = truth + (size_t)r * truth_stride + (size_t)c * truth_channels;
+            const bool t = (truth_channels == 3) ? (bgr2gray_px(tp[0], tp[1], tp[2]) != 0) : (tp[0] != 0);
+            inter += m && t;
+            uni += m || t;
+        }
     }
-    // every lane of a warp holds the same totals; one atomic pair per block
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        inter += __shfl_xor_sync(0xffffffffu, inter, o);
+        uni += __shfl_xor_sync(0xffffffffu, uni, o);
+    }
     __shared__ unsigned s_i[8], s_u[8];
+    const int lane = threadIdx.x & 31;
     if (lane == 0) { s_i[threadIdx.x >> 5] = inter; s_u[threadIdx.x >> 5] = uni; }
     __syncthreads();
     if (threadIdx.x == 0) {
