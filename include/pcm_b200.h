@@ -113,7 +113,10 @@ typedef struct pcm_update_params {
 /* One `update()` (:45-112) on HOST buffers, synchronous:
  *   frame     H x W x 3 BGR, rows frame_stride bytes apart; not modified
  *   rect      crop {x, y, w, h} from pcm_crop_rect
- *   labels    h*w int32 over-segmentation labels of the crop, values in [0, n_labels)
+ *   labels    h*w int32 over-segmentation labels of the crop, values in [0, n_labels);
+ *             n_labels <= 0: taken as max(label) + 1 (found while the map is staged;
+ *             only without priors).  Label chunks identical to the previous call's are
+ *             not re-sent to the device.
  *   priors    n_labels float32 (computePriors :129-163) or NULL for all -1
  *   mask      first byte of the channel to write (the reference writes channel 2
  *             of an H x W x 3 image: mask + 2, mask_pixel_stride = 3); only the
@@ -159,13 +162,17 @@ int pcm_convert(pcm_handle* h, const uint8_t* bgr, int height, int width, int64_
 int pcm_gather_features(pcm_handle* h, const uint8_t* frame, int frame_h, int frame_w, int64_t frame_stride,
                         const int rect[4], int16_t* X);
 
+/* Keep the per-stage buffers that only the parity taps need (today: the 0/255 map before
+ * dilation, one extra byte per pixel written by the dilation kernel).  Off by default. */
+int pcm_set_debug(pcm_handle* h, int on);
+
 /* Stage dumps of the LAST pcm_update / pcm_update_device on this handle
  * (any pointer may be NULL):
  *   p1[h*w]       blended P(foreground) (:80-95), float64
  *   sa[h*w]       blended novelty error (:57-63, :88-93), float64 (zeros if off)
  *   scores[S]     per-label score as the reference's float32 (:241)
  *   areas[S]      per-label pixel counts (:97)
- *   pre[h*w]      0/255 map before dilation (:242-246)
+ *   pre[h*w]      0/255 map before dilation (:242-246); needs pcm_set_debug(h, 1)
  *   n_exact       number of labels decided by the exact sequential-f32 path */
 int pcm_debug_last(pcm_handle* h, double* p1, double* sa, float* scores, int64_t* areas,
                    uint8_t* pre, int32_t* n_exact);

@@ -10,6 +10,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -19,6 +20,11 @@
 #include <vector>
 
 using namespace pcm;
+
+namespace pcm {   // pcm_host_simd.cpp
+void gather_strided(const uint8_t* src, int64_t stride, uint8_t* dst, int n);
+void scatter_strided(const uint8_t* src, uint8_t* dst, int64_t stride, int n);
+}
 
 // ---------------------------------------------------------------------------------
 // errors
@@ -42,6 +48,38 @@ static int fail(int code, const char* fmt, ...) {
             return fail(PCM_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
                         __FILE__, __LINE__);                                                 \
     } while (0)
+
+// ---------------------------------------------------------------------------------
+// PCM_TRACE=1: wall-clock breakdown of the host-buffer entry points, printed at pcm_destroy
+// ---------------------------------------------------------------------------------
+#include <chrono>
+static bool trace_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PCM_TRACE"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+struct HostTrace {
+    enum { UPD_SYNC, UPD_STAGE, UPD_ENQUEUE, UPD_WAIT, UPD_SCATTER, IOU_STAGE, IOU_WAIT, N };
+    double ms[N] = {0};
+    long calls[N] = {0};
+    std::chrono::steady_clock::time_point t;
+    void start() { if (trace_enabled()) t = std::chrono::steady_clock::now(); }
+    void lap(int id) {
+        if (!trace_enabled()) return;
+        auto now = std::chrono::steady_clock::now();
+        ms[id] += std::chrono::duration<double, std::milli>(now - t).count();
+        calls[id]++;
+        t = now;
+    }
+    void report() const {
+        if (!trace_enabled()) return;
+        static const char* names[N] = {"update: reserve+sync", "update: stage+H2D issue", "update: enqueue kernels",
+                                       "update: wait (H2D, kernels, D2H)", "update: scatter mask", "iou: stage+H2D issue",
+                                       "iou: kernel+D2H wait"};
+        for (int i = 0; i < N; ++i)
+            if (calls[i]) fprintf(stderr, "[pcm trace] %-34s %8.3f ms/call over %ld calls\n", names[i], ms[i] / calls[i], calls[i]);
+    }
+};
 
 // ---------------------------------------------------------------------------------
 // grow-only buffers
@@ -121,10 +159,18 @@ struct pcm_handle {
     // pinned staging (host)
     PinBuf h_frame, h_labels, h_priors, h_mask, h_small;
 
+    // host-path label cache: h_labels / labels hold the label map of the previous pcm_update
+    // (label_cache_px elements, 1 MiB chunks); a chunk whose bytes are unchanged is not re-sent
+    size_t label_cache_px = 0;
+    std::vector<int> label_chunk_max;
+
     // description of the last update (for pcm_debug_last)
     int last_cw = 0, last_ch = 0, last_S = 0;
     bool last_novelty = false;
     bool last_valid = false;
+    bool last_pre = false;
+    bool keep_pre = false;        // pcm_set_debug: K3 also writes the pre-dilation map
+    HostTrace trace;
 };
 
 // seg buffer layout: [sum S f64][asum S f64][area S i32][n_flagged i32][err i32]
@@ -244,7 +290,7 @@ static int int_threshold(double thr) {
 }
 
 struct EncTree {
-    std::vector<uint2> nodes;     // entries (see pcm_kernels.cuh): y = entry INDEX of the left child here
+    std::vector<NodeT> nodes;     // entries (see pcm_kernels.cuh): left = entry INDEX of the left child here
     std::vector<double> values;   // parallel: class-1 fraction of leaf entries
     int n_leaf = 0;
     int depth = 0;
@@ -280,7 +326,7 @@ struct Encoder {
         struct Item { int node, entry, depth; };
         std::vector<Item> queue;
         queue.push_back({skip(0), 0, 0});
-        out.nodes.assign(1, make_uint2(0, 0));
+        out.nodes.assign(1, make_node(0, 0, 0));
         out.values.assign(1, 0.0);
         const int vplane = 3 * g.n_spaces;
         size_t visited = 0;
@@ -289,7 +335,7 @@ struct Encoder {
             if (++visited > (size_t)n + 1) { err = "tree is not a tree"; return false; }
             const int i = it.node;
             if (left[i] == -1) {
-                out.nodes[it.entry] = make_uint2(0x0000ffffu, (unsigned)it.entry);
+                out.nodes[it.entry] = make_node(0u, LEAF_THR, (unsigned)it.entry);
                 out.values[it.entry] = value1[i];
                 out.n_leaf++;
                 out.depth = std::max(out.depth, it.depth);
@@ -305,9 +351,9 @@ struct Encoder {
             const unsigned off = (unsigned)(plane * g.PS + (dr + g.n) * g.RS + (dc + g.HX));
             if (off >= (1u << 16)) { err = "tap offset overflow"; return false; }
             const int child = (int)out.nodes.size();
-            out.nodes.resize(child + 2, make_uint2(0, 0));
+            out.nodes.resize(child + 2, make_node(0, 0, 0));
             out.values.resize(child + 2, 0.0);
-            out.nodes[it.entry] = make_uint2((off << 16) | (unsigned)thr, (unsigned)child);
+            out.nodes[it.entry] = make_node(off, (unsigned)thr, (unsigned)child);
             queue.push_back({skip(left[i]), child, it.depth + 1});
             queue.push_back({skip(right[i]), child + 1, it.depth + 1});
         }
@@ -326,6 +372,32 @@ static void free_model(Model& m) {
 // ---------------------------------------------------------------------------------
 // API: lifetime
 // ---------------------------------------------------------------------------------
+// K1 instantiations: forest in shared memory or behind L1, walk depth fixed at compile time
+// for the depths the reference's configs use (config.yaml:26 -> 5; benchmark.py:44 -> 7, 10)
+// or taken from the arguments (DEPTH = 0).
+typedef void (*ScoreFn)(const CUtensorMap, const ScoreArgs);
+struct ScoreVariant { bool smem; int depth; ScoreFn fn; const char* name; };
+constexpr int N_SCORE_VARIANTS = 8;
+static const ScoreVariant& score_variant(int i) {
+    static const ScoreVariant v[N_SCORE_VARIANTS] = {
+        {true, 5, score_kernel<true, 5>, "score_kernel<smem,5>"},   {true, 7, score_kernel<true, 7>, "score_kernel<smem,7>"},
+        {true, 10, score_kernel<true, 10>, "score_kernel<smem,10>"}, {true, 0, score_kernel<true, 0>, "score_kernel<smem,dyn>"},
+        {false, 5, score_kernel<false, 5>, "score_kernel<global,5>"}, {false, 7, score_kernel<false, 7>, "score_kernel<global,7>"},
+        {false, 10, score_kernel<false, 10>, "score_kernel<global,10>"}, {false, 0, score_kernel<false, 0>, "score_kernel<global,dyn>"},
+    };
+    return v[i];
+}
+static const ScoreVariant& pick_score_variant(bool smem, int depth) {
+    int dyn = -1;
+    for (int i = 0; i < N_SCORE_VARIANTS; ++i) {
+        const ScoreVariant& v = score_variant(i);
+        if (v.smem != smem) continue;
+        if (v.depth == depth) return v;
+        if (v.depth == 0) dyn = i;
+    }
+    return score_variant(dyn);
+}
+
 extern "C" int pcm_abi_version(void) { return PCM_ABI_VERSION; }
 extern "C" const char* pcm_last_error(void) { return g_last_error.c_str(); }
 
@@ -358,14 +430,15 @@ extern "C" int pcm_create(int device, pcm_handle** out) {
     build_tables(h->h_tables);
     CUDA_TRY(cudaMalloc(&h->d_tables, sizeof(ColorTables)));
     CUDA_TRY(cudaMemcpy(h->d_tables, &h->h_tables, sizeof(ColorTables), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-    CUDA_TRY(cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+    for (int i = 0; i < N_SCORE_VARIANTS; ++i)
+        CUDA_TRY(cudaFuncSetAttribute(score_variant(i).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
     *out = h;
     return PCM_OK;
 }
 
 extern "C" void pcm_destroy(pcm_handle* h) {
     if (!h) return;
+    h->trace.report();
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto& m : h->models) free_model(m);
@@ -437,7 +510,7 @@ extern "C" int pcm_add_model(pcm_handle* h, int n_frame, int n_trees, const int6
     if (!h->features_set) return fail(PCM_E_STATE, "pcm_add_model: call pcm_set_features first");
     if (n_trees < 1) return fail(PCM_E_INVALID, "pcm_add_model: n_trees %d", n_trees);
     CUDA_TRY(cudaSetDevice(h->device));
-    std::vector<uint2> nodes;
+    std::vector<NodeT> nodes;
     std::vector<double> leaves;
     std::vector<int4> trees;
     int max_depth = 0, n_leaf = 0;
@@ -447,37 +520,37 @@ extern "C" int pcm_add_model(pcm_handle* h, int n_frame, int n_trees, const int6
         Encoder enc{h->geom, feature + b, threshold + b, left + b, right + b, value1 + b, (int)(e - b)};
         if (!enc.run()) return fail(PCM_E_LIMIT, "pcm_add_model: tree %d: %s", t, enc.err.c_str());
         const unsigned base = (unsigned)nodes.size();       // entry index of this tree's root
-        trees.push_back(make_int4((int)(8u * base), enc.out.depth, 0, 0));
-        for (uint2 nd : enc.out.nodes) {
-            nd.y = 8u * (nd.y + base);                      // forest-relative byte offset
+        trees.push_back(make_int4((int)(NODE_BYTES * base), enc.out.depth, 0, 0));
+        for (NodeT nd : enc.out.nodes) {
+            node_set_left(nd, NODE_BYTES * (node_left(nd) + base));   // forest-relative byte offset
             nodes.push_back(nd);
         }
         leaves.insert(leaves.end(), enc.out.values.begin(), enc.out.values.end());
         max_depth = std::max(max_depth, enc.out.depth);
         n_leaf += enc.out.n_leaf;
     }
-    if (nodes.size() > (1u << 27)) return fail(PCM_E_LIMIT, "pcm_add_model: forest too large");
+    if (nodes.size() > (1u << 26)) return fail(PCM_E_LIMIT, "pcm_add_model: forest too large");
     Model m;
     m.n_frame = n_frame;
     m.max_depth = max_depth;
-    CUDA_TRY(cudaMalloc(&m.d_nodes, nodes.size() * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc(&m.d_nodes, nodes.size() * sizeof(NodeT)));
     CUDA_TRY(cudaMalloc(&m.d_leaves, leaves.size() * sizeof(double)));
     CUDA_TRY(cudaMalloc(&m.d_trees, trees.size() * sizeof(int4)));
-    CUDA_TRY(cudaMemcpy(m.d_nodes, nodes.data(), nodes.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m.d_nodes, nodes.data(), nodes.size() * sizeof(NodeT), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(m.d_leaves, leaves.data(), leaves.size() * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(m.d_trees, trees.data(), trees.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    m.forest.nodes = static_cast<const uint2*>(m.d_nodes);
+    m.forest.nodes = static_cast<const NodeT*>(m.d_nodes);
     m.forest.leaves = static_cast<const double*>(m.d_leaves);
     m.forest.trees = static_cast<const int4*>(m.d_trees);
     m.forest.n_trees = n_trees;
     m.forest.n_nodes = (int)nodes.size();
     m.forest.n_leaves = n_leaf;
     for (int t = 0; t < n_trees && t < MAX_TOP_TREES; ++t) {
-        const uint2 root = nodes[trees[t].x / 8];
-        const bool root_is_leaf = root.y == (unsigned)trees[t].x;     // pseudo-node: y = self
+        const NodeT root = nodes[trees[t].x / NODE_BYTES];
+        const bool root_is_leaf = node_left(root) == (unsigned)trees[t].x;     // pseudo-node: left = self
         m.top.n[t][0] = root;
-        m.top.n[t][1] = root_is_leaf ? root : nodes[root.y / 8];
-        m.top.n[t][2] = root_is_leaf ? root : nodes[root.y / 8 + 1];
+        m.top.n[t][1] = root_is_leaf ? root : nodes[node_left(root) / NODE_BYTES];
+        m.top.n[t][2] = root_is_leaf ? root : nodes[node_left(root) / NODE_BYTES + 1];
     }
     h->models.push_back(m);
     if (model_index) *model_index = (int)h->models.size() - 1;
@@ -629,7 +702,12 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     a.f0 = m0.forest;
     a.top0 = m0.top;
     a.blend = p->model_next >= 0;
-    if (a.blend) { a.f1 = h->models[p->model_next].forest; a.top1 = h->models[p->model_next].top; }
+    a.depth = m0.max_depth;
+    if (a.blend) {
+        a.f1 = h->models[p->model_next].forest;
+        a.top1 = h->models[p->model_next].top;
+        a.depth = std::max(a.depth, h->models[p->model_next].max_depth);
+    }
     a.w0 = p->w_cur; a.w1 = p->w_next;
     a.novelty = p->novelty != 0;
     if (a.novelty) {
@@ -650,18 +728,17 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     if (!forest_smem) ls = score_smem_layout(a.g, a.f0, a.f1, a.blend, a.novelty, false);
     if ((int)ls.total > h->max_smem_optin)
         return fail(PCM_E_LIMIT, "update: tile needs %u B of shared memory (> %d)", ls.total, h->max_smem_optin);
+    const ScoreVariant& sv = pick_score_variant(forest_smem, a.depth);
     int occ = 0;
-    if (forest_smem) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, score_kernel<true>, NTHREADS, ls.total));
-    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, score_kernel<false>, NTHREADS, ls.total));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sv.fn, NTHREADS, ls.total));
     occ = std::max(occ, 1);
     const int n_tiles = a.tiles_x * a.tiles_y;
     const int grid = std::min(n_tiles, h->sm_count * occ);
     {
         KernelTimer kt(h, 0);
-        if (forest_smem) score_kernel<true><<<grid, NTHREADS, ls.total, st>>>(tmap, a);
-        else score_kernel<false><<<grid, NTHREADS, ls.total, st>>>(tmap, a);
+        sv.fn<<<grid, NTHREADS, ls.total, st>>>(tmap, a);
     }
-    CHECK_LAUNCH(h, forest_smem ? "score_kernel<smem>" : "score_kernel<global>");
+    CHECK_LAUNCH(h, sv.name);
 
     // ---- K2: per-label decision (+ exact path) ------------------------------------------------
     DecideArgs da{};
@@ -698,6 +775,7 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     h->last_cw = cw; h->last_ch = ch; h->last_S = S;
     h->last_novelty = a.novelty;
     h->last_valid = true;
+    h->last_pre = want_pre;
     return PCM_OK;
 }
 
@@ -710,21 +788,26 @@ extern "C" int pcm_update_device(pcm_handle* h, const uint8_t* d_frame, int H, i
     if (stride < (int64_t)W * 3) return fail(PCM_E_INVALID, "pcm_update_device: stride %lld < 3*W", (long long)stride);
     CUDA_TRY(cudaSetDevice(h->device));
     return enqueue_update(h, d_frame, H, W, stride, rect, d_labels, n_labels, d_priors, params, d_mask,
-                          mask_row_stride, rect[0], rect[1], true);
+                          mask_row_stride, rect[0], rect[1], h->keep_pre);
 }
 
 extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int64_t stride, const int rect[4],
                           const int32_t* labels, int n_labels, const float* priors, const pcm_update_params* params,
                           uint8_t* mask, int64_t mask_row_stride, int64_t mask_pixel_stride) {
     if (!h || !frame || !labels || !mask) return fail(PCM_E_INVALID, "pcm_update: NULL argument");
-    int rc = validate_update(h, H, W, rect, n_labels, params);
+    const bool auto_labels = n_labels <= 0;            // n_labels = max(label) + 1, found while staging
+    if (auto_labels && priors) return fail(PCM_E_INVALID, "pcm_update: priors need an explicit n_labels");
+    int rc = validate_update(h, H, W, rect, auto_labels ? 1 : n_labels, params);
     if (rc) return rc;
     if (stride < (int64_t)W * 3) return fail(PCM_E_INVALID, "pcm_update: stride %lld < 3*W", (long long)stride);
     CUDA_TRY(cudaSetDevice(h->device));
     const int cx = rect[0], cy = rect[1], cw = rect[2], ch = rect[3];
     const size_t npx = (size_t)cw * ch, row_bytes = (size_t)cw * 3;
     cudaStream_t st = h->stream;
+    h->trace.start();
     // host -> pinned -> device: only the crop travels
+    const void* old_hl = h->h_labels.p;
+    const void* old_dl = h->labels.p;
     CUDA_TRY(h->h_frame.reserve(npx * 3));
     CUDA_TRY(h->frame.reserve(npx * 3));
     CUDA_TRY(h->h_labels.reserve(npx * sizeof(int32_t)));
@@ -733,38 +816,62 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
     CUDA_TRY(h->mask.reserve(npx));
     CUDA_TRY(h->h_small.reserve(64));
     CUDA_TRY(cudaStreamSynchronize(st));   // staging buffers are reused between calls
-    // Row chunks are copied into pinned memory by the host pool and handed to the copy engine
-    // one by one, so the DMA of chunk i overlaps the staging of chunk i+1.
-    HostPool& pool = HostPool::instance();
+    h->trace.lap(HostTrace::UPD_SYNC);
+
+    // One dispatch of the host pool stages everything: an item is a ~1 MiB chunk of crop rows or
+    // of the label map; the worker copies it into pinned memory and queues its H2D copy itself,
+    // so the DMA of finished chunks overlaps the staging of the others.  A label chunk whose
+    // bytes equal the previous call's (kept in the pinned buffer) is neither copied nor re-sent.
+    constexpr size_t CHUNK = 1u << 20;
+    const int rows_per_chunk = std::max(1, (int)(CHUNK / std::max<size_t>(row_bytes, 1)));
+    const int n_frame_items = (ch + rows_per_chunk - 1) / rows_per_chunk;
+    const size_t label_bytes = npx * sizeof(int32_t);
+    const int n_label_items = (int)((label_bytes + CHUNK - 1) / CHUNK);
+    const bool cache_ok = h->label_cache_px == npx && old_hl == h->h_labels.p && old_dl == h->labels.p &&
+                          (int)h->label_chunk_max.size() == n_label_items;
+    if (!cache_ok) h->label_chunk_max.assign(n_label_items, -1);
+    h->label_cache_px = 0;                 // invalid until every chunk is staged
     uint8_t* hf = h->h_frame.as<uint8_t>();
-    {
-        const int rows_per_chunk = std::max(1, (int)((1u << 20) / std::max<size_t>(row_bytes, 1)));
-        for (int r0 = 0; r0 < ch; r0 += rows_per_chunk) {
-            const int r1 = std::min(ch, r0 + rows_per_chunk);
-            const int parts = std::min(pool.size(), r1 - r0);
-            pool.parallel_for(parts, [&](int part) {
-                const int a0 = r0 + (int)((long long)(r1 - r0) * part / parts);
-                const int a1 = r0 + (int)((long long)(r1 - r0) * (part + 1) / parts);
-                for (int r = a0; r < a1; ++r)
-                    memcpy(hf + (size_t)r * row_bytes, frame + (size_t)(cy + r) * stride + (size_t)cx * 3, row_bytes);
-            });
-            CUDA_TRY(cudaMemcpyAsync(h->frame.as<uint8_t>() + (size_t)r0 * row_bytes, hf + (size_t)r0 * row_bytes,
-                                     (size_t)(r1 - r0) * row_bytes, cudaMemcpyHostToDevice, st));
+    uint8_t* hl = h->h_labels.as<uint8_t>();
+    uint8_t* df = h->frame.as<uint8_t>();
+    uint8_t* dl = h->labels.as<uint8_t>();
+    const uint8_t* lsrc = reinterpret_cast<const uint8_t*>(labels);
+    int* chunk_max = h->label_chunk_max.data();
+    std::atomic<int> cuda_err{0};
+    const int device = h->device;
+    HostPool& pool = HostPool::instance();
+    pool.parallel_for(n_frame_items + n_label_items, [&](int item) {
+        cudaSetDevice(device);
+        cudaError_t e = cudaSuccess;
+        if (item < n_frame_items) {
+            const int r0 = item * rows_per_chunk, r1 = std::min(ch, r0 + rows_per_chunk);
+            for (int r = r0; r < r1; ++r)
+                memcpy(hf + (size_t)r * row_bytes, frame + (size_t)(cy + r) * stride + (size_t)cx * 3, row_bytes);
+            e = cudaMemcpyAsync(df + (size_t)r0 * row_bytes, hf + (size_t)r0 * row_bytes, (size_t)(r1 - r0) * row_bytes,
+                                cudaMemcpyHostToDevice, st);
+        } else {
+            const int c = item - n_frame_items;
+            const size_t o = (size_t)c * CHUNK, len = std::min(CHUNK, label_bytes - o);
+            if (!(cache_ok && memcmp(hl + o, lsrc + o, len) == 0)) {
+                const int32_t* src = reinterpret_cast<const int32_t*>(lsrc + o);
+                int32_t* dst = reinterpret_cast<int32_t*>(hl + o);
+                int mx = -1;
+                const size_t n = len / sizeof(int32_t);
+                for (size_t i = 0; i < n; ++i) { const int32_t v = src[i]; dst[i] = v; mx = v > mx ? v : mx; }
+                chunk_max[c] = mx;
+                e = cudaMemcpyAsync(dl + o, hl + o, len, cudaMemcpyHostToDevice, st);
+            }
         }
-    }
-    {
-        const size_t total = npx * sizeof(int32_t), chunk = 1u << 20;
-        uint8_t* hl = h->h_labels.as<uint8_t>();
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(labels);
-        for (size_t o = 0; o < total; o += chunk) {
-            const size_t len = std::min(chunk, total - o);
-            const int parts = (int)std::min<size_t>(pool.size(), (len + 65535) / 65536);
-            pool.parallel_for(parts, [&](int part) {
-                const size_t b0 = len * part / parts, b1 = len * (part + 1) / parts;
-                memcpy(hl + o + b0, src + o + b0, b1 - b0);
-            });
-            CUDA_TRY(cudaMemcpyAsync(h->labels.as<uint8_t>() + o, hl + o, len, cudaMemcpyHostToDevice, st));
-        }
+        if (e != cudaSuccess) cuda_err.store((int)e);
+    });
+    if (cuda_err.load()) return fail(PCM_E_CUDA, "pcm_update: staging copy failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
+    h->label_cache_px = npx;
+    h->trace.lap(HostTrace::UPD_STAGE);
+    if (auto_labels) {
+        int mx = -1;
+        for (int c = 0; c < n_label_items; ++c) mx = std::max(mx, chunk_max[c]);
+        if (mx < 0) return fail(PCM_E_LABEL, "pcm_update: label map has no non-negative label");
+        n_labels = mx + 1;
     }
     const float* d_priors = nullptr;
     if (priors) {
@@ -776,11 +883,13 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
     }
     const int crop_rect[4] = {0, 0, cw, ch};
     rc = enqueue_update(h, h->frame.as<uint8_t>(), ch, cw, (int64_t)row_bytes, crop_rect, h->labels.as<int32_t>(),
-                        n_labels, d_priors, params, h->mask.as<uint8_t>(), cw, 0, 0, true);
+                        n_labels, d_priors, params, h->mask.as<uint8_t>(), cw, 0, 0, h->keep_pre);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(h->h_mask.p, h->mask.p, npx, cudaMemcpyDeviceToHost, st));
+    h->trace.lap(HostTrace::UPD_ENQUEUE);
     rc = check_label_error(h, true);
     if (rc) return rc;
+    h->trace.lap(HostTrace::UPD_WAIT);
     // scatter the dense crop into the caller's (possibly interleaved) mask
     const uint8_t* hm = h->h_mask.as<uint8_t>();
     {
@@ -790,12 +899,11 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
             for (int r = a0; r < a1; ++r) {
                 uint8_t* dst = mask + (size_t)(cy + r) * mask_row_stride + (size_t)cx * mask_pixel_stride;
                 const uint8_t* src = hm + (size_t)r * cw;
-                if (mask_pixel_stride == 1) memcpy(dst, src, cw);
-                else
-                    for (int c = 0; c < cw; ++c) dst[(size_t)c * mask_pixel_stride] = src[c];
+                scatter_strided(src, dst, mask_pixel_stride, cw);
             }
         });
     }
+    h->trace.lap(HostTrace::UPD_SCATTER);
     return PCM_OK;
 }
 
@@ -834,29 +942,42 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
     CUDA_TRY(h->counts.reserve(2 * sizeof(int64_t)));
     CUDA_TRY(h->h_small.reserve(64));
     CUDA_TRY(cudaStreamSynchronize(st));
+    h->trace.start();
     HostPool& pool = HostPool::instance();
     uint8_t* hm = h->h_mask.as<uint8_t>();
     uint8_t* ht = h->h_frame.as<uint8_t>();
-    const int parts = std::min(pool.size(), std::max(1, (int)(npx >> 16)));
-    pool.parallel_for(parts, [&](int part) {
-        const int a0 = (int)((long long)height * part / parts), a1 = (int)((long long)height * (part + 1) / parts);
-        for (int r = a0; r < a1; ++r) {
-            memcpy(ht + (size_t)r * width * truth_channels, truth + (size_t)r * truth_row_stride,
-                   (size_t)width * truth_channels);
+    uint8_t* dm = h->mask.as<uint8_t>();
+    uint8_t* dt = h->frame.as<uint8_t>();
+    // one pool dispatch: an item is a band of rows of the truth or of the mask; the worker packs
+    // it densely into pinned memory and queues its own H2D copy
+    const size_t trow = (size_t)width * truth_channels;
+    const int rows_t = std::max(1, (int)((1u << 20) / std::max<size_t>(trow, 1)));
+    const int rows_m = std::max(1, (int)((1u << 20) / (size_t)width));
+    const int n_t = (height + rows_t - 1) / rows_t, n_m = (height + rows_m - 1) / rows_m;
+    std::atomic<int> cuda_err{0};
+    const int device = h->device;
+    pool.parallel_for(n_t + n_m, [&](int item) {
+        cudaSetDevice(device);
+        cudaError_t e;
+        if (item < n_t) {
+            const int r0 = item * rows_t, r1 = std::min(height, r0 + rows_t);
+            for (int r = r0; r < r1; ++r) memcpy(ht + (size_t)r * trow, truth + (size_t)r * truth_row_stride, trow);
+            e = cudaMemcpyAsync(dt + (size_t)r0 * trow, ht + (size_t)r0 * trow, (size_t)(r1 - r0) * trow,
+                                cudaMemcpyHostToDevice, st);
+        } else {
+            const int r0 = (item - n_t) * rows_m, r1 = std::min(height, r0 + rows_m);
+            for (int r = r0; r < r1; ++r) {
+                const uint8_t* src = mask + (size_t)r * mask_row_stride;
+                uint8_t* dst = hm + (size_t)r * width;
+                gather_strided(src, mask_pixel_stride, dst, width);
+            }
+            e = cudaMemcpyAsync(dm + (size_t)r0 * width, hm + (size_t)r0 * width, (size_t)(r1 - r0) * width,
+                                cudaMemcpyHostToDevice, st);
         }
+        if (e != cudaSuccess) cuda_err.store((int)e);
     });
-    CUDA_TRY(cudaMemcpyAsync(h->frame.p, ht, tbytes, cudaMemcpyHostToDevice, st));
-    pool.parallel_for(parts, [&](int part) {
-        const int a0 = (int)((long long)height * part / parts), a1 = (int)((long long)height * (part + 1) / parts);
-        for (int r = a0; r < a1; ++r) {
-            const uint8_t* src = mask + (size_t)r * mask_row_stride;
-            uint8_t* dst = hm + (size_t)r * width;
-            if (mask_pixel_stride == 1) memcpy(dst, src, width);
-            else
-                for (int c = 0; c < width; ++c) dst[c] = src[(size_t)c * mask_pixel_stride];
-        }
-    });
-    CUDA_TRY(cudaMemcpyAsync(h->mask.p, hm, npx, cudaMemcpyHostToDevice, st));
+    if (cuda_err.load()) return fail(PCM_E_CUDA, "pcm_iou: staging copy failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
+    h->trace.lap(HostTrace::IOU_STAGE);
     CUDA_TRY(cudaMemsetAsync(h->counts.p, 0, 2 * sizeof(int64_t), st));
     int rc = pcm_iou_device(h, h->mask.as<uint8_t>(), width, h->frame.as<uint8_t>(), (int64_t)width * truth_channels,
                             truth_channels, height, width, h->counts.as<int64_t>());
@@ -864,6 +985,7 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
     int64_t* hc = h->h_small.as<int64_t>() + 2;
     CUDA_TRY(cudaMemcpyAsync(hc, h->counts.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    h->trace.lap(HostTrace::IOU_WAIT);
     counts[0] = hc[0];
     counts[1] = hc[1];
     h->last_valid = false;   // frame / mask scratch was reused
@@ -946,12 +1068,21 @@ extern "C" int pcm_debug_last(pcm_handle* h, double* p1, double* sa, float* scor
         CUDA_TRY(cudaMemcpy(tmp.data(), h->seg.as<char>() + sl.area, sizeof(int) * (size_t)S, cudaMemcpyDeviceToHost));
         for (int i = 0; i < S; ++i) areas[i] = tmp[i];
     }
-    if (pre) CUDA_TRY(cudaMemcpy(pre, h->pre.p, npx, cudaMemcpyDeviceToHost));
+    if (pre) {
+        if (!h->last_pre) return fail(PCM_E_STATE, "pcm_debug_last: pre-dilation map not kept (call pcm_set_debug(h, 1) first)");
+        CUDA_TRY(cudaMemcpy(pre, h->pre.p, npx, cudaMemcpyDeviceToHost));
+    }
     if (n_exact) {
         int v = 0;
         CUDA_TRY(cudaMemcpy(&v, h->seg.as<char>() + sl.nflag, sizeof(int), cudaMemcpyDeviceToHost));
         *n_exact = v;
     }
+    return PCM_OK;
+}
+
+extern "C" int pcm_set_debug(pcm_handle* h, int on) {
+    if (!h) return fail(PCM_E_INVALID, "pcm_set_debug: NULL handle");
+    h->keep_pre = on != 0;
     return PCM_OK;
 }
 

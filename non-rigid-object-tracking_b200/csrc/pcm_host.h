@@ -7,6 +7,7 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -22,6 +23,8 @@ public:
     int size() const { return (int)workers_.size() + 1; }
 
     // Calls fn(i) for i in [0, n) on the pool's threads plus the caller; returns when all are done.
+    // Every call publishes its own Job object, so a worker that wakes up late only ever sees a
+    // finished job (next >= n) or the current one -- never a mix of two calls' fields.
     void parallel_for(int n, const std::function<void(int)>& fn) {
         if (n <= 0) return;
         if (n == 1 || workers_.empty()) {
@@ -29,19 +32,18 @@ public:
             return;
         }
         std::unique_lock<std::mutex> guard(submit_);   // one job at a time
+        auto job = std::make_shared<Job>();
+        job->fn = &fn;
+        job->n = n;
         {
             std::lock_guard<std::mutex> lk(m_);
-            fn_ = &fn;
-            n_ = n;
-            next_.store(0);
-            pending_ = n;
+            job_ = job;
             ++generation_;
         }
         cv_.notify_all();
-        run_items();
+        run_items(*job);
         std::unique_lock<std::mutex> lk(m_);
-        done_.wait(lk, [&] { return pending_ == 0; });
-        fn_ = nullptr;
+        done_.wait(lk, [&] { return job->done.load() == n; });
     }
 
 private:
@@ -64,34 +66,42 @@ private:
         cv_.notify_all();
         for (auto& t : workers_) t.join();
     }
-    void run_items() {
+    struct Job {
+        const std::function<void(int)>* fn = nullptr;
+        int n = 0;
+        std::atomic<int> next{0};
+        std::atomic<int> done{0};
+    };
+    void run_items(Job& job) {
         for (;;) {
-            const int i = next_.fetch_add(1);
-            if (i >= n_) break;
-            (*fn_)(i);
-            std::lock_guard<std::mutex> lk(m_);
-            if (--pending_ == 0) done_.notify_all();
+            const int i = job.next.fetch_add(1);
+            if (i >= job.n) break;
+            (*job.fn)(i);
+            if (job.done.fetch_add(1) + 1 == job.n) {
+                std::lock_guard<std::mutex> lk(m_);   // pairs with the waiter's predicate check
+                done_.notify_all();
+            }
         }
     }
     void worker() {
         unsigned long seen = 0;
         for (;;) {
+            std::shared_ptr<Job> job;
             {
                 std::unique_lock<std::mutex> lk(m_);
                 cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
                 if (stop_) return;
                 seen = generation_;
+                job = job_;
             }
-            run_items();
+            if (job) run_items(*job);
         }
     }
 
     std::vector<std::thread> workers_;
     std::mutex m_, submit_;
     std::condition_variable cv_, done_;
-    const std::function<void(int)>* fn_ = nullptr;
-    int n_ = 0, pending_ = 0;
-    std::atomic<int> next_{0};
+    std::shared_ptr<Job> job_;
     unsigned long generation_ = 0;
     bool stop_ = false;
 };

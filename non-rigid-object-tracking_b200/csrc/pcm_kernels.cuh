@@ -20,24 +20,49 @@ namespace pcm {
 
 // ------------------------------------------------------------------------------
 // packed forest (built on the host by Encoder in pcm_api.cu)
-//   Every tree owns a contiguous run of 8-byte entries: internal nodes and one
-//   self-looping pseudo-node per leaf, laid out so that the two children of a node are
-//   ADJACENT entries (left, then right).  The traversal is branch-free and a thread that
-//   has reached a leaf simply stays there.
-//     entry.x = tap << 16 | thr   tap: byte offset of the tested value inside the plane
-//                                 tile; thr: the value v (u8, 0 outside the crop) goes
-//                                 RIGHT iff v > thr
-//     entry.y = byte offset of the LEFT child's entry from the start of the forest's
-//               entry array (right child = +8); relocated to an absolute shared-memory
-//               address when the forest is staged in shared memory
-//     leaf pseudo-node: x = 0x0000ffff (never right), y = self
-//   values[i] = class-1 fraction of entry i (leaf entries; 0 elsewhere), parallel array
-//   trees[t] = {root entry offset (bytes), depth, -, -}
+//   Every tree owns a contiguous run of fixed-size entries (NodeT): internal nodes and one
+//   self-looping pseudo-node per leaf, laid out breadth-first so that the two children of a
+//   node are ADJACENT entries (left, then right).  The traversal is branch-free and a thread
+//   that has reached a leaf simply stays there.
+//     tap   byte offset of the tested value inside the plane tile
+//     thr   the value v (u8, 0 outside the crop) goes RIGHT iff v > thr
+//     left  byte offset of the LEFT child's entry from the start of the forest's entry
+//           array (right child = + NODE_BYTES); relocated to an absolute shared-memory
+//           address when the forest is staged in shared memory
+//     leaf pseudo-node: tap = 0, thr = LEAF_THR (never right), left = self
+//   leaves[i] = class-1 fraction of entry i (leaf entries; 0 elsewhere), parallel array
+//   trees[t] = {root entry offset (bytes), depth, -, -}   (only the offset is used, and only
+//              for trees beyond MAX_TOP_TREES)
 // The crop-border sentinel -1 of the reference (:263) is handled by the encoder:
 // nodes with integer threshold -1 test the validity plane instead (0 outside the crop).
 // ------------------------------------------------------------------------------
+#ifndef PCM_NODE16
+#define PCM_NODE16 0
+#endif
+#if PCM_NODE16
+// 16-byte entries {tap, thr, left, -}: one LDS.128 delivers the three fields unpacked, so a
+// node visit is LDS.128, add (tap address), LDS.U8, compare, predicated add -- no shift/mask
+// work on the ALU pipe (2 cycles per warp instruction on sm_100).
+typedef uint4 NodeT;
+__host__ __device__ inline NodeT make_node(unsigned tap, unsigned thr, unsigned left) { return make_uint4(tap, thr, left, 0u); }
+__host__ __device__ inline unsigned node_tap(const NodeT& n) { return n.x; }
+__host__ __device__ inline unsigned node_thr(const NodeT& n) { return n.y; }
+__host__ __device__ inline unsigned node_left(const NodeT& n) { return n.z; }
+__host__ __device__ inline void node_set_left(NodeT& n, unsigned v) { n.z = v; }
+constexpr unsigned LEAF_THR = 0xffffffffu;
+#else
+typedef uint2 NodeT;   // {tap << 16 | thr, left}
+__host__ __device__ inline NodeT make_node(unsigned tap, unsigned thr, unsigned left) { return make_uint2((tap << 16) | thr, left); }
+__host__ __device__ inline unsigned node_tap(const NodeT& n) { return n.x >> 16; }
+__host__ __device__ inline unsigned node_thr(const NodeT& n) { return n.x & 0xffffu; }
+__host__ __device__ inline unsigned node_left(const NodeT& n) { return n.y; }
+__host__ __device__ inline void node_set_left(NodeT& n, unsigned v) { n.y = v; }
+constexpr unsigned LEAF_THR = 0xffffu;
+#endif
+constexpr unsigned NODE_BYTES = sizeof(NodeT);
+
 struct DevForest {
-    const uint2* nodes;      // [n_nodes] entries
+    const NodeT* nodes;      // [n_nodes] entries
     const double* leaves;    // [n_nodes] values, parallel to nodes
     const int4* trees;
     int n_trees, n_nodes, n_leaves;
@@ -49,7 +74,7 @@ struct DevForest {
 // (entry.y here is still forest-relative).
 constexpr int MAX_TOP_TREES = 48;
 struct TopNodes {
-    uint2 n[MAX_TOP_TREES][3];   // {root, left child, right child}
+    NodeT n[MAX_TOP_TREES][3];   // {root, left child, right child}
 };
 
 struct DevPCA {
@@ -174,6 +199,18 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t a) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ NodeT lds_node(uint32_t a) {
+#if PCM_NODE16
+    return lds_v4(a);
+#else
+    return lds_v2(a);
+#endif
+}
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
@@ -206,8 +243,11 @@ __device__ __forceinline__ double contribution(double p1, double sa, double thr)
     return __dsub_rn(p1, __dsub_rn(fmax(sa, thr), thr));
 }
 
-// lab < 0: lane does not take part.  `row` is warp-uniform.
-__device__ __forceinline__ void segment_accumulate(const SegAcc& s, int lab, double d, int row) {
+// One run of a thread's column: `cnt` pixels of label `lab` in rows [r0, r1] with sum `sm` and
+// sum of magnitudes `as`.  lab < 0: the lane does not take part.  Lanes with equal labels are
+// combined (shuffles for the float64 sums, redux.sync for the integers) and the group's
+// leader issues one set of atomics.
+__device__ __forceinline__ void segment_flush(const SegAcc& s, int lab, double sm, double as, int cnt, int r0, int r1) {
     const int lane = threadIdx.x & 31;
     unsigned todo = __ballot_sync(0xffffffffu, lab >= 0);
     while (todo) {
@@ -215,18 +255,21 @@ __device__ __forceinline__ void segment_accumulate(const SegAcc& s, int lab, dou
         const int L = __shfl_sync(0xffffffffu, lab, leader);
         const bool mine = (lab == L);
         const unsigned members = __ballot_sync(0xffffffffu, mine);
-        double sm = mine ? d : 0.0, as = mine ? fabs(d) : 0.0;
+        double x = mine ? sm : 0.0, y = mine ? as : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            sm += __shfl_xor_sync(0xffffffffu, sm, o);
-            as += __shfl_xor_sync(0xffffffffu, as, o);
+            x += __shfl_xor_sync(0xffffffffu, x, o);
+            y += __shfl_xor_sync(0xffffffffu, y, o);
         }
+        const int n = __reduce_add_sync(0xffffffffu, mine ? cnt : 0);
+        const int lo = __reduce_min_sync(0xffffffffu, mine ? r0 : 0x7fffffff);
+        const int hi = __reduce_max_sync(0xffffffffu, mine ? r1 : -1);
         if (lane == leader) {
-            atomicAdd(s.sum + L, sm);
-            atomicAdd(s.asum + L, as);
-            atomicAdd(s.area + L, __popc(members));
-            atomicMin(s.rmin + L, row);
-            atomicMax(s.rmax + L, row);
+            atomicAdd(s.sum + L, x);
+            atomicAdd(s.asum + L, y);
+            atomicAdd(s.area + L, n);
+            atomicMin(s.rmin + L, lo);
+            atomicMax(s.rmax + L, hi);
         }
         todo &= ~members;
     }
@@ -239,6 +282,7 @@ struct ScoreArgs {
     unsigned* tile_counter;          // dynamic tile scheduler (zeroed by K0)
     DevForest f0, f1;
     TopNodes top0, top1;             // first two levels of f0 / f1 (constant bank)
+    int depth;                       // levels walked in every tree: max depth over f0 (and f1)
     int blend;                       // 0/1: f1 (and pca1) valid
     double w0, w1;                   // np.average weights
     int novelty;                     // 0/1
@@ -253,65 +297,95 @@ struct ScoreArgs {
 // Branch-free: the PIX_PER_THREAD pointer chases are issued level by level so that
 // their dependent shared-memory loads overlap.  SM = forest staged in shared memory
 // (node links are absolute shared addresses); otherwise nodes/leaves are read through L1.
-template <bool SM>
-__device__ __forceinline__ void traverse_forest(const uint32_t nodes_s, const uint32_t vdelta_s,
+// ref + NODE_BYTES (the adjacent right child) iff v > thr: one compare + one predicated add
+__device__ __forceinline__ uint32_t step_child(uint32_t left, uint32_t v, uint32_t thr) {
+#if PCM_NODE16
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 16;\n\t}" : "+r"(left) : "r"(v), "r"(thr));
+#else
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 8;\n\t}" : "+r"(left) : "r"(v), "r"(thr));
+#endif
+    return left;
+}
+
+// DEPTH > 0: every tree of the forest is walked DEPTH levels (compile-time, fully unrolled);
+// DEPTH == 0: `depth` levels (kernel-uniform run-time value).  Walking a tree deeper than it is
+// costs nothing but time -- leaves self-loop -- so one depth serves the whole forest.
+template <bool SM, int DEPTH>
+__device__ __forceinline__ void traverse_forest(const uint32_t nodes_s, const uint32_t leaves_s,
                                                 const uint8_t* __restrict__ nodes_g,
                                                 const uint8_t* __restrict__ leaves_g,
-                                                const int4* __restrict__ trees, int n_trees, const TopNodes& top,
+                                                const int4* __restrict__ trees, const int n_trees, const int depth,
+                                                const TopNodes& top,
                                                 const uint32_t (&pix)[PIX_PER_THREAD],
                                                 double (&acc)[PIX_PER_THREAD]) {
     const uint32_t base = SM ? nodes_s : 0u;
-    for (int t = 0; t < n_trees; ++t) {
-        const int4 ti = trees[t];
-        uint32_t ref[PIX_PER_THREAD];
-        int lvl = 0;
-        if (t < MAX_TOP_TREES) {
-            // levels 0 and 1 from warp-uniform operands (constant bank)
-            const uint2 e0 = top.n[t][0], eL = top.n[t][1], eR = top.n[t][2];
-            uint32_t v[PIX_PER_THREAD], x1[PIX_PER_THREAD];
-#pragma unroll
-            for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = lds_u8(pix[g] + (e0.x >> 16));
-#pragma unroll
-            for (int g = 0; g < PIX_PER_THREAD; ++g) {
-                const bool right = v[g] > (e0.x & 0xffffu);
-                x1[g] = right ? eR.x : eL.x;
-                ref[g] = (right ? eR.y : eL.y) + base;
-            }
-#pragma unroll
-            for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = lds_u8(pix[g] + (x1[g] >> 16));
-#pragma unroll
-            for (int g = 0; g < PIX_PER_THREAD; ++g) {
-                asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 8;\n\t}"
-                    : "+r"(ref[g]) : "r"(v[g]), "r"(x1[g] & 0xffffu));
-            }
-            lvl = 2;
-        } else {
-#pragma unroll
-            for (int g = 0; g < PIX_PER_THREAD; ++g) ref[g] = (uint32_t)ti.x + base;
-        }
-        for (; lvl < ti.y; ++lvl) {
-            uint2 nd[PIX_PER_THREAD];
+    // leaf value of entry at `ref`: leaves + (ref - base) * 8 / NODE_BYTES
+    constexpr int VSH = (NODE_BYTES == 16) ? 1 : 0;
+    const uint32_t vdelta = leaves_s - (nodes_s >> VSH);   // shared path: value address = (ref >> VSH) + vdelta
+
+    auto descend = [&](uint32_t (&ref)[PIX_PER_THREAD], const int levels) {
+        auto level = [&]() {
+            NodeT nd[PIX_PER_THREAD];
             uint32_t v[PIX_PER_THREAD];
 #pragma unroll
             for (int g = 0; g < PIX_PER_THREAD; ++g)
-                nd[g] = SM ? lds_v2(ref[g]) : __ldg(reinterpret_cast<const uint2*>(nodes_g + ref[g]));
+                nd[g] = SM ? lds_node(ref[g]) : __ldg(reinterpret_cast<const NodeT*>(nodes_g + ref[g]));
 #pragma unroll
-            for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = lds_u8(pix[g] + (nd[g].x >> 16));
+            for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = lds_u8(pix[g] + node_tap(nd[g]));
 #pragma unroll
-            for (int g = 0; g < PIX_PER_THREAD; ++g) {
-                // ref = left child, + 8 (the adjacent right child) iff v > thr: one predicated add
-                uint32_t nxt = nd[g].y;
-                asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 8;\n\t}"
-                    : "+r"(nxt) : "r"(v[g]), "r"(nd[g].x & 0xffffu));
-                ref[g] = nxt;
-            }
+            for (int g = 0; g < PIX_PER_THREAD; ++g) ref[g] = step_child(node_left(nd[g]), v[g], node_thr(nd[g]));
+        };
+        if (DEPTH > 0) {
+#pragma unroll
+            for (int l = 0; l < levels; ++l) level();
+        } else {
+#pragma unroll 1
+            for (int l = 0; l < levels; ++l) level();
         }
 #pragma unroll
         for (int g = 0; g < PIX_PER_THREAD; ++g) {
-            const double leaf = SM ? lds_f64(ref[g] + vdelta_s)
-                                   : __ldg(reinterpret_cast<const double*>(leaves_g + ref[g]));
+            const double leaf = SM ? lds_f64((ref[g] >> VSH) + vdelta)
+                                   : __ldg(reinterpret_cast<const double*>(leaves_g + (ref[g] >> VSH)));
             acc[g] = __dadd_rn(acc[g], leaf);
         }
+    };
+
+    // trees whose first two levels sit in the constant bank (all of them in practice)
+    const int n_top = n_trees < MAX_TOP_TREES ? n_trees : MAX_TOP_TREES;
+    const int rest = DEPTH > 0 ? (DEPTH > 2 ? DEPTH - 2 : 0) : (depth > 2 ? depth - 2 : 0);
+#pragma unroll 1
+    for (int t = 0; t < n_top; ++t) {
+        // levels 0 and 1 from warp-uniform operands; also right for trees of depth < 2 because a
+        // leaf pseudo-node selects itself
+        const NodeT e0 = top.n[t][0], eL = top.n[t][1], eR = top.n[t][2];
+        uint32_t ref[PIX_PER_THREAD], v[PIX_PER_THREAD], tap1[PIX_PER_THREAD], thr1[PIX_PER_THREAD];
+#pragma unroll
+        for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = lds_u8(pix[g] + node_tap(e0));
+#pragma unroll
+        for (int g = 0; g < PIX_PER_THREAD; ++g) {
+            const bool right = v[g] > node_thr(e0);
+#if PCM_NODE16
+            tap1[g] = right ? eR.x : eL.x;
+            thr1[g] = right ? eR.y : eL.y;
+#else
+            tap1[g] = right ? eR.x : eL.x;   // packed tap | thr
+            thr1[g] = tap1[g] & 0xffffu;
+            tap1[g] >>= 16;
+#endif
+            ref[g] = (right ? node_left(eR) : node_left(eL)) + base;
+        }
+#pragma unroll
+        for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = lds_u8(pix[g] + tap1[g]);
+#pragma unroll
+        for (int g = 0; g < PIX_PER_THREAD; ++g) ref[g] = step_child(ref[g], v[g], thr1[g]);
+        descend(ref, DEPTH > 0 ? (DEPTH > 2 ? DEPTH - 2 : 0) : rest);
+    }
+#pragma unroll 1
+    for (int t = n_top; t < n_trees; ++t) {
+        uint32_t ref[PIX_PER_THREAD];
+#pragma unroll
+        for (int g = 0; g < PIX_PER_THREAD; ++g) ref[g] = (uint32_t)trees[t].x + base;
+        descend(ref, DEPTH > 0 ? DEPTH : depth);
     }
 }
 
@@ -390,10 +464,10 @@ __host__ __device__ inline ScoreSmem score_smem_layout(const Geom& g, const DevF
     s.f1_trees = o;
     if (blend) o = align_up(o + 16 * f1.n_trees, 16);
     if (forest_smem) {
-        s.f0_nodes = o;  o = align_up(o + 8 * f0.n_nodes, 16);
+        s.f0_nodes = o;  o = align_up(o + NODE_BYTES * f0.n_nodes, 16);
         s.f0_leaves = o; o = align_up(o + 8 * f0.n_nodes, 16);
         if (blend) {
-            s.f1_nodes = o;  o = align_up(o + 8 * f1.n_nodes, 16);
+            s.f1_nodes = o;  o = align_up(o + NODE_BYTES * f1.n_nodes, 16);
             s.f1_leaves = o; o = align_up(o + 8 * f1.n_nodes, 16);
         }
     }
@@ -412,19 +486,19 @@ __device__ __forceinline__ void copy_to_smem(T* dst, const T* __restrict__ src, 
 }
 
 // stage a forest's nodes in shared memory, turning child offsets into absolute shared addresses
-__device__ __forceinline__ void stage_nodes(uint8_t* dst, const uint2* __restrict__ src, int n) {
+__device__ __forceinline__ void stage_nodes(uint8_t* dst, const NodeT* __restrict__ src, int n) {
     const uint32_t base = smem_u32(dst);
     for (int i = threadIdx.x; i < n; i += NTHREADS) {
-        uint2 nd = src[i];
-        nd.y += base;
-        reinterpret_cast<uint2*>(dst)[i] = nd;
+        NodeT nd = src[i];
+        node_set_left(nd, node_left(nd) + base);
+        reinterpret_cast<NodeT*>(dst)[i] = nd;
     }
 }
 
 // K1 -----------------------------------------------------------------------------
 // Persistent CTAs; tiles are handed out by an atomic counter and arrive through a
 // two-stage TMA pipeline (the box of tile i+1 is in flight while tile i is scored).
-template <bool FOREST_SMEM>
+template <bool FOREST_SMEM, int DEPTH>
 __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __grid_constant__ CUtensorMap tmap, const ScoreArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const Geom& g = a.g;
@@ -518,10 +592,19 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
 #pragma unroll
         for (int i = 0; i < PIX_PER_THREAD; ++i) pix[i] = tiles_s + buf * tile_bytes + (row0 + i) * g.RS + col;
 
+        // labels of the thread's pixels: requested now, consumed in the epilogue (their HBM/L2
+        // latency hides behind the forest traversal)
+        int lab[PIX_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < PIX_PER_THREAD; ++i) {
+            const int oy = ty0 + row0 + i;
+            lab[i] = (ox < a.cw && oy < a.ch) ? __ldg(a.seg.labels + (size_t)oy * a.cw + ox) : -1;
+        }
+
         double p[PIX_PER_THREAD];
 #pragma unroll
         for (int i = 0; i < PIX_PER_THREAD; ++i) p[i] = 0.0;
-        traverse_forest<FOREST_SMEM>(f0n_s, f0l_s - f0n_s, f0n_g, f0l_g, f0t, a.f0.n_trees, a.top0, pix, p);
+        traverse_forest<FOREST_SMEM, DEPTH>(f0n_s, f0l_s, f0n_g, f0l_g, f0t, a.f0.n_trees, a.depth, a.top0, pix, p);
         const double T0 = (double)a.f0.n_trees;
 #pragma unroll
         for (int i = 0; i < PIX_PER_THREAD; ++i) p[i] = __ddiv_rn(p[i], T0);
@@ -529,7 +612,7 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
             double q[PIX_PER_THREAD];
 #pragma unroll
             for (int i = 0; i < PIX_PER_THREAD; ++i) q[i] = 0.0;
-            traverse_forest<FOREST_SMEM>(f1n_s, f1l_s - f1n_s, f1n_g, f1l_g, f1t, a.f1.n_trees, a.top1, pix, q);
+            traverse_forest<FOREST_SMEM, DEPTH>(f1n_s, f1l_s, f1n_g, f1l_g, f1t, a.f1.n_trees, a.depth, a.top1, pix, q);
             const double T1 = (double)a.f1.n_trees;
 #pragma unroll
             for (int i = 0; i < PIX_PER_THREAD; ++i) p[i] = blend2(p[i], __ddiv_rn(q[i], T1), a.w0, a.w1);
@@ -549,20 +632,33 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
             }
         }
         // ---- epilogue: P(fg) [, err] to HBM and the per-label sums (K2 fused here) --------------
+        // A thread walks down its column and merges consecutive pixels of the same label; the
+        // warp flushes (segment_flush) only when some lane's label changes, so a superpixel that
+        // spans the thread's rows costs one flush per tile instead of one per row.
+        int run_lab = -1, run_cnt = 0, run_r0 = 0, run_r1 = 0;
+        double run_sum = 0.0, run_abs = 0.0;
 #pragma unroll
         for (int i = 0; i < PIX_PER_THREAD; ++i) {
             const int oy = ty0 + row0 + i;
-            const bool in = (ox < a.cw) && (oy < a.ch);
-            int lab = -1;
-            if (in) {
+            int l = lab[i];
+            if (ox < a.cw && oy < a.ch) {
                 const size_t o = (size_t)oy * a.cw + ox;
                 a.p1_out[o] = p[i];
                 if (a.novelty) a.sa_out[o] = e[i];
-                lab = a.seg.labels[o];
-                if (lab < 0 || lab >= a.seg.n_labels) { *a.seg.err = 1; lab = -1; }
+                if (l < 0 || l >= a.seg.n_labels) { *a.seg.err = 1; l = -1; }
             }
-            segment_accumulate(a.seg, lab, contribution(p[i], e[i], a.seg.thr), oy);
+            const bool change = (l != run_lab) && run_lab >= 0;
+            if (__any_sync(0xffffffffu, change)) {
+                segment_flush(a.seg, change ? run_lab : -1, run_sum, run_abs, run_cnt, run_r0, run_r1);
+                if (change) run_lab = -1;
+            }
+            if (l >= 0) {
+                const double d = contribution(p[i], e[i], a.seg.thr);
+                if (run_lab < 0) { run_lab = l; run_cnt = 0; run_sum = 0.0; run_abs = 0.0; run_r0 = oy; }
+                run_sum += d; run_abs += fabs(d); run_cnt++; run_r1 = oy;
+            }
         }
+        segment_flush(a.seg, run_lab, run_sum, run_abs, run_cnt, run_r0, run_r1);
         __syncthreads();   // tile buffer `buf` may be refilled; sched[buf^1] is visible
     }
 }

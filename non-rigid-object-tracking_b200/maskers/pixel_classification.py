@@ -28,8 +28,19 @@ from .masker import Masker
 
 
 class PixelClassificationNonRigidMasker(Masker):
-    def __init__(self, poly_roi=None, update_mask=None, segment_fn=None, prior_fn=None, device=0, **args):
+    def __init__(self, poly_roi=None, update_mask=None, segment_fn=None, prior_fn=None, device=0,
+                 model_cache=None, cache_tag=None, train_jobs=None, **args):
+        """Reference keywords: debug, frame, config, poly_roi, update_mask (main.py:138-144).
+        Extra, all optional: `segment_fn(crop) -> int32 labels` and `prior_fn` (providers for the
+        stages outside the hot path), `device` (CUDA ordinal), `model_cache` + `cache_tag` (a dict
+        shared between maskers of a hyper-parameter sweep: training rows, fitted forests and PCAs
+        are reused when (tag, frame, features, n_estimators, max_depth) repeat -- fits are
+        deterministic, random_state=42), `train_jobs` (sklearn n_jobs for the fit; the fitted
+        forest does not depend on it)."""
         Masker.__init__(self, **args)
+        self.model_cache = model_cache
+        self.cache_tag = cache_tag
+        self.train_jobs = train_jobs
         self.poly_roi = copy.deepcopy(poly_roi)
         self.index = 0
         self.models = []
@@ -56,25 +67,44 @@ class PixelClassificationNonRigidMasker(Masker):
     def addModel(self, frame, poly_roi, bbox, n_frame, bbox_roni=None, show_prob_map=False):
         if bbox_roni is None:
             raise ValueError("bbox_roni is required (the reference opens a GUI selector here, :287)")
-        x, y, w, h = [int(v) for v in bbox]
-        roi = np.zeros((h, w), np.uint8)
-        cv.fillPoly(roi, np.array([[(p[0] - x, p[1] - y) for p in poly_roi]], dtype=np.int32), 255)
-        X = self._rows(frame, (x, y, w, h))
-        labels = (roi.reshape(-1) > 0).astype(np.int64)
-        Xn = self._rows(frame, tuple(int(v) for v in bbox_roni))
-        X = np.concatenate([X, Xn], axis=0)
-        labels = np.concatenate([labels, np.zeros(len(Xn), np.int64)])
-
         params = self.config["params"]
-        clf = RandomForestClassifier(random_state=42, n_estimators=params["n_estimators"],
-                                     max_depth=params["max_depth"]).fit(X, labels)
-        print("F1 score classifier for frame {}= {}".format(n_frame, round(f1_score(labels, clf.predict(X)), 2)))
+        cache = self.model_cache if self.model_cache is not None and self.cache_tag is not None else None
+        kx = (self.cache_tag, n_frame, params["features"], "rows")
+        if cache is not None and kx in cache:
+            X, labels = cache[kx]
+        else:
+            x, y, w, h = [int(v) for v in bbox]
+            roi = np.zeros((h, w), np.uint8)
+            cv.fillPoly(roi, np.array([[(p[0] - x, p[1] - y) for p in poly_roi]], dtype=np.int32), 255)
+            X = self._rows(frame, (x, y, w, h))
+            labels = (roi.reshape(-1) > 0).astype(np.int64)
+            Xn = self._rows(frame, tuple(int(v) for v in bbox_roni))
+            X = np.concatenate([X, Xn], axis=0)
+            labels = np.concatenate([labels, np.zeros(len(Xn), np.int64)])
+            if cache is not None:
+                cache[kx] = (X, labels)
+
+        kf = (self.cache_tag, n_frame, params["features"], params["n_estimators"], params["max_depth"], "forest")
+        if cache is not None and kf in cache:
+            clf = cache[kf]
+        else:
+            clf = RandomForestClassifier(random_state=42, n_estimators=params["n_estimators"],
+                                         max_depth=params["max_depth"], n_jobs=self.train_jobs).fit(X, labels)
+            print("F1 score classifier for frame {}= {}".format(n_frame, round(f1_score(labels, clf.predict(X)), 2)))
+            if cache is not None:
+                cache[kf] = clf
         if params["novelty_detection"]:
-            pca = PCA(n_components=params["n_components"]).fit(X[labels == 1])
-            if pca.components_.shape[0] != 1:
-                raise ValueError("the native novelty path supports n_components == 1 (config.yaml:27)")
-            residual = np.sum(np.sqrt(np.power(X - pca.inverse_transform(pca.transform(X)), 2)), axis=1)
-            threshold = np.percentile(residual, 90)
+            kp = (self.cache_tag, n_frame, params["features"], params["n_components"], "pca")
+            if cache is not None and kp in cache:
+                pca, threshold = cache[kp]
+            else:
+                pca = PCA(n_components=params["n_components"]).fit(X[labels == 1])
+                if pca.components_.shape[0] != 1:
+                    raise ValueError("the native novelty path supports n_components == 1 (config.yaml:27)")
+                residual = np.sum(np.sqrt(np.power(X - pca.inverse_transform(pca.transform(X)), 2)), axis=1)
+                threshold = np.percentile(residual, 90)
+                if cache is not None:
+                    cache[kp] = (pca, threshold)
         else:
             pca, threshold = None, 0.0
 
@@ -84,6 +114,10 @@ class PixelClassificationNonRigidMasker(Masker):
         self.models.append({"n_frame": n_frame, "model": clf})
         self.novelty_det.append({"n_frame": n_frame, "model": pca, "threshold": threshold})
         return bbox_roni
+
+    def close(self):
+        """Release the native context (device buffers, stream)."""
+        self.native.close()
 
     # -- per-frame hot path (reference :45-126) --------------------------------------
     def update(self, bbox, frame, mask, color=None):
@@ -96,9 +130,9 @@ class PixelClassificationNonRigidMasker(Masker):
         cur = self.current_model
 
         segments = np.ascontiguousarray(self.segment_fn(crop), np.int32)
-        n_labels = int(segments.max()) + 1
-        priors = None
+        n_labels, priors = 0, None             # 0: the library takes max(label) + 1 while staging
         if self.index != 0 and params["prior_weight"] != 0.0:
+            n_labels = int(segments.max()) + 1
             priors = self.prior_fn(self.prevFrame, self.prevForegroundMask, crop, segments, n_labels)
 
         blend = bool(self.multi_selection) and len(self.models) > cur + 1

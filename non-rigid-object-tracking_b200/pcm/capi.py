@@ -63,6 +63,7 @@ def load_library():
         "pcm_iou_device": (I, [P, P, L, P, L, I, I, I, P]),
         "pcm_convert": (I, [P, P, I, I, L, I, P, L]),
         "pcm_gather_features": (I, [P, P, I, I, L, P, P]),
+        "pcm_set_debug": (I, [P, I]),
         "pcm_debug_last": (I, [P, P, P, P, P, P, P]),
         "pcm_debug_tables": (I, [P, P, P, P, P]),
         "pcm_launch_count": (L, [P]),
@@ -83,7 +84,7 @@ EXPORTED_SYMBOLS = [
     "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_use_own_stream", "pcm_synchronize",
     "pcm_set_features", "pcm_num_features", "pcm_add_model", "pcm_set_novelty", "pcm_num_models", "pcm_crop_rect",
     "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_convert", "pcm_gather_features",
-    "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_profile_enable", "pcm_profile_read",
+    "pcm_set_debug", "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_profile_enable", "pcm_profile_read",
 ]
 
 KERNEL_NAMES = ["score", "segment_reduce", "segment_decide", "segment_resolve", "mask_dilate", "iou", "planes"]
@@ -107,11 +108,17 @@ def crop_rect(bbox, frame_h, frame_w):
 class Handle:
     """One native masker context (one per tracked target)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, debug=False):
         self.lib = load_library()
         self._h = C.c_void_p()
         self._check(self.lib.pcm_create(int(device), C.byref(self._h)))
         self.device = device
+        if debug:
+            self.set_debug(True)
+
+    def set_debug(self, on=True):
+        """Keep the stage buffers `debug_last` reports (pre-dilation map)."""
+        self._check(self.lib.pcm_set_debug(self._h, int(bool(on))))
 
     def _check(self, rc):
         if rc:
@@ -200,6 +207,7 @@ class Handle:
         labels = np.ascontiguousarray(labels, np.int32)
         if labels.size != rect[2] * rect[3]:
             raise ValueError("labels has %d elements, crop has %d" % (labels.size, rect[2] * rect[3]))
+        n_labels = int(n_labels or 0)          # 0 / None: the library takes max(label) + 1
         pr = None if priors is None else np.ascontiguousarray(priors, np.float32)
         if pr is not None and pr.size != n_labels:
             raise ValueError("priors must have n_labels entries")

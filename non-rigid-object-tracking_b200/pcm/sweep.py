@@ -1,0 +1,196 @@
+"""Hyper-parameter sweep of the reference's benchmark.py (:26-89), sharded over GPUs.
+
+The reference runs VIDEOS x HYPERPARAMS sequences as `python main.py cfg out` subprocesses on
+a thread pool and collects "{iou};{seconds}" files.  Here the same grid is split over the
+ranks of a `torch.distributed` job -- one process per GPU, whole sequences per rank, no
+per-pixel communication -- and the per-sequence scores are brought together with ONE
+collective at the end (`all_gather` of a `[n, 3]` float64 tensor: sequence id, mean IoU,
+seconds; NCCL on GPUs, gloo in the CPU tests).  Rank 0 writes `benchmark_results.csv` with the
+reference's columns (`<video>_benchmark`, `<video>_time`, `avg_benchmark`).
+"""
+import itertools
+import os
+import time
+
+import numpy as np
+
+from . import sequence as seq_mod
+
+# benchmark.py:41-51
+VIDEOS = ["soldier", "frog", "worm", "bmx"]
+HYPERPARAMS = {
+    "n_estimators": [20, 30],
+    "max_depth": [7, 10],
+    "n_components": [1],
+    "novelty_detection": [True, False],
+    "over_segmentation": ["quickshift", "felzenszwalb"],
+    "features": ["8 hsv_lab", "6 lab"],
+    "dilation_kernel": [7],
+    "prior_weight": [0.1, 0.0],
+}
+# frames per clip: only used to balance the shards
+CLIP_FRAMES = {"soldier": 32, "frog": 279, "worm": 243, "bmx": 36, "parachute": 51, "bird_of_paradise": 98}
+
+
+def params_list(hyper=None):
+    """Cartesian product in the reference's order (benchmark.py:53-55)."""
+    hyper = hyper or HYPERPARAMS
+    keys, values = zip(*hyper.items())
+    return [dict(zip(keys, v)) for v in itertools.product(*values)]
+
+
+def build_items(videos=None, hyper=None):
+    """[(sequence id, combo index i, video v, params)], id = i * len(videos) + position of v."""
+    videos = videos or VIDEOS
+    items = []
+    for i, params in enumerate(params_list(hyper)):
+        for k, v in enumerate(videos):
+            items.append((i * len(videos) + k, i, v, params))
+    return items
+
+
+def item_cost(item):
+    """Relative cost of a sequence: per-frame host work (segmentation provider, SIFT prior) plus
+    a share of the fits it may trigger."""
+    _, _, v, p = item
+    frames = CLIP_FRAMES.get(v, 100)
+    per_frame = 1.0 + (3.0 if p.get("prior_weight") else 0.0) + (0.5 if p.get("novelty_detection") else 0.0)
+    return frames * per_frame + 30.0
+
+
+def forest_key(item):
+    _, _, v, p = item
+    return (v, p["features"], p["n_estimators"], p["max_depth"])
+
+
+def partition(items, world):
+    """Longest-processing-time assignment of GROUPS of sequences that share their forests
+    (same video, features, n_estimators, max_depth) so that every fit happens on one rank only.
+    Returns `world` lists of items; deterministic."""
+    groups = {}
+    for it in items:
+        groups.setdefault(forest_key(it), []).append(it)
+    order = sorted(groups.items(), key=lambda kv: (-sum(item_cost(i) for i in kv[1]), str(kv[0])))
+    # more ranks than groups: split the heaviest groups until every rank has work
+    while len(order) < world and any(len(g) > 1 for _, g in order):
+        k, g = max(order, key=lambda kv: (len(kv[1]) > 1, sum(item_cost(i) for i in kv[1])))
+        order.remove((k, g))
+        half = len(g) // 2
+        order += [((k, 0, id(g)), g[:half]), ((k, 1, id(g)), g[half:])]
+        order.sort(key=lambda kv: -sum(item_cost(i) for i in kv[1]))
+    load = [0.0] * world
+    shards = [[] for _ in range(world)]
+    for _, g in order:
+        r = min(range(world), key=lambda j: (load[j], j))
+        shards[r] += g
+        load[r] += sum(item_cost(i) for i in g)
+    for s in shards:
+        s.sort(key=lambda it: (forest_key(it)[0], forest_key(it)[1], forest_key(it)[2], forest_key(it)[3], it[0]))
+    return shards
+
+
+def sequence_config(base, polygons, video, params, videos_path, truth_path):
+    """The per-sequence config of benchmark.py:69-75."""
+    return {**base, "input_video": "%s/%s.mp4" % (videos_path, video), "input_truth": "%s/%s.mp4" % (truth_path, video),
+            "params": dict(params), **polygons[video]}
+
+
+def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Video", truth_path="Input/SegTrack2/Truth",
+              max_frames=None, train_jobs=None, progress=None):
+    """Run this rank's sequences; returns float64 [n, 3] = (sequence id, mean IoU, seconds)."""
+    cache = {}
+    out = np.zeros((len(items), 3), np.float64)
+    for k, (sid, i, v, params) in enumerate(items):
+        cfg = sequence_config(base, polygons, v, params, videos_path, truth_path)
+        cfg["train_jobs"] = train_jobs
+        r = seq_mod.run_sequence(cfg, device=device, model_cache=cache, cache_tag=v, max_frames=max_frames)
+        out[k] = (sid, r["mean_iou"], r["seconds"])
+        if progress:
+            progress(k + 1, len(items), sid, r)
+    return out
+
+
+def gather(local, world, dist=None, device=None):
+    """ONE collective: every rank contributes its padded [n_max, 3] block; returns the [N, 3]
+    array sorted by sequence id (on every rank)."""
+    if world == 1 or dist is None:
+        return local[np.argsort(local[:, 0])] if len(local) else local
+    import torch
+    n = torch.tensor([len(local)], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    n_max = max(int(s.item()) for s in sizes)
+    block = torch.full((max(n_max, 1), 3), -1.0, dtype=torch.float64, device=device)
+    if len(local):
+        block[:len(local)] = torch.from_numpy(local).to(block.device)
+    blocks = [torch.empty_like(block) for _ in range(world)]
+    dist.all_gather(blocks, block)
+    rows = [b[:int(s.item())].cpu().numpy() for b, s in zip(blocks, sizes)]
+    allr = np.concatenate(rows, axis=0) if rows else np.zeros((0, 3))
+    return allr[np.argsort(allr[:, 0])]
+
+
+def results_table(all_rows, videos=None, hyper=None):
+    """pandas frame with the reference's layout (benchmark.py:66-68,86-88)."""
+    import pandas as pd
+    videos = videos or VIDEOS
+    plist = params_list(hyper)
+    results = {i: dict(p) for i, p in enumerate(plist)}
+    for sid, iou, secs in all_rows:
+        i, k = divmod(int(sid), len(videos))
+        results[i][videos[k] + "_benchmark"] = iou
+        results[i][videos[k] + "_time"] = secs
+    table = pd.DataFrame.from_dict(results, orient="index")
+    cols = [v + "_benchmark" for v in videos if v + "_benchmark" in table]
+    if cols:
+        table["avg_benchmark"] = table[cols].mean(axis=1)
+    return table
+
+
+def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, out_csv=None, backend=None,
+        train_jobs=None, log=None):
+    """Entry point used by benchmark.py / bench.py --workload sweep.  Reads RANK / WORLD_SIZE /
+    LOCAL_RANK; returns (summary dict, table or None) -- the table on rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    videos = videos or VIDEOS
+    items = build_items(videos, hyper)
+    if limit:
+        items = items[:limit]
+    shards = partition(items, world)
+    dist = dev = None
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dev = torch.device("cuda", local_rank)
+            if not dist.is_initialized():
+                dist.init_process_group("nccl", device_id=dev)
+        elif not dist.is_initialized():
+            dist.init_process_group(backend)
+        dist.barrier()
+    if train_jobs is None:
+        train_jobs = max(1, (os.cpu_count() or 1) // max(world, 1))
+    t0 = time.time()
+    local = run_shard(shards[rank], base, polygons, device=local_rank, max_frames=max_frames, train_jobs=train_jobs,
+                      progress=(lambda k, n, sid, r: log("[rank %d] %d/%d seq %d iou %.3f %.2fs (train %.2fs)" %
+                                                         (rank, k, n, sid, r["mean_iou"], r["seconds"], r["train_seconds"])))
+                      if log else None)
+    t_local = time.time() - t0
+    all_rows = gather(local, world, dist, dev)
+    t_all = t_local
+    if world > 1:
+        t = torch.tensor([t_local], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_all = float(t.item())
+    summary = dict(n_sequences=len(items), seconds=t_all, sequences_per_s=len(items) / t_all if t_all > 0 else 0.0,
+                   n_gpus=world, per_rank_sequences=[len(s) for s in shards], train_jobs=train_jobs)
+    table = None
+    if rank == 0:
+        table = results_table(all_rows, videos, hyper)
+        if out_csv:
+            table.to_csv(out_csv, index=False)
+    return summary, table

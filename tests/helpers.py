@@ -96,6 +96,7 @@ def native_masker_from_golden(g, device=0, **kw):
     from pcm.providers import make_segment_provider
     m = getMaskerByName("PC", debug=False, frame=g.frames[0], config=g.config, poly_roi=None, update_mask=False,
                         segment_fn=make_segment_provider(g.meta["segments"]), device=device, **kw)
+    m.native.set_debug(True)
     for s in range(g.n_models):
         idx = m.native.add_model_arrays(g.model_frames()[s], g.tree_arrays(s))
         pca = g.pca(s)

@@ -22,7 +22,7 @@ NOVELTY_RTOL = 1e-5
 @pytest.fixture(scope="module")
 def handle():
     from pcm import capi
-    h = capi.Handle(0)
+    h = capi.Handle(0, debug=True)
     yield h
     h.close()
 
@@ -61,7 +61,7 @@ def test_gather_features_matches_reference_golden():
     for ci in range(int(z["feat_n"])):
         crop = z["feat%d_crop" % ci]
         n, spaces = orc.parse_features(str(z["feat%d_features" % ci]))
-        h = capi.Handle(0)
+        h = capi.Handle(0, debug=True)
         h.set_features(n, spaces)
         X = h.gather_features(crop, (0, 0, crop.shape[1], crop.shape[0]))
         assert np.array_equal(X, z["feat%d_X" % ci]), ci
@@ -173,7 +173,7 @@ def test_random_forests_bit_exact(features, shape):
     crop = frame[rect[1]:rect[1] + rect[3], rect[0]:rect[0] + rect[2]]
     trees0 = _random_forest_arrays(rng, 7, 6, F)
     trees1 = _random_forest_arrays(rng, 5, 9, F)
-    h = capi.Handle(0)
+    h = capi.Handle(0, debug=True)
     h.set_features(n, spaces)
     h.add_model_arrays(0, trees0)
     h.add_model_arrays(10, trees1)
@@ -205,7 +205,7 @@ def test_guard_band_labels_take_exact_path():
     lo, hi = 0.5 - 3e-9, 0.5 + 3e-9
     trees = [(np.array([0, -2, -2], np.int32), np.array([127.5 / 255, -2.0, -2.0]),
               np.array([1, -1, -1], np.int32), np.array([2, -1, -1], np.int32), np.array([0.5, lo, hi]))]
-    h = capi.Handle(0)
+    h = capi.Handle(0, debug=True)
     h.set_features(n, spaces)
     h.add_model_arrays(0, trees)
     from pcm.providers import voronoi_segments
@@ -233,7 +233,7 @@ def test_priors_and_prior_weight():
     frame = rng.integers(0, 256, (hgt, wid, 3), dtype=np.uint8)
     F = 3 * 9
     trees = _random_forest_arrays(rng, 6, 4, F)
-    h = capi.Handle(0)
+    h = capi.Handle(0, debug=True)
     h.set_features(1, ["rgb"])
     h.add_model_arrays(0, trees)
     from pcm.providers import grid_segments
@@ -253,7 +253,7 @@ def test_label_out_of_range_is_an_error():
     from pcm import capi
     rng = np.random.default_rng(2)
     frame = rng.integers(0, 256, (40, 40, 3), dtype=np.uint8)
-    h = capi.Handle(0)
+    h = capi.Handle(0, debug=True)
     h.set_features(1, ["rgb"])
     h.add_model_arrays(0, _random_forest_arrays(rng, 2, 2, 27))
     seg = np.zeros((40, 40), np.int32)
@@ -277,7 +277,7 @@ def test_full_hd_frame_properties():
     n, spaces = 8, ["hsv", "lab"]
     F = 390
     trees = _random_forest_arrays(rng, 20, 5, F)
-    h = capi.Handle(0)
+    h = capi.Handle(0, debug=True)
     h.set_features(n, spaces)
     h.add_model_arrays(0, trees)
     rect = capi.crop_rect((20, 20, 1880, 1040), 1080, 1920)
@@ -312,4 +312,70 @@ def test_full_hd_frame_properties():
     a = d["p1"].reshape(1080, 1920)[sub[1] + n:sub[1] + sub[3] - n, sub[0] + n:sub[0] + sub[2] - n]
     b = d2["p1"].reshape(sub[3], sub[2])[n:-n, n:-n]
     assert np.array_equal(a, b)
+    h.close()
+
+
+@pytest.mark.parametrize("n_trees,depth", [(20, 5), (30, 7), (30, 10), (4, 12), (3, 1), (60, 3), (2, 0)])
+def test_forest_shapes_bit_exact(n_trees, depth):
+    """Every K1 instantiation (walk depth 5 / 7 / 10 fixed at compile time, any other depth at
+    run time), forests larger than the constant-bank top table (60 > 48 trees), stumps and a
+    root-only tree: P(fg) bit-equal to the oracle."""
+    from pcm import capi
+    rng = np.random.default_rng(100 * n_trees + depth)
+    n, spaces = 6, ["lab"]
+    F = 3 * (1 + 8 * n)
+    hgt, wid = 75, 131
+    frame = rng.integers(0, 256, (hgt + 9, wid + 14, 3), dtype=np.uint8)
+    rect = (5, 4, wid, hgt)
+    crop = frame[4:4 + hgt, 5:5 + wid]
+    trees = _random_forest_arrays(rng, n_trees, depth, F)
+    h = capi.Handle(0, debug=True)
+    h.set_features(n, spaces)
+    h.add_model_arrays(0, trees)
+    mask = np.zeros(frame.shape, np.uint8)
+    h.update(frame, rect, np.zeros((hgt, wid), np.int32), 1, None, capi.Handle.make_params(0), mask)
+    d = h.debug_last(hgt, wid, 1)
+    X = orc.get_features_int(orc.build_planes(crop, spaces), n)
+    assert np.array_equal(d["p1"], orc.forest_p1(orc.forest_from_arrays(trees, F), X))
+    h.close()
+
+
+def test_label_cache_and_auto_n_labels():
+    """Host path: label chunks equal to the previous call's are not re-sent, changed chunks are;
+    n_labels = 0 lets the library take max(label) + 1.  Masks must equal the oracle's every time."""
+    from pcm import capi
+    from pcm.providers import grid_segments, voronoi_segments
+    rng = np.random.default_rng(33)
+    hgt, wid = 600, 900                       # 2.16 MB of labels: three 1 MiB chunks
+    frame = rng.integers(0, 256, (hgt, wid, 3), dtype=np.uint8)
+    F = 27
+    trees = _random_forest_arrays(rng, 8, 4, F)
+    forest = orc.forest_from_arrays(trees, F)
+    h = capi.Handle(0)
+    h.set_features(1, ["rgb"])
+    h.add_model_arrays(0, trees)
+    p1 = orc.forest_p1(forest, orc.get_features_int([frame], 1))
+
+    def check(seg, rect=(0, 0, wid, hgt), p=p1):
+        S = int(seg.max()) + 1
+        mask = np.zeros((hgt, wid, 3), np.uint8)
+        h.update(frame, rect, seg, 0, None, capi.Handle.make_params(0, dilation_kernel=3), mask)
+        scores, _ = orc.saliency_scores(p, np.zeros(seg.size), seg, 0.0, np.full(S, -1, np.float32), 0.0)
+        x, y, w, hh = rect
+        assert np.array_equal(mask[y:y + hh, x:x + w, 2], orc.dilate(orc.saliency_mask(scores, seg), 3))
+
+    seg = grid_segments(frame, 12)
+    check(seg)
+    check(seg)                                # all chunks cached
+    seg2 = seg.copy()
+    seg2[hgt // 2:, :] = voronoi_segments(frame[hgt // 2:], 40, seed=1) + int(seg.max()) + 1   # later chunks change
+    check(seg2)
+    seg3 = seg2.copy()
+    seg3[0, 0] = int(seg2.max()) + 5          # first chunk changes, raises max(label)
+    check(seg3)
+    check(seg)                                # back to the first map
+    sub = (17, 9, 400, 300)                   # other crop size: cache invalid
+    crop = frame[9:309, 17:417]
+    check(grid_segments(crop, 7), sub, orc.forest_p1(forest, orc.get_features_int([crop], 1)))
+    check(seg)
     h.close()

@@ -1,0 +1,104 @@
+"""Host-side logic of the multi-GPU sweep (pcm/sweep.py): grid construction, sharding and the
+single final gather -- exercised with world_size 2 over gloo on CPU.  The per-sequence GPU work
+itself is covered by tests/test_gpu_sequence.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def test_grid_matches_reference_benchmark_py():
+    from pcm import sweep
+    plist = sweep.params_list()
+    assert len(plist) == 64                                   # benchmark.py:42-51: 2*2*1*2*2*2*1*2
+    assert plist[0] == dict(n_estimators=20, max_depth=7, n_components=1, novelty_detection=True,
+                            over_segmentation="quickshift", features="8 hsv_lab", dilation_kernel=7, prior_weight=0.1)
+    # itertools.product order: the last key varies fastest
+    assert plist[1]["prior_weight"] == 0.0 and plist[2]["features"] == "6 lab"
+    items = sweep.build_items()
+    assert len(items) == 256
+    assert [it[0] for it in items] == list(range(256))
+    assert items[5][1:3] == (1, "frog")                       # id = i * len(videos) + k
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8, 40])
+def test_partition_is_a_balanced_exact_cover(world):
+    from pcm import sweep
+    items = sweep.build_items()
+    shards = sweep.partition(items, world)
+    assert len(shards) == world
+    ids = sorted(it[0] for s in shards for it in s)
+    assert ids == list(range(256))                            # every sequence exactly once
+    assert all(len(s) > 0 for s in shards)
+    loads = [sum(sweep.item_cost(it) for it in s) for s in shards]
+    if world <= 8:
+        assert max(loads) <= 1.35 * (sum(loads) / world)
+        # sequences that share a forest (video, features, n_estimators, max_depth) stay on one rank
+        owner = {}
+        for r, s in enumerate(shards):
+            for it in s:
+                assert owner.setdefault(sweep.forest_key(it), r) == r
+    assert sweep.partition(items, world) == shards            # deterministic
+
+
+def test_results_table_has_the_reference_columns():
+    from pcm import sweep
+    videos = ["soldier", "frog"]
+    hyper = dict(n_estimators=[20, 30], max_depth=[5], prior_weight=[0.0])
+    rows = np.array([[0, 0.5, 1.0], [1, 0.7, 2.0], [2, 0.6, 1.5], [3, 0.8, 2.5]])
+    t = sweep.results_table(rows, videos, hyper)
+    assert list(t.columns) == ["n_estimators", "max_depth", "prior_weight", "soldier_benchmark", "soldier_time",
+                               "frog_benchmark", "frog_time", "avg_benchmark"]
+    assert t.loc[0, "avg_benchmark"] == pytest.approx(0.6) and t.loc[1, "frog_time"] == 2.5
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from pcm import sweep
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    items = sweep.build_items(["soldier", "bmx"], dict(n_estimators=[20, 30], max_depth=[7, 10], features=["6 lab"], prior_weight=[0.0, 0.1]))
+    shard = sweep.partition(items, world)[rank]
+    # stand-in for run_shard: a deterministic score per sequence id
+    local = np.array([[it[0], 0.25 + 0.01 * it[0], 1.0 + it[0]] for it in shard], np.float64).reshape(-1, 3)
+    allr = sweep.gather(local, world, dist, None)
+    q.put((rank, len(shard), allr))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n_items = 2 * 8
+    assert sum(g[1] for g in got) == n_items and all(g[1] > 0 for g in got)
+    for _, _, allr in got:                                    # every rank holds the full, sorted table
+        assert allr.shape == (n_items, 3)
+        assert np.array_equal(allr[:, 0], np.arange(n_items))
+        assert np.allclose(allr[:, 1], 0.25 + 0.01 * np.arange(n_items))
+        assert np.allclose(allr[:, 2], 1.0 + np.arange(n_items))
+
+
+def test_gather_single_rank_needs_no_collective():
+    from pcm import sweep
+    local = np.array([[3, 0.1, 1.0], [1, 0.2, 2.0]])
+    out = sweep.gather(local, 1)
+    assert np.array_equal(out[:, 0], [1, 3])
