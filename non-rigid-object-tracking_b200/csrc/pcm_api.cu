@@ -673,10 +673,17 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     pa.n_flagged = reinterpret_cast<int*>(seg + sl.nflag);
     pa.err = reinterpret_cast<int*>(seg + sl.err);
     {
+        // persistent blocks: the 6.6 KB of lookup tables are staged once per block, so a block
+        // should convert many pixel groups
         const long long groups = (long long)ch * ((cw + 3) / 4);
-        const int blocks = (int)std::min<long long>((groups + 255) / 256, (long long)h->sm_count * 16);
+        static const int per_sm = [] { const char* e = getenv("PCM_K0_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
+        const int blocks = (int)std::min<long long>((groups + 255) / 256, (long long)h->sm_count * per_sm);
         KernelTimer kt(h, 6);
-        planes_kernel<<<std::max(blocks, 1), 256, 0, st>>>(pa);
+        const int mode = (g.n_spaces == 2 && g.space_id[0] == PCM_SPACE_HSV && g.space_id[1] == PCM_SPACE_LAB) ? 1
+                         : (g.n_spaces == 1 && g.space_id[0] == PCM_SPACE_LAB) ? 2 : 0;
+        if (mode == 1) planes_kernel<1><<<std::max(blocks, 1), 256, 0, st>>>(pa);
+        else if (mode == 2) planes_kernel<2><<<std::max(blocks, 1), 256, 0, st>>>(pa);
+        else planes_kernel<0><<<std::max(blocks, 1), 256, 0, st>>>(pa);
     }
     CHECK_LAUNCH(h, "planes_kernel");
 
@@ -767,8 +774,16 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     dl.pre = want_pre ? h->pre.as<uint8_t>() : nullptr;
     dim3 dg((cw + DIL_TW - 1) / DIL_TW, (ch + DIL_TH - 1) / DIL_TH);
     {
+        // 16-byte label loads need every label row to start on a 16-byte boundary
+        const bool vec = (cw % 4 == 0) && (reinterpret_cast<uintptr_t>(d_labels) % 16 == 0);
         KernelTimer kt(h, 4);
-        mask_dilate_kernel<<<dg, 256, 0, st>>>(dl);
+        typedef void (*DilFn)(const DilateArgs);
+        static const DilFn table[2][2][2] = {
+            {{mask_dilate_kernel<false, false, 0>, mask_dilate_kernel<false, false, 7>},
+             {mask_dilate_kernel<false, true, 0>, mask_dilate_kernel<false, true, 7>}},
+            {{mask_dilate_kernel<true, false, 0>, mask_dilate_kernel<true, false, 7>},
+             {mask_dilate_kernel<true, true, 0>, mask_dilate_kernel<true, true, 7>}}};
+        table[vec][dl.pre != nullptr][dl.k == 7]<<<dg, 256, 0, st>>>(dl);
     }
     CHECK_LAUNCH(h, "mask_dilate_kernel");
 

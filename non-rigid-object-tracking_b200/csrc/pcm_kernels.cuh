@@ -109,6 +109,10 @@ struct PlanesArgs {
     int* err;
 };
 
+// MODE 1: features "<n> hsv_lab" (config.yaml:30), MODE 2: "<n> lab" (benchmark.py:48), MODE 0: any
+// combination (space ids read per pixel).  FULL groups (four pixels inside the crop, 4-byte aligned
+// source) take a path without per-pixel bounds checks.
+template <int MODE>
 __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
     __shared__ ColorTables tab;
     for (int i = threadIdx.x; i < (int)(sizeof(ColorTables) / 4); i += blockDim.x)
@@ -119,18 +123,45 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
     }
     __syncthreads();
     const int groups_per_row = (a.cw + 3) >> 2;
-    const long long n_groups = (long long)a.ch * groups_per_row;
-    const int nch = 3 * a.g.n_spaces;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_groups;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(i / groups_per_row);
-        const int c0 = (int)(i - (long long)r * groups_per_row) * 4;
-        const uint8_t* src = a.frame + (long long)(a.cy + r) * a.stride + (long long)(a.cx + c0) * 3;
-        uint32_t out[3 * MAX_SPACES + 1];
+    const int n_groups = a.ch * groups_per_row;          // crop <= 2^30 px (validate_update)
+    const int n_spaces = MODE == 1 ? 2 : (MODE == 2 ? 1 : a.g.n_spaces);
+    const int nch = 3 * n_spaces;
+    constexpr int NOUT = MODE == 1 ? 6 : (MODE == 2 ? 3 : 3 * MAX_SPACES);
+
+    auto convert = [&](int b, int gg, int rr, int j, uint32_t (&out)[NOUT]) {
+        if (MODE == 1 || MODE == 2) {
+            int v0, v1, v2;
+            if (MODE == 1) {
+                bgr2hsv_px(b, gg, rr, tab.sdiv, tab.hdiv, v0, v1, v2);
+                out[0] |= (uint32_t)v0 << (8 * j); out[1] |= (uint32_t)v1 << (8 * j); out[2] |= (uint32_t)v2 << (8 * j);
+            }
+            bgr2lab_px(b, gg, rr, tab.gamma, tab.cbrt_tab, v0, v1, v2);
+            constexpr int o = MODE == 1 ? 3 : 0;
+            out[o] |= (uint32_t)v0 << (8 * j); out[o + 1] |= (uint32_t)v1 << (8 * j); out[o + 2] |= (uint32_t)v2 << (8 * j);
+        } else {
 #pragma unroll
-        for (int p = 0; p < 3 * MAX_SPACES + 1; ++p) out[p] = 0;
-        // 4 pixels = 12 bytes: three aligned words when possible, byte loads otherwise
-        uint32_t w3[3] = {0u, 0u, 0u};
+            for (int q = 0; q < MAX_SPACES; ++q) {
+                if (q < n_spaces) {
+                    int v0, v1, v2;
+                    const int sid = a.g.space_id[q];
+                    if (sid == 1) bgr2hsv_px(b, gg, rr, tab.sdiv, tab.hdiv, v0, v1, v2);
+                    else if (sid == 2) bgr2lab_px(b, gg, rr, tab.gamma, tab.cbrt_tab, v0, v1, v2);
+                    else { v0 = b; v1 = gg; v2 = rr; }
+                    out[3 * q + 0] |= (uint32_t)v0 << (8 * j);
+                    out[3 * q + 1] |= (uint32_t)v1 << (8 * j);
+                    out[3 * q + 2] |= (uint32_t)v2 << (8 * j);
+                }
+            }
+        }
+    };
+
+    // 4 pixels = 12 bytes: three aligned words when possible, byte loads otherwise.  The words of
+    // the thread's NEXT group are requested before the current group is converted.
+    auto fetch = [&](int i, uint32_t (&w3)[3]) {
+        const int r = i / groups_per_row;
+        const int c0 = (i - r * groups_per_row) * 4;
+        const uint8_t* src = a.frame + (long long)(a.cy + r) * a.stride + (long long)(a.cx + c0) * 3;
+        w3[0] = w3[1] = w3[2] = 0u;
         if (c0 + 3 < a.cw && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
 #pragma unroll
             for (int q = 0; q < 3; ++q) w3[q] = __ldg(reinterpret_cast<const uint32_t*>(src) + q);
@@ -139,33 +170,42 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
             for (int q = 0; q < 12; ++q)
                 if (c0 + q / 3 < a.cw) w3[q / 4] |= (uint32_t)__ldg(src + q) << (8 * (q % 4));
         }
+    };
+    const int stride = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t w3[3], nx[3] = {0u, 0u, 0u};
+    if (i < n_groups) fetch(i, w3);
+    for (; i < n_groups; i += stride) {
+        if (i + stride < n_groups) fetch(i + stride, nx);
+        const int r = i / groups_per_row;
+        const int c0 = (i - r * groups_per_row) * 4;
+        uint32_t out[NOUT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (c0 + j < a.cw) {
-                const int b = (w3[(3 * j) / 4] >> (8 * ((3 * j) % 4))) & 0xff;
-                const int gg = (w3[(3 * j + 1) / 4] >> (8 * ((3 * j + 1) % 4))) & 0xff;
-                const int rr = (w3[(3 * j + 2) / 4] >> (8 * ((3 * j + 2) % 4))) & 0xff;
+        for (int p = 0; p < NOUT; ++p) out[p] = 0;
+        uint32_t valid = 0;
+        const bool full = c0 + 3 < a.cw;
+        if (full) {
 #pragma unroll
-                for (int q = 0; q < MAX_SPACES; ++q) {
-                    if (q < a.g.n_spaces) {
-                        int v0, v1, v2;
-                        const int sid = a.g.space_id[q];
-                        if (sid == 1) bgr2hsv_px(b, gg, rr, tab.sdiv, tab.hdiv, v0, v1, v2);
-                        else if (sid == 2) bgr2lab_px(b, gg, rr, tab.gamma, tab.cbrt_tab, v0, v1, v2);
-                        else { v0 = b; v1 = gg; v2 = rr; }
-                        out[3 * q + 0] |= (uint32_t)v0 << (8 * j);
-                        out[3 * q + 1] |= (uint32_t)v1 << (8 * j);
-                        out[3 * q + 2] |= (uint32_t)v2 << (8 * j);
-                    }
+            for (int j = 0; j < 4; ++j)
+                convert((w3[(3 * j) / 4] >> (8 * ((3 * j) % 4))) & 0xff, (w3[(3 * j + 1) / 4] >> (8 * ((3 * j + 1) % 4))) & 0xff,
+                        (w3[(3 * j + 2) / 4] >> (8 * ((3 * j + 2) % 4))) & 0xff, j, out);
+            valid = 0x01010101u;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (c0 + j < a.cw) {
+                    convert((w3[(3 * j) / 4] >> (8 * ((3 * j) % 4))) & 0xff, (w3[(3 * j + 1) / 4] >> (8 * ((3 * j + 1) % 4))) & 0xff,
+                            (w3[(3 * j + 2) / 4] >> (8 * ((3 * j + 2) % 4))) & 0xff, j, out);
+                    valid |= 1u << (8 * j);
                 }
-                out[3 * MAX_SPACES] |= 1u << (8 * j);
             }
         }
         uint8_t* dst = a.planes + (long long)r * a.pitch + c0;
 #pragma unroll
-        for (int p = 0; p < 3 * MAX_SPACES; ++p)
+        for (int p = 0; p < NOUT; ++p)
             if (p < nch) *reinterpret_cast<uint32_t*>(dst + p * a.plane_stride) = out[p];
-        *reinterpret_cast<uint32_t*>(dst + nch * a.plane_stride) = out[3 * MAX_SPACES];
+        *reinterpret_cast<uint32_t*>(dst + nch * a.plane_stride) = valid;
+        w3[0] = nx[0]; w3[1] = nx[1]; w3[2] = nx[2];
     }
 }
 
@@ -697,12 +737,15 @@ __global__ void __launch_bounds__(256) segment_decide_kernel(const DecideArgs a)
     int area = 0;
     double prior = -1.0;
     if (s < a.n_labels) {
+        // independent loads first: this kernel is one dependent-latency chain per label otherwise
         area = a.area[s];
+        const double sum = a.sum[s], asum = a.asum[s];
+        const double pr = a.priors ? (double)a.priors[s] : -1.0;
         if (area <= 0) { a.decision[s] = 0; a.scores[s] = 0.f; }
         else {
-            prior = a.priors ? (double)a.priors[s] : -1.0;
-            const double sc = __dadd_rn(__dmul_rn(__ddiv_rn(a.sum[s], (double)area), omw), __dmul_rn(prior, w));
-            const double band = 2.0 * 5.9604644775390625e-08 * (a.asum[s] / (double)area) * fabs(omw) + 2.4e-7;
+            prior = pr;
+            const double sc = __dadd_rn(__dmul_rn(__ddiv_rn(sum, (double)area), omw), __dmul_rn(prior, w));
+            const double band = 2.0 * 5.9604644775390625e-08 * (asum / (double)area) * fabs(omw) + 2.4e-7;
             flagged = fabs(sc - 0.5) <= band;
             a.decision[s] = sc > 0.5;
             a.scores[s] = (float)sc;
@@ -749,49 +792,106 @@ struct DilateArgs {
     uint8_t* pre;              // optional [ch*cw] pre-dilation map
 };
 
-constexpr int DIL_TW = 128, DIL_TH = 16, DIL_MAXK = 33;
+constexpr int DIL_TW = 128, DIL_TH = 32, DIL_MAXK = 33;
+constexpr int DIL_SH_MAX = DIL_TH + DIL_MAXK - 1;                 // staged rows incl. halo
+constexpr int DIL_PITCH = DIL_TW + 4 * ((DIL_MAXK + 2) / 4 + 1);   // staged row pitch (bytes, multiple of 4)
+static_assert(DIL_MAXK - 1 <= 32, "one halo label per lane");
 
-// One block = 128 x 16 output pixels.  Stage 1 gathers decision[label] for the tile plus its
-// k-1 halo (all label loads of a thread are issued before the dependent decision loads),
-// stage 2 ORs along rows, stage 3 ORs along columns and writes 4 pixels per thread.
+// One block = 128 x 32 output pixels, 8 warps.
+//   stage 1  decision[label] for the tile plus its k-1 halo -> s0 (0/1 bytes).  A warp owns whole
+//            rows: each lane fetches four labels of the tile interior with one 16-byte load (when
+//            the label rows are 16-byte aligned) and lanes < k-1 fetch one halo label; the loads
+//            of a batch of rows are all in flight before the dependent decision loads.  The
+//            interior starts at a 4-byte aligned column of s0 (PAD bytes of left padding).
+//   stage 2  OR along rows, four pixels per thread: the k shifted windows of a 32-bit word come
+//            from funnel shifts of adjacent words (SWAR) -> s1
+//   stage 3  OR along columns on 32-bit words, * 255, one 4-byte store per thread
+// KF > 0: kernel size fixed at compile time (7 = every config of the reference); KF = 0: a.k
+template <bool VEC, bool PRE, int KF>
 __global__ void __launch_bounds__(256) mask_dilate_kernel(const DilateArgs a) {
-    __shared__ __align__(16) uint8_t s0[(DIL_TH + DIL_MAXK) * (DIL_TW + DIL_MAXK + 3)];
-    __shared__ __align__(16) uint8_t s1[(DIL_TH + DIL_MAXK) * DIL_TW];
-    const int k = a.k, before = k / 2, SW = DIL_TW + k - 1, SH = DIL_TH + k - 1;
+    __shared__ __align__(16) uint8_t s0[DIL_SH_MAX * DIL_PITCH];
+    __shared__ __align__(16) uint8_t s1[DIL_SH_MAX * DIL_TW];
+    const int k = KF > 0 ? KF : a.k, before = k / 2, after = k - 1 - before, SH = DIL_TH + k - 1;
+    const int pad = (4 - (before & 3)) & 3;         // s0 column of tile column x is x - tx0 + before + pad
     const int tx0 = blockIdx.x * DIL_TW, ty0 = blockIdx.y * DIL_TH;
-    constexpr int B = 4;
-    for (int i0 = threadIdx.x; i0 < SW * SH; i0 += B * 256) {
-        int lab[B];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x4 = tx0 + 4 * lane;                  // first of the lane's four interior columns
+    // halo column of this lane: lanes [0, before) left of the tile, [before, k-1) right of it
+    const int hx = lane < before ? tx0 - before + lane : tx0 + DIL_TW + (lane - before);
+    const bool h_on = lane < k - 1 && hx >= 0 && hx < a.cw;
+    const int hs = hx - tx0 + before + pad;         // its s0 column
+    constexpr int RB = 4;                           // rows per batch of a warp
+    for (int r0 = warp * RB; r0 < SH; r0 += 8 * RB) {
+        int4 v4[RB];
+        int vh[RB];
 #pragma unroll
-        for (int j = 0; j < B; ++j) {
-            const int i = i0 + j * 256;
-            lab[j] = -1;
-            if (i < SW * SH) {
-                const int r = i / SW, c = i - r * SW;
-                const int y = ty0 - before + r, x = tx0 - before + c;
-                if (y >= 0 && y < a.ch && x >= 0 && x < a.cw) lab[j] = __ldg(a.labels + (size_t)y * a.cw + x);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < B; ++j) {
-            const int i = i0 + j * 256;
-            if (i < SW * SH) {
-                const uint8_t v = (lab[j] >= 0 && lab[j] < a.n_labels) ? __ldg(a.decision + lab[j]) : 0;
-                s0[i] = v;
-                if (a.pre && lab[j] >= 0) {
-                    const int r = i / SW, c = i - r * SW;
-                    if (r >= before && r < before + DIL_TH && c >= before && c < before + DIL_TW)
-                        a.pre[(size_t)(ty0 - before + r) * a.cw + (tx0 - before + c)] = v ? 255 : 0;
+        for (int q = 0; q < RB; ++q) {
+            const int r = r0 + q, y = ty0 - before + r;
+            const bool row_ok = r < SH && y >= 0 && y < a.ch;
+            const int32_t* lrow = a.labels + (size_t)(row_ok ? y : 0) * a.cw;
+            v4[q] = make_int4(-1, -1, -1, -1);
+            if (row_ok) {
+                if (VEC && x4 + 3 < a.cw) v4[q] = __ldg(reinterpret_cast<const int4*>(lrow + x4));
+                else {
+                    if (x4 + 0 < a.cw) v4[q].x = __ldg(lrow + x4 + 0);
+                    if (x4 + 1 < a.cw) v4[q].y = __ldg(lrow + x4 + 1);
+                    if (x4 + 2 < a.cw) v4[q].z = __ldg(lrow + x4 + 2);
+                    if (x4 + 3 < a.cw) v4[q].w = __ldg(lrow + x4 + 3);
                 }
             }
+            vh[q] = (row_ok && h_on) ? __ldg(lrow + hx) : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+            const int r = r0 + q, y = ty0 - before + r;
+            if (r >= SH) break;
+            const int l4[4] = {v4[q].x, v4[q].y, v4[q].z, v4[q].w};
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t v = ((unsigned)l4[j] < (unsigned)a.n_labels) ? __ldg(a.decision + l4[j]) : 0u;
+                word |= v << (8 * j);
+            }
+            *reinterpret_cast<uint32_t*>(s0 + r * DIL_PITCH + before + pad + 4 * lane) = word;
+            if (PRE && r >= before && r < before + DIL_TH && y < a.ch) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (l4[j] >= 0) a.pre[(size_t)y * a.cw + x4 + j] = ((word >> (8 * j)) & 1u) ? 255 : 0;
+            }
+            if (lane < k - 1) s0[r * DIL_PITCH + hs] = ((unsigned)vh[q] < (unsigned)a.n_labels) ? __ldg(a.decision + vh[q]) : 0;
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < SH * DIL_TW; i += 256) {
-        const int r = i / DIL_TW, c = i - r * DIL_TW;
-        uint8_t v = 0;
-        for (int d = 0; d < k; ++d) v |= s0[r * SW + c + d];
-        s1[i] = v;
+    // stage 2: output word j of row r = OR over d < k of the source bytes starting at s0 column pad + 4j + d
+    for (int i = threadIdx.x; i < SH * (DIL_TW / 4); i += 256) {
+        const int r = i / (DIL_TW / 4), j = i - r * (DIL_TW / 4);
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(s0 + r * DIL_PITCH) + j;
+        uint32_t acc = 0;
+        if (KF > 0) {
+            constexpr int NW = (3 + (KF > 0 ? KF : 1) - 1) / 4 + 2;      // words that can be touched
+            uint32_t w[NW];
+#pragma unroll
+            for (int q = 0; q < NW; ++q) w[q] = row[q];
+#pragma unroll
+            for (int d = 0; d < (KF > 0 ? KF : 1); ++d) {
+                // byte offset pad + d: pad is block-uniform, so the word pick is a uniform select
+                const int o = pad + d;
+                uint32_t lo = w[0], hi = w[1];
+#pragma unroll
+                for (int q = 1; q < NW - 1; ++q)
+                    if ((o >> 2) == q) { lo = w[q]; hi = w[q + 1]; }
+                acc |= __funnelshift_r(lo, hi, 8 * (o & 3));
+            }
+        } else {
+            int wi = pad >> 2, sh = (pad & 3) * 8;      // pad < 4: wi = 0
+            uint32_t lo = row[wi], hi = row[wi + 1];
+            for (int d = 0; d < k; ++d) {
+                acc |= __funnelshift_r(lo, hi, sh);
+                sh += 8;
+                if (sh == 32) { sh = 0; ++wi; lo = hi; hi = row[wi + 1]; }
+            }
+        }
+        reinterpret_cast<uint32_t*>(s1)[i] = acc;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < DIL_TH * DIL_TW / 4; i += 256) {
@@ -799,7 +899,12 @@ __global__ void __launch_bounds__(256) mask_dilate_kernel(const DilateArgs a) {
         const int y = ty0 + r, x = tx0 + c;
         if (y >= a.ch || x >= a.cw) continue;
         uint32_t v = 0;
-        for (int d = 0; d < k; ++d) v |= *reinterpret_cast<const uint32_t*>(s1 + (r + d) * DIL_TW + c);
+        if (KF > 0) {
+#pragma unroll
+            for (int d = 0; d < (KF > 0 ? KF : 1); ++d) v |= *reinterpret_cast<const uint32_t*>(s1 + (r + d) * DIL_TW + c);
+        } else {
+            for (int d = 0; d < k; ++d) v |= *reinterpret_cast<const uint32_t*>(s1 + (r + d) * DIL_TW + c);
+        }
         // bytes are 0/1 -> 0/255
         v = (v & 0x01010101u) * 255u;
         uint8_t* dst = a.mask + (size_t)(a.cy + y) * a.mask_stride + (a.cx + x);

@@ -379,3 +379,53 @@ def test_label_cache_and_auto_n_labels():
     check(grid_segments(crop, 7), sub, orc.forest_p1(forest, orc.get_features_int([crop], 1)))
     check(seg)
     h.close()
+
+
+def test_4k_multi_object_frame():
+    """BASELINE config[4] shape: 3840x2160 frame, four targets with ~600x800 boxes (640x840
+    crops), one masker context per target writing into ONE shared mask (main.py:286,302):
+    sampled P(fg) bit-equal to the oracle, every crop's mask equal to the oracle's decision +
+    dilation, later targets overwrite earlier ones where crops overlap (:246), IoU counts over
+    the whole 4K frame equal numpy's."""
+    from pcm import capi
+    from pcm.providers import grid_segments
+    from pcm.synthetic import SyntheticSequence
+    rng = np.random.default_rng(44)
+    seq = SyntheticSequence(3840, 2160, 2, seed=1, n_targets=4)
+    frame = seq.frame(1)
+    n, spaces, F = 8, ["hsv", "lab"], 390
+    planes_full = None
+    mask = np.zeros_like(frame)
+    want = np.zeros(frame.shape[:2], np.uint8)
+    boxes = [(300, 500, 800, 600), (1100, 700, 800, 600), (1800, 620, 800, 600), (2900, 1500, 800, 600)]   # 2nd/3rd overlap
+    for t, box in enumerate(boxes):
+        trees = _random_forest_arrays(rng, 20, 5, F)
+        h = capi.Handle(0, debug=True)
+        h.set_features(n, spaces)
+        h.add_model_arrays(0, trees)
+        rect = capi.crop_rect(box, 2160, 3840)
+        x, y, w, hh = rect
+        assert (w, hh) == (840, 640)
+        crop = frame[y:y + hh, x:x + w]
+        seg = grid_segments(crop, 16)
+        S = int(seg.max()) + 1
+        h.update(frame, rect, seg, S, None, capi.Handle.make_params(0, dilation_kernel=7), mask)
+        d = h.debug_last(hh, w, S)
+        planes = orc.build_planes(crop, spaces)
+        rr = np.concatenate([rng.integers(0, hh, 4000), [0, hh - 1, 0, hh - 1]])
+        cc = np.concatenate([rng.integers(0, w, 4000), [0, 0, w - 1, w - 1]])
+        assert np.array_equal(d["p1"].reshape(hh, w)[rr, cc],
+                              orc.forest_p1(orc.forest_from_arrays(trees, F), orc.features_at(planes, n, rr, cc)))
+        scores, _ = orc.saliency_scores_fast(d["p1"], seg)
+        near = np.abs(scores.astype(np.float64) - 0.5) < 1e-4
+        pre = orc.saliency_mask(scores, seg)
+        ok = ~near[seg]
+        assert np.array_equal(d["pre"][ok], pre[ok])
+        want[y:y + hh, x:x + w] = orc.dilate(d["pre"], 7)          # overwrite, like the reference
+        assert np.array_equal(mask[..., 2], want), "target %d" % t
+        h.close()
+    assert not mask[..., :2].any()
+    truth = seq.truth(1)
+    hq = capi.Handle(0)
+    assert hq.iou_counts(mask[..., 2], truth) == orc.iou_counts(mask[..., 2], truth)
+    hq.close()
