@@ -61,27 +61,65 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every few ms
+    (nvidia-ml-py), or the `nvidia-smi --query-gpu` line of the profiling recipe if NVML is
+    not importable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
-        self.samples = []
+        self.samples = []          # (sm_mhz, sm_max_mhz, [reason flags])
         self.stop = threading.Event()
         self.gpu = gpu_index
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu_index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.masks = [getattr(pynvml, n, 0) for n in ("nvmlClocksEventReasonHwSlowdown", "nvmlClocksEventReasonHwThermalSlowdown",
+                                                          "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksEventReasonSwPowerCap")]
+            if not all(self.masks):
+                self.masks = [0x8, 0x40, 0x20, 0x4]      # NVML bit values of the four reasons
+        except Exception:
+            self.nvml = None
         self.thread = threading.Thread(target=self.run, daemon=True)
+
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[i])
+            except Exception:
+                pass
+        return i
+
+    def sample_once(self):
+        if self.nvml is not None:
+            p = self.nvml
+            mhz = float(p.nvmlDeviceGetClockInfo(self.handle, p.NVML_CLOCK_SM))
+            try:
+                bits = int(p.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                bits = int(p.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.samples.append((mhz, self.max_mhz, [bool(bits & m) for m in self.masks]))
+        else:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+            parts = [q.strip() for q in out.strip().split(",")]
+            if len(parts) >= 6:
+                self.samples.append((float(parts[0]), float(parts[1]), [q.lower().startswith("active") for q in parts[2:6]]))
 
     def run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                self.sample_once()
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.004 if self.nvml is not None else 0.1)
 
     def __enter__(self):
         self.thread.start()
@@ -94,12 +132,10 @@ class ClockSampler:
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = [x[0] for x in self.samples]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(x[2][i] for x in self.samples)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(x[1] for x in self.samples), "reasons": reasons,
+                "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def sequence_state(i, model_frames):
@@ -496,8 +532,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # stdout carries exactly ONE JSON line; everything else (sklearn / masker prints) -> stderr
+    # stdout carries exactly ONE JSON line; everything else -> stderr.  Python-level prints
+    # (sklearn, masker) are redirected through sys.stdout, C-level ones (NCCL prints its version
+    # banner straight to file descriptor 1) through the descriptor itself.
     real_stdout = sys.stdout
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
     try:
         if args.impl == "reference":
@@ -508,6 +549,8 @@ def main():
             out = run_b200(args, rank, world, local_rank)
     finally:
         sys.stdout = real_stdout
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
     if out is not None:
         print(json.dumps(out), flush=True)
 

@@ -128,6 +128,10 @@ int pcm_update(pcm_handle* h, const uint8_t* frame, int frame_h, int frame_w, in
                const pcm_update_params* params,
                uint8_t* mask, int64_t mask_row_stride, int64_t mask_pixel_stride);
 
+/* labels == NULL: continue from the preceding pcm_quickshift on this handle -- the label map
+ * AND the crop pixels are the ones that call left on the device (`frame` and `rect` must be
+ * the same as in that call; the frame is not read again).  n_labels is ignored. */
+
 /* Same work on DEVICE buffers, asynchronous on the handle's stream.
  * d_mask is a dense plane (pixel stride 1) of frame_h x frame_w, rows
  * mask_row_stride bytes apart; only the crop rectangle is written. */
@@ -149,6 +153,30 @@ int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stride, int64_t
 int pcm_iou_device(pcm_handle* h, const uint8_t* d_mask, int64_t mask_row_stride,
                    const uint8_t* d_truth, int64_t truth_row_stride, int truth_channels,
                    int height, int width, int64_t* d_counts);
+
+/* ---- over-segmentation of the crop (:70-71), SURVEY.md §8 row f-1 ----------- */
+
+/* skimage.segmentation.quickshift(crop, kernel_size, max_dist, ratio, random_seed) of
+ * scikit-image 0.17.2 (environment.yaml:12) on the crop `rect` of a HOST frame:
+ * sRGB->Lab (float64; the BGR channel order is taken as it comes, like the reference does),
+ * window densities, nearest-higher-density parent, links longer than max_dist cut, labels
+ * numbered like np.unique(root, return_inverse=True).
+ *   noise       h*w float64 = RandomState(random_seed).normal(scale=1e-5, size=(h, w)), the
+ *               tie-breaking noise of _quickshift_cy.pyx, or NULL to reuse the noise of the
+ *               previous call with the same crop size
+ *   labels_out  h*w int32 on the host, or NULL when only the device-resident map is needed
+ *               (pcm_update with labels == NULL)
+ *   n_labels_out  number of segments
+ * Limits: ceil(3 * kernel_size) <= 15.  Synchronous. */
+int pcm_quickshift(pcm_handle* h, const uint8_t* frame, int frame_h, int frame_w, int64_t frame_stride,
+                   const int rect[4], double ratio, double kernel_size, double max_dist,
+                   const double* noise, int32_t* labels_out, int* n_labels_out);
+
+/* Device variant: d_frame / d_noise (may be NULL: no noise) / d_labels_out (h*w int32, may be
+ * NULL) are device pointers; waits for the stream to return the segment count. */
+int pcm_quickshift_device(pcm_handle* h, const uint8_t* d_frame, int frame_h, int frame_w, int64_t frame_stride,
+                          const int rect[4], double ratio, double kernel_size, double max_dist,
+                          const double* d_noise, int32_t* d_labels_out, int* n_labels_out);
 
 /* ---- parity taps (tests, smoke; not needed by the reference flow) -------- */
 

@@ -5,6 +5,7 @@
 // every entry point either runs the CUDA kernels or fails.
 #include "../../include/pcm_b200.h"
 #include "pcm_kernels.cuh"
+#include "pcm_quickshift.cuh"
 #include "pcm_host.h"
 
 #include <cudaTypedefs.h>
@@ -163,6 +164,16 @@ struct pcm_handle {
     // (label_cache_px elements, 1 MiB chunks); a chunk whose bytes are unchanged is not re-sent
     size_t label_cache_px = 0;
     std::vector<int> label_chunk_max;
+
+    // quickshift over-segmentation (pcm_quickshift): scratch, the resident label map and the crop
+    // it was computed from (pcm_update with labels == NULL continues from here)
+    DevBuf qs_lab, qs_dens, qs_noise, qs_parent, qs_root, qs_flag, qs_rank, qs_sums, qs_labels, qs_lin, qs_count;
+    PinBuf h_noise;
+    int qs_cw = 0, qs_ch = 0, qs_n_labels = 0;
+    int qs_noise_cw = 0, qs_noise_ch = 0;
+    bool qs_valid = false;
+    const uint8_t* qs_frame_ptr = nullptr;     // host frame the resident crop was staged from
+    int qs_rect[4] = {0, 0, 0, 0};
 
     // description of the last update (for pcm_debug_last)
     int last_cw = 0, last_ch = 0, last_S = 0;
@@ -432,6 +443,8 @@ extern "C" int pcm_create(int device, pcm_handle** out) {
     CUDA_TRY(cudaMemcpy(h->d_tables, &h->h_tables, sizeof(ColorTables), cudaMemcpyHostToDevice));
     for (int i = 0; i < N_SCORE_VARIANTS; ++i)
         CUDA_TRY(cudaFuncSetAttribute(score_variant(i).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(qs_window_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+    CUDA_TRY(cudaFuncSetAttribute(qs_window_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
     *out = h;
     return PCM_OK;
 }
@@ -445,7 +458,10 @@ extern "C" void pcm_destroy(pcm_handle* h) {
     for (DevBuf* b : {&h->frame, &h->labels, &h->priors, &h->planes, &h->sched, &h->p1, &h->sa, &h->seg, &h->rmin, &h->rmax, &h->decision,
                       &h->scores, &h->flagged, &h->mask, &h->pre, &h->counts})
         b->release();
-    for (PinBuf* b : {&h->h_frame, &h->h_labels, &h->h_priors, &h->h_mask, &h->h_small}) b->release();
+    for (DevBuf* b : {&h->qs_lab, &h->qs_dens, &h->qs_noise, &h->qs_parent, &h->qs_root, &h->qs_flag, &h->qs_rank, &h->qs_sums,
+                      &h->qs_labels, &h->qs_lin, &h->qs_count})
+        b->release();
+    for (PinBuf* b : {&h->h_frame, &h->h_labels, &h->h_priors, &h->h_mask, &h->h_small, &h->h_noise}) b->release();
     for (auto& t : h->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : h->free_events) cudaEventDestroy(e);
     if (h->d_tables) cudaFree(h->d_tables);
@@ -794,6 +810,64 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     return PCM_OK;
 }
 
+// D2H of the dense crop mask, wait, scatter into the caller's (possibly interleaved) mask
+static int finish_host_update(pcm_handle* h, const int rect[4], uint8_t* mask, int64_t mask_row_stride, int64_t mask_pixel_stride) {
+    const int cx = rect[0], cy = rect[1], cw = rect[2], ch = rect[3];
+    const size_t npx = (size_t)cw * ch;
+    cudaStream_t st = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->h_mask.p, h->mask.p, npx, cudaMemcpyDeviceToHost, st));
+    int rc = check_label_error(h, true);
+    if (rc) return rc;
+    h->trace.lap(HostTrace::UPD_WAIT);
+    const uint8_t* hm = h->h_mask.as<uint8_t>();
+    HostPool& pool = HostPool::instance();
+    const int parts = std::min(pool.size(), std::max(1, (int)(npx >> 16)));
+    pool.parallel_for(parts, [&](int part) {
+        const int a0 = (int)((long long)ch * part / parts), a1 = (int)((long long)ch * (part + 1) / parts);
+        for (int r = a0; r < a1; ++r)
+            scatter_strided(hm + (size_t)r * cw, mask + (size_t)(cy + r) * mask_row_stride + (size_t)cx * mask_pixel_stride,
+                            mask_pixel_stride, cw);
+    });
+    h->trace.lap(HostTrace::UPD_SCATTER);
+    return PCM_OK;
+}
+
+// pcm_update(labels == NULL): the crop pixels and the label map are the ones the preceding
+// pcm_quickshift on this handle left on the device
+static int update_from_quickshift(pcm_handle* h, const uint8_t* frame, int H, int W, int64_t stride, const int rect[4],
+                                  const float* priors, const pcm_update_params* params, uint8_t* mask,
+                                  int64_t mask_row_stride, int64_t mask_pixel_stride) {
+    if (!rect) return fail(PCM_E_INVALID, "pcm_update: NULL rect");
+    if (!h->qs_valid || h->qs_frame_ptr != frame || memcmp(h->qs_rect, rect, sizeof h->qs_rect) != 0)
+        return fail(PCM_E_STATE, "pcm_update: labels == NULL needs a preceding pcm_quickshift of the same frame and rect");
+    int rc = validate_update(h, H, W, rect, h->qs_n_labels, params);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->trace.start();
+    const int cw = rect[2], ch = rect[3];
+    const size_t npx = (size_t)cw * ch;
+    cudaStream_t st = h->stream;
+    CUDA_TRY(h->h_mask.reserve(npx));
+    CUDA_TRY(h->mask.reserve(npx));
+    CUDA_TRY(h->h_small.reserve(64));
+    const float* d_priors = nullptr;
+    if (priors) {
+        CUDA_TRY(h->h_priors.reserve(sizeof(float) * (size_t)h->qs_n_labels));
+        CUDA_TRY(h->priors.reserve(sizeof(float) * (size_t)h->qs_n_labels));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        memcpy(h->h_priors.p, priors, sizeof(float) * (size_t)h->qs_n_labels);
+        CUDA_TRY(cudaMemcpyAsync(h->priors.p, h->h_priors.p, sizeof(float) * (size_t)h->qs_n_labels, cudaMemcpyHostToDevice, st));
+        d_priors = h->priors.as<float>();
+    }
+    h->trace.lap(HostTrace::UPD_STAGE);
+    const int crop_rect[4] = {0, 0, cw, ch};
+    rc = enqueue_update(h, h->frame.as<uint8_t>(), ch, cw, (int64_t)cw * 3, crop_rect, h->qs_labels.as<int32_t>(),
+                        h->qs_n_labels, d_priors, params, h->mask.as<uint8_t>(), cw, 0, 0, h->keep_pre);
+    if (rc) return rc;
+    h->trace.lap(HostTrace::UPD_ENQUEUE);
+    return finish_host_update(h, rect, mask, mask_row_stride, mask_pixel_stride);
+}
+
 extern "C" int pcm_update_device(pcm_handle* h, const uint8_t* d_frame, int H, int W, int64_t stride, const int rect[4],
                                  const int32_t* d_labels, int n_labels, const float* d_priors,
                                  const pcm_update_params* params, uint8_t* d_mask, int64_t mask_row_stride) {
@@ -809,7 +883,9 @@ extern "C" int pcm_update_device(pcm_handle* h, const uint8_t* d_frame, int H, i
 extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int64_t stride, const int rect[4],
                           const int32_t* labels, int n_labels, const float* priors, const pcm_update_params* params,
                           uint8_t* mask, int64_t mask_row_stride, int64_t mask_pixel_stride) {
-    if (!h || !frame || !labels || !mask) return fail(PCM_E_INVALID, "pcm_update: NULL argument");
+    if (!h || !frame || !mask) return fail(PCM_E_INVALID, "pcm_update: NULL argument");
+    if (!labels) return update_from_quickshift(h, frame, H, W, stride, rect, priors, params, mask, mask_row_stride, mask_pixel_stride);
+    h->qs_valid = false;                               // the resident crop is about to be replaced
     const bool auto_labels = n_labels <= 0;            // n_labels = max(label) + 1, found while staging
     if (auto_labels && priors) return fail(PCM_E_INVALID, "pcm_update: priors need an explicit n_labels");
     int rc = validate_update(h, H, W, rect, auto_labels ? 1 : n_labels, params);
@@ -900,26 +976,8 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
     rc = enqueue_update(h, h->frame.as<uint8_t>(), ch, cw, (int64_t)row_bytes, crop_rect, h->labels.as<int32_t>(),
                         n_labels, d_priors, params, h->mask.as<uint8_t>(), cw, 0, 0, h->keep_pre);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(h->h_mask.p, h->mask.p, npx, cudaMemcpyDeviceToHost, st));
     h->trace.lap(HostTrace::UPD_ENQUEUE);
-    rc = check_label_error(h, true);
-    if (rc) return rc;
-    h->trace.lap(HostTrace::UPD_WAIT);
-    // scatter the dense crop into the caller's (possibly interleaved) mask
-    const uint8_t* hm = h->h_mask.as<uint8_t>();
-    {
-        const int parts = std::min(pool.size(), std::max(1, (int)(npx >> 16)));
-        pool.parallel_for(parts, [&](int part) {
-            const int a0 = (int)((long long)ch * part / parts), a1 = (int)((long long)ch * (part + 1) / parts);
-            for (int r = a0; r < a1; ++r) {
-                uint8_t* dst = mask + (size_t)(cy + r) * mask_row_stride + (size_t)cx * mask_pixel_stride;
-                const uint8_t* src = hm + (size_t)r * cw;
-                scatter_strided(src, dst, mask_pixel_stride, cw);
-            }
-        });
-    }
-    h->trace.lap(HostTrace::UPD_SCATTER);
-    return PCM_OK;
+    return finish_host_update(h, rect, mask, mask_row_stride, mask_pixel_stride);
 }
 
 extern "C" int pcm_iou_device(pcm_handle* h, const uint8_t* d_mask, int64_t mask_row_stride, const uint8_t* d_truth,
@@ -957,6 +1015,7 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
     CUDA_TRY(h->counts.reserve(2 * sizeof(int64_t)));
     CUDA_TRY(h->h_small.reserve(64));
     CUDA_TRY(cudaStreamSynchronize(st));
+    h->qs_valid = false;                               // the frame scratch is reused for the truth image
     h->trace.start();
     HostPool& pool = HostPool::instance();
     uint8_t* hm = h->h_mask.as<uint8_t>();
@@ -1004,6 +1063,167 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
     counts[0] = hc[0];
     counts[1] = hc[1];
     h->last_valid = false;   // frame / mask scratch was reused
+    return PCM_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// API: quickshift over-segmentation
+// ---------------------------------------------------------------------------------
+static int enqueue_quickshift(pcm_handle* h, const uint8_t* d_frame, int64_t stride, int cx, int cy, int cw, int ch,
+                              double ratio, double kernel_size, double max_dist, const double* d_noise,
+                              int32_t* d_labels_out) {
+    if (!(kernel_size >= 1.0)) return fail(PCM_E_INVALID, "quickshift: kernel_size must be >= 1");
+    const int kw = (int)ceil(3.0 * kernel_size);
+    if (kw > QS_MAX_KW) return fail(PCM_E_LIMIT, "quickshift: window half width %d > %d", kw, QS_MAX_KW);
+    const size_t n = (size_t)cw * ch;
+    if (n > (1u << 30)) return fail(PCM_E_LIMIT, "quickshift: crop too large");
+    cudaStream_t st = h->stream;
+    CUDA_TRY(h->qs_lab.reserve(3 * n * sizeof(double)));
+    CUDA_TRY(h->qs_dens.reserve(n * sizeof(double)));
+    CUDA_TRY(h->qs_parent.reserve(n * sizeof(int)));
+    CUDA_TRY(h->qs_root.reserve(n * sizeof(int)));
+    CUDA_TRY(h->qs_flag.reserve(n * sizeof(int)));
+    CUDA_TRY(h->qs_rank.reserve(n * sizeof(int)));
+    const int n_blocks = (int)((n + QS_SCAN_ELEMS - 1) / QS_SCAN_ELEMS);
+    CUDA_TRY(h->qs_sums.reserve((size_t)n_blocks * sizeof(int)));
+    CUDA_TRY(h->qs_labels.reserve(n * sizeof(int32_t)));
+    CUDA_TRY(h->qs_count.reserve(sizeof(int)));
+    if (!h->qs_lin.p) {
+        // sRGB companding table of skimage.color.rgb2xyz for the 256 byte values
+        double lin[256];
+        for (int v = 0; v < 256; ++v) {
+            const double x = v / 255.0;
+            lin[v] = x > 0.04045 ? pow((x + 0.055) / 1.055, 2.4) : x / 12.92;
+        }
+        CUDA_TRY(h->qs_lin.reserve(sizeof lin));
+        CUDA_TRY(cudaMemcpy(h->qs_lin.p, lin, sizeof lin, cudaMemcpyHostToDevice));
+    }
+    QsArgs a{};
+    a.frame = d_frame; a.stride = stride; a.cx = cx; a.cy = cy; a.cw = cw; a.ch = ch;
+    a.lin = h->qs_lin.as<double>();
+    a.ratio = ratio;
+    a.lab = h->qs_lab.as<double>();
+    a.dens = h->qs_dens.as<double>();
+    a.noise = d_noise;
+    a.parent = h->qs_parent.as<int>();
+    a.root = h->qs_root.as<int>();
+    a.kw = kw;
+    a.inv = -0.5 / (kernel_size * kernel_size);
+    a.max_dist = max_dist;
+    const int flat_blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
+    qs_lab_kernel<<<flat_blocks, 256, 0, st>>>(a);
+    CHECK_LAUNCH(h, "qs_lab_kernel");
+    const dim3 grid((cw + QS_BW - 1) / QS_BW, (ch + QS_BH - 1) / QS_BH);
+    const size_t tile = (size_t)(QS_BW + 2 * kw) * (QS_BH + 2 * kw) * sizeof(double);
+    qs_window_kernel<false><<<grid, QS_BW * QS_BH, 3 * tile, st>>>(a);
+    CHECK_LAUNCH(h, "qs_window_kernel<density>");
+    qs_window_kernel<true><<<grid, QS_BW * QS_BH, 4 * tile, st>>>(a);
+    CHECK_LAUNCH(h, "qs_window_kernel<parent>");
+    CUDA_TRY(cudaMemsetAsync(h->qs_flag.p, 0, n * sizeof(int), st));
+    qs_root_kernel<<<flat_blocks, 256, 0, st>>>(a.parent, a.root, h->qs_flag.as<int>(), (int)n);
+    CHECK_LAUNCH(h, "qs_root_kernel");
+    qs_scan_reduce_kernel<<<n_blocks, 256, 0, st>>>(h->qs_flag.as<int>(), (int)n, h->qs_sums.as<int>());
+    CHECK_LAUNCH(h, "qs_scan_reduce_kernel");
+    qs_scan_sums_kernel<<<1, 256, 0, st>>>(h->qs_sums.as<int>(), n_blocks, h->qs_count.as<int>());
+    CHECK_LAUNCH(h, "qs_scan_sums_kernel");
+    qs_scan_apply_kernel<<<n_blocks, 256, 0, st>>>(h->qs_flag.as<int>(), (int)n, h->qs_sums.as<int>(), h->qs_rank.as<int>());
+    CHECK_LAUNCH(h, "qs_scan_apply_kernel");
+    qs_label_kernel<<<flat_blocks, 256, 0, st>>>(a.root, h->qs_rank.as<int>(), h->qs_labels.as<int32_t>(), (int)n);
+    CHECK_LAUNCH(h, "qs_label_kernel");
+    if (d_labels_out) CUDA_TRY(cudaMemcpyAsync(d_labels_out, h->qs_labels.p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return PCM_OK;
+}
+
+static int read_qs_count(pcm_handle* h, int* n_labels_out) {
+    CUDA_TRY(h->h_small.reserve(64));
+    int* hs = h->h_small.as<int>() + 8;
+    CUDA_TRY(cudaMemcpyAsync(hs, h->qs_count.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->qs_n_labels = *hs;
+    if (n_labels_out) *n_labels_out = *hs;
+    return PCM_OK;
+}
+
+extern "C" int pcm_quickshift_device(pcm_handle* h, const uint8_t* d_frame, int H, int W, int64_t stride, const int rect[4],
+                                     double ratio, double kernel_size, double max_dist, const double* d_noise,
+                                     int32_t* d_labels_out, int* n_labels_out) {
+    if (!h || !d_frame || !rect) return fail(PCM_E_INVALID, "pcm_quickshift_device: NULL argument");
+    if (rect[2] <= 0 || rect[3] <= 0 || rect[0] < 0 || rect[1] < 0 || rect[0] + rect[2] > W || rect[1] + rect[3] > H)
+        return fail(PCM_E_INVALID, "pcm_quickshift_device: rect outside the frame");
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->qs_valid = false;
+    int rc = enqueue_quickshift(h, d_frame, stride, rect[0], rect[1], rect[2], rect[3], ratio, kernel_size, max_dist, d_noise,
+                                d_labels_out);
+    if (rc) return rc;
+    return read_qs_count(h, n_labels_out);
+}
+
+extern "C" int pcm_quickshift(pcm_handle* h, const uint8_t* frame, int H, int W, int64_t stride, const int rect[4],
+                              double ratio, double kernel_size, double max_dist, const double* noise,
+                              int32_t* labels_out, int* n_labels_out) {
+    if (!h || !frame || !rect) return fail(PCM_E_INVALID, "pcm_quickshift: NULL argument");
+    if (rect[2] <= 0 || rect[3] <= 0 || rect[0] < 0 || rect[1] < 0 || rect[0] + rect[2] > W || rect[1] + rect[3] > H)
+        return fail(PCM_E_INVALID, "pcm_quickshift: rect outside the frame");
+    if (stride < (int64_t)W * 3) return fail(PCM_E_INVALID, "pcm_quickshift: stride %lld < 3*W", (long long)stride);
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int cx = rect[0], cy = rect[1], cw = rect[2], ch = rect[3];
+    const size_t npx = (size_t)cw * ch, row_bytes = (size_t)cw * 3;
+    cudaStream_t st = h->stream;
+    h->qs_valid = false;
+    CUDA_TRY(h->h_frame.reserve(npx * 3));
+    CUDA_TRY(h->frame.reserve(npx * 3));
+    if (noise) {
+        CUDA_TRY(h->h_noise.reserve(npx * sizeof(double)));
+        CUDA_TRY(h->qs_noise.reserve(npx * sizeof(double)));
+    } else if (h->qs_noise_cw != cw || h->qs_noise_ch != ch) {
+        return fail(PCM_E_STATE, "pcm_quickshift: noise == NULL needs a previous call with noise for the same %dx%d crop", cw, ch);
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    // crop rows (and, when given, the tie-breaking noise) -> pinned -> device, one pool dispatch
+    constexpr size_t CHUNK = 1u << 20;
+    const int rows_per_chunk = std::max(1, (int)(CHUNK / std::max<size_t>(row_bytes, 1)));
+    const int n_frame_items = (ch + rows_per_chunk - 1) / rows_per_chunk;
+    const size_t noise_bytes = noise ? npx * sizeof(double) : 0;
+    const int n_noise_items = (int)((noise_bytes + CHUNK - 1) / CHUNK);
+    uint8_t* hf = h->h_frame.as<uint8_t>();
+    uint8_t* df = h->frame.as<uint8_t>();
+    uint8_t* hn = h->h_noise.as<uint8_t>();
+    uint8_t* dn = h->qs_noise.as<uint8_t>();
+    const uint8_t* nsrc = reinterpret_cast<const uint8_t*>(noise);
+    std::atomic<int> cuda_err{0};
+    const int device = h->device;
+    HostPool::instance().parallel_for(n_frame_items + n_noise_items, [&](int item) {
+        cudaSetDevice(device);
+        cudaError_t e;
+        if (item < n_frame_items) {
+            const int r0 = item * rows_per_chunk, r1 = std::min(ch, r0 + rows_per_chunk);
+            for (int r = r0; r < r1; ++r)
+                memcpy(hf + (size_t)r * row_bytes, frame + (size_t)(cy + r) * stride + (size_t)cx * 3, row_bytes);
+            e = cudaMemcpyAsync(df + (size_t)r0 * row_bytes, hf + (size_t)r0 * row_bytes, (size_t)(r1 - r0) * row_bytes,
+                                cudaMemcpyHostToDevice, st);
+        } else {
+            const size_t o = (size_t)(item - n_frame_items) * CHUNK, len = std::min(CHUNK, noise_bytes - o);
+            memcpy(hn + o, nsrc + o, len);
+            e = cudaMemcpyAsync(dn + o, hn + o, len, cudaMemcpyHostToDevice, st);
+        }
+        if (e != cudaSuccess) cuda_err.store((int)e);
+    });
+    if (cuda_err.load()) return fail(PCM_E_CUDA, "pcm_quickshift: staging copy failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
+    if (noise) { h->qs_noise_cw = cw; h->qs_noise_ch = ch; }
+    int rc = enqueue_quickshift(h, df, (int64_t)row_bytes, 0, 0, cw, ch, ratio, kernel_size, max_dist, h->qs_noise.as<double>(), nullptr);
+    if (rc) return rc;
+    if (labels_out) {
+        CUDA_TRY(h->h_labels.reserve(npx * sizeof(int32_t)));
+        h->label_cache_px = 0;                        // the pinned label buffer no longer mirrors `labels`
+        CUDA_TRY(cudaMemcpyAsync(h->h_labels.p, h->qs_labels.p, npx * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    rc = read_qs_count(h, n_labels_out);
+    if (rc) return rc;
+    if (labels_out) memcpy(labels_out, h->h_labels.p, npx * sizeof(int32_t));
+    h->qs_cw = cw; h->qs_ch = ch;
+    h->qs_frame_ptr = frame;
+    memcpy(h->qs_rect, rect, sizeof h->qs_rect);
+    h->qs_valid = true;
     return PCM_OK;
 }
 

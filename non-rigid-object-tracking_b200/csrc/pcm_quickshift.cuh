@@ -1,0 +1,218 @@
+// pcm_quickshift.cuh -- quickshift over-segmentation of the crop on the GPU ("next" row f-1 of
+// the step that feeds labels to the hot path,
+// reference maskers/pixel_classification.py:70-71
+//     quickshift(crop_frame, kernel_size=3, max_dist=6, ratio=0.5, random_seed=42)).
+//
+// Algorithm = scikit-image 0.17.2 (environment.yaml:12; source not in the reference tree, so
+// parity is pinned only against the restatement in oracle/quickshift_oracle.py):
+//   Q1 qs_lab_kernel      u8 crop -> float64 Lab * ratio, planar   (skimage rgb2xyz + xyz2lab)
+//   Q2 qs_density_kernel  density = sum over the (2w+1)^2 window of exp(-d2 / (2 ks^2)) + tie noise
+//   Q3 qs_parent_kernel   parent = nearest window pixel of higher density; cut links > max_dist
+//   Q4 qs_root_kernel     follow parents to the root
+//   Q5 qs_flag / scan / qs_label   labels = rank of the root among all roots (np.unique inverse)
+// All sums run in the window's raster order with separate multiplies and adds (no FMA
+// contraction), exactly as the Cython loops do, so equal inputs give equal float64 densities
+// up to the last-ulp differences of exp() between math libraries.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pcm {
+
+struct QsArgs {
+    const uint8_t* frame;      // BGR interleaved
+    long long stride;
+    int cx, cy, cw, ch;
+    const double* lin;         // [256] sRGB -> linear
+    double ratio;
+    double* lab;               // [3][ch][cw]
+    double* dens;              // [ch][cw]
+    const double* noise;       // [ch][cw] or nullptr
+    int* parent;               // [ch*cw]
+    int* root;                 // [ch*cw]
+    int kw;                    // window half width = ceil(3 * kernel_size)
+    double inv;                // -0.5 / kernel_size^2
+    double max_dist;
+};
+
+__global__ void __launch_bounds__(256) qs_lab_kernel(const QsArgs a) {
+    const int n = a.cw * a.ch;
+    const size_t ps = (size_t)n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int r = i / a.cw, c = i - r * a.cw;
+        const uint8_t* px = a.frame + (long long)(a.cy + r) * a.stride + (long long)(a.cx + c) * 3;
+        // the reference hands an OpenCV BGR crop to a function that expects RGB: channel 0 plays 'R'
+        const double c0 = a.lin[px[0]], c1 = a.lin[px[1]], c2 = a.lin[px[2]];
+        const double M[3][3] = {{0.412453, 0.357580, 0.180423}, {0.212671, 0.715160, 0.072169}, {0.019334, 0.119193, 0.950227}};
+        const double white[3] = {0.95047, 1.0, 1.08883};
+        double f[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double x = __dadd_rn(__dadd_rn(__dmul_rn(c0, M[k][0]), __dmul_rn(c1, M[k][1])), __dmul_rn(c2, M[k][2]));
+            const double t = __ddiv_rn(x, white[k]);
+            f[k] = t > 0.008856 ? cbrt(t) : __dadd_rn(__dmul_rn(7.787, t), 16.0 / 116.0);
+        }
+        const double L = __dsub_rn(__dmul_rn(116.0, f[1]), 16.0);
+        const double A = __dmul_rn(500.0, __dsub_rn(f[0], f[1]));
+        const double B = __dmul_rn(200.0, __dsub_rn(f[1], f[2]));
+        a.lab[i] = __dmul_rn(L, a.ratio);
+        a.lab[ps + i] = __dmul_rn(A, a.ratio);
+        a.lab[2 * ps + i] = __dmul_rn(B, a.ratio);
+    }
+}
+
+// squared 5-D distance in the Cython loop's order: channels, then rows, then columns
+__device__ __forceinline__ double qs_dist(double l0, double a0, double b0, double l1, double a1, double b1, int dr, int dc) {
+    double t = __dsub_rn(l0, l1);
+    double d = __dmul_rn(t, t);
+    t = __dsub_rn(a0, a1);
+    d = __dadd_rn(d, __dmul_rn(t, t));
+    t = __dsub_rn(b0, b1);
+    d = __dadd_rn(d, __dmul_rn(t, t));
+    t = (double)dr;
+    d = __dadd_rn(d, __dmul_rn(t, t));
+    t = (double)dc;
+    d = __dadd_rn(d, __dmul_rn(t, t));
+    return d;
+}
+
+// 32 x 8 pixels per block; the Lab values of the block's window (tile + halo) are staged in
+// shared memory once and reused by the (2w+1)^2 taps of every pixel.
+constexpr int QS_BW = 32, QS_BH = 8, QS_MAX_KW = 15;
+
+template <bool PARENT>
+__global__ void __launch_bounds__(QS_BW * QS_BH) qs_window_kernel(const QsArgs a) {
+    extern __shared__ double qs_smem[];
+    const int kw = a.kw, TW = QS_BW + 2 * kw, TH = QS_BH + 2 * kw;
+    double* sL = qs_smem;
+    double* sA = sL + TW * TH;
+    double* sB = sA + TW * TH;
+    double* sD = sB + TW * TH;            // densities (PARENT only)
+    const int x0 = blockIdx.x * QS_BW, y0 = blockIdx.y * QS_BH;
+    const size_t ps = (size_t)a.cw * a.ch;
+    for (int i = threadIdx.x; i < TW * TH; i += QS_BW * QS_BH) {
+        const int tr = i / TW, tc = i - tr * TW;
+        const int y = y0 - kw + tr, x = x0 - kw + tc;
+        const bool in = y >= 0 && y < a.ch && x >= 0 && x < a.cw;
+        const size_t o = in ? (size_t)y * a.cw + x : 0;
+        sL[i] = in ? a.lab[o] : 0.0;
+        sA[i] = in ? a.lab[ps + o] : 0.0;
+        sB[i] = in ? a.lab[2 * ps + o] : 0.0;
+        if (PARENT) sD[i] = in ? a.dens[o] : 0.0;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x % QS_BW, ly = threadIdx.x / QS_BW;
+    const int c = x0 + lx, r = y0 + ly;
+    if (c >= a.cw || r >= a.ch) return;
+    const int r_min = max(r - kw, 0), r_max = min(r + kw + 1, a.ch);
+    const int c_min = max(c - kw, 0), c_max = min(c + kw + 1, a.cw);
+    const int me = (ly + kw) * TW + (lx + kw);
+    const double l0 = sL[me], a0 = sA[me], b0 = sB[me];
+    if (!PARENT) {
+        double acc = 0.0;
+        for (int r_ = r_min; r_ < r_max; ++r_) {
+            const int row = (r_ - y0 + kw) * TW + kw - x0;
+            for (int c_ = c_min; c_ < c_max; ++c_) {
+                const int j = row + c_;
+                const double d = qs_dist(l0, a0, b0, sL[j], sA[j], sB[j], r - r_, c - c_);
+                acc = __dadd_rn(acc, exp(__dmul_rn(d, a.inv)));
+            }
+        }
+        const size_t o = (size_t)r * a.cw + c;
+        a.dens[o] = a.noise ? __dadd_rn(acc, a.noise[o]) : acc;
+    } else {
+        const double cur = sD[me];
+        double closest = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+        int best = r * a.cw + c;
+        for (int r_ = r_min; r_ < r_max; ++r_) {
+            const int row = (r_ - y0 + kw) * TW + kw - x0;
+            for (int c_ = c_min; c_ < c_max; ++c_) {
+                const int j = row + c_;
+                if (sD[j] > cur) {
+                    const double d = qs_dist(l0, a0, b0, sL[j], sA[j], sB[j], r - r_, c - c_);
+                    if (d < closest) { closest = d; best = r_ * a.cw + c_; }
+                }
+            }
+        }
+        // parent_flat[dist_parent_flat > max_dist] = self, dist_parent = sqrt(closest)
+        if (sqrt(closest) > a.max_dist) best = r * a.cw + c;
+        a.parent[r * a.cw + c] = best;
+    }
+}
+
+__global__ void __launch_bounds__(256) qs_root_kernel(const int* __restrict__ parent, int* __restrict__ root,
+                                                      int* __restrict__ flag, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int p = i, q = __ldg(parent + i);
+        while (q != p) { p = q; q = __ldg(parent + p); }      // density strictly increases along links: no cycles
+        root[i] = p;
+        if (p == i) flag[i] = 1;
+    }
+}
+
+// ---- exclusive scan of the root flags (np.unique ranks), 1024 elements per block ------------
+constexpr int QS_SCAN_ELEMS = 1024;
+
+__device__ __forceinline__ int qs_block_exclusive(int v, int& total) {   // 256 threads
+    __shared__ int warp_sums[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { if (w < warp) base += warp_sums[w]; tot += warp_sums[w]; }
+    __syncthreads();
+    total = tot;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(256) qs_scan_reduce_kernel(const int* __restrict__ flag, int n, int* __restrict__ block_sums) {
+    const int base = blockIdx.x * QS_SCAN_ELEMS + threadIdx.x * 4;
+    int s = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += (base + j < n) ? flag[base + j] : 0;
+    int total;
+    qs_block_exclusive(s, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) qs_scan_sums_kernel(int* __restrict__ block_sums, int n_blocks, int* __restrict__ n_labels) {
+    int carry = 0;                       // single block; chunks of 256 block sums
+    for (int b0 = 0; b0 < n_blocks; b0 += 256) {
+        const int i = b0 + threadIdx.x;
+        const int v = i < n_blocks ? block_sums[i] : 0;
+        int total;
+        const int ex = qs_block_exclusive(v, total);
+        if (i < n_blocks) block_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *n_labels = carry;
+}
+
+__global__ void __launch_bounds__(256) qs_scan_apply_kernel(const int* __restrict__ flag, int n, const int* __restrict__ block_offsets,
+                                                            int* __restrict__ rank) {
+    const int base = blockIdx.x * QS_SCAN_ELEMS + threadIdx.x * 4;
+    int f[4], s = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[j] = (base + j < n) ? flag[base + j] : 0; s += f[j]; }
+    int total;
+    int ex = qs_block_exclusive(s, total) + block_offsets[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (base + j < n) rank[base + j] = ex;
+        ex += f[j];
+    }
+}
+
+__global__ void __launch_bounds__(256) qs_label_kernel(const int* __restrict__ root, const int* __restrict__ rank,
+                                                       int32_t* __restrict__ labels, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) labels[i] = rank[root[i]];
+}
+
+}  // namespace pcm

@@ -54,8 +54,12 @@ class PixelClassificationNonRigidMasker(Masker):
         self.spaces = tokens[1].split("_")
         self.native = capi.Handle(device)
         self.native.set_features(self.n_neighbors, self.spaces)
-        # providers for the two stages that are not part of the hot path
-        self.segment_fn = segment_fn or make_segment_provider(params["over_segmentation"])
+        # over-segmentation (:70-75): quickshift runs on the GPU (pcm_quickshift);
+        # felzenszwalb / SLIC have no native implementation yet and use a stand-in provider
+        self.native_quickshift = segment_fn is None and params["over_segmentation"] == "quickshift"
+        self.segment_fn = segment_fn or (None if self.native_quickshift
+                                         else make_segment_provider(params["over_segmentation"]))
+        self._qs_noise_shape = None
         self.prior_fn = prior_fn or SiftPrior()
         self.prevForegroundMask = None
 
@@ -129,11 +133,27 @@ class PixelClassificationNonRigidMasker(Masker):
         params = self.config["params"]
         cur = self.current_model
 
-        segments = np.ascontiguousarray(self.segment_fn(crop), np.int32)
+        want_prior = self.index != 0 and params["prior_weight"] != 0.0
         n_labels, priors = 0, None             # 0: the library takes max(label) + 1 while staging
-        if self.index != 0 and params["prior_weight"] != 0.0:
-            n_labels = int(segments.max()) + 1
-            priors = self.prior_fn(self.prevFrame, self.prevForegroundMask, crop, segments, n_labels)
+        if self.native_quickshift:
+            # quickshift(crop, kernel_size=3, max_dist=6, ratio=0.5, random_seed=42) (:71); the label
+            # map stays on the device and only travels to the host when the SIFT prior needs it
+            if frame.strides[2] != 1 or frame.strides[1] != 3:
+                frame = np.ascontiguousarray(frame)
+            noise = None
+            if self._qs_noise_shape != (h, w):
+                noise = np.random.RandomState(42).normal(scale=0.00001, size=(h, w))
+                self._qs_noise_shape = (h, w)
+            segments, n_labels = self.native.quickshift(frame, (x, y, w, h), ratio=0.5, kernel_size=3, max_dist=6,
+                                                        noise=noise, want_labels=want_prior)
+            if want_prior:
+                priors = self.prior_fn(self.prevFrame, self.prevForegroundMask, crop, segments, n_labels)
+            segments = None                    # update() continues from the device-resident map
+        else:
+            segments = np.ascontiguousarray(self.segment_fn(crop), np.int32)
+            if want_prior:
+                n_labels = int(segments.max()) + 1
+                priors = self.prior_fn(self.prevFrame, self.prevForegroundMask, crop, segments, n_labels)
 
         blend = bool(self.multi_selection) and len(self.models) > cur + 1
         w_cur, w_next = 1.0, 0.0

@@ -61,6 +61,8 @@ def load_library():
         "pcm_update_device": (I, [P, P, I, I, L, P, P, I, P, C.POINTER(UpdateParams), P, L]),
         "pcm_iou": (I, [P, P, L, L, P, L, I, I, I, P]),
         "pcm_iou_device": (I, [P, P, L, P, L, I, I, I, P]),
+        "pcm_quickshift": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
+        "pcm_quickshift_device": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
         "pcm_convert": (I, [P, P, I, I, L, I, P, L]),
         "pcm_gather_features": (I, [P, P, I, I, L, P, P]),
         "pcm_set_debug": (I, [P, I]),
@@ -83,7 +85,8 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_use_own_stream", "pcm_synchronize",
     "pcm_set_features", "pcm_num_features", "pcm_add_model", "pcm_set_novelty", "pcm_num_models", "pcm_crop_rect",
-    "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_convert", "pcm_gather_features",
+    "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device",
+    "pcm_convert", "pcm_gather_features",
     "pcm_set_debug", "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_profile_enable", "pcm_profile_read",
 ]
 
@@ -204,9 +207,10 @@ class Handle:
             frame = np.ascontiguousarray(frame, np.uint8)
         if mask.dtype != np.uint8 or mask.strides[-1] != 1 and mask.ndim == 3:
             raise ValueError("mask must be a uint8 array with unit channel stride")
-        labels = np.ascontiguousarray(labels, np.int32)
-        if labels.size != rect[2] * rect[3]:
-            raise ValueError("labels has %d elements, crop has %d" % (labels.size, rect[2] * rect[3]))
+        if labels is not None:
+            labels = np.ascontiguousarray(labels, np.int32)
+            if labels.size != rect[2] * rect[3]:
+                raise ValueError("labels has %d elements, crop has %d" % (labels.size, rect[2] * rect[3]))
         n_labels = int(n_labels or 0)          # 0 / None: the library takes max(label) + 1
         pr = None if priors is None else np.ascontiguousarray(priors, np.float32)
         if pr is not None and pr.size != n_labels:
@@ -219,6 +223,25 @@ class Handle:
             mptr, row, pix = C.c_void_p(mask.ctypes.data), mask.strides[0], mask.strides[1]
         self._check(self.lib.pcm_update(self._h, _ptr(frame), frame.shape[0], frame.shape[1], frame.strides[0], r,
                                         _ptr(labels), int(n_labels), _ptr(pr), C.byref(params), mptr, row, pix))
+
+    def quickshift(self, frame, rect, ratio=0.5, kernel_size=3, max_dist=6, noise=None, want_labels=True):
+        """quickshift over-segmentation of the crop `rect` (defaults = the reference's call,
+        pixel_classification.py:71).  Returns (labels int32 HxW or None, n_labels); the map also
+        stays on the device for `update(..., labels=None)`.  `noise`: h*w float64 tie-breaking
+        noise, or None to reuse the previous call's (same crop size)."""
+        if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3 or frame.strides[2] != 1 \
+                or frame.strides[1] != 3:
+            raise ValueError("frame must be an HxWx3 uint8 array with packed pixels")
+        r = (C.c_int * 4)(*[int(v) for v in rect])
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float64)
+        if nz is not None and nz.size != rect[2] * rect[3]:
+            raise ValueError("noise must have one value per crop pixel")
+        out = np.empty((rect[3], rect[2]), np.int32) if want_labels else None
+        n = C.c_int(0)
+        self._check(self.lib.pcm_quickshift(self._h, _ptr(frame), frame.shape[0], frame.shape[1], frame.strides[0], r,
+                                            float(ratio), float(kernel_size), float(max_dist), _ptr(nz), _ptr(out),
+                                            C.byref(n)))
+        return out, n.value
 
     def update_device(self, d_frame, frame_h, frame_w, stride, rect, d_labels, n_labels, d_priors, params, d_mask,
                       mask_stride):

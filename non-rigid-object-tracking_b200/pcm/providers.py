@@ -55,6 +55,7 @@ def make_segment_provider(name, **kw):
         sites = int(name.split(":")[1]) if ":" in name else kw.get("n_sites", 200)
         return lambda crop: voronoi_segments(crop, sites, kw.get("seed", 0))
     if name in ("quickshift", "felzenszwalb", "SLIC"):
+        # 'quickshift' normally never gets here: the masker runs it on the GPU (pcm_quickshift)
         block = {"quickshift": 6, "felzenszwalb": 10, "SLIC": 12}[name]
         return lambda crop: grid_segments(crop, block)
     raise ValueError("unknown over_segmentation %r" % name)

@@ -1,0 +1,71 @@
+"""The C-ABI library on a machine WITHOUT a GPU: it loads, exports every function that
+include/pcm_b200.h declares (and nothing is declared that the ctypes binding does not know),
+and fails loudly -- there is no CPU fallback behind the boundary."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from helpers import ROOT
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "pcm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_binding_and_library_agree():
+    from pcm import capi
+    names = _declared()
+    assert len(names) >= 25
+    lib = capi.load_library()
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, "declared in pcm_b200.h but not exported: %s" % missing
+    assert sorted(capi.EXPORTED_SYMBOLS) == names, "pcm/capi.py and include/pcm_b200.h list different entry points"
+    assert lib.pcm_abi_version() == 1
+
+
+def test_crop_rect_needs_no_device():
+    """pcm_crop_rect is host integer logic (reference :49-51): bbox quirks incl. negative x."""
+    from pcm import capi
+    import pcm_oracle as orc
+    H, W = 224, 528
+    for bbox in [(419, 16, 30, 200), (5, 3, 40, 40), (-7, 10, 50, 30), (500, 200, 60, 60), (0, 0, 528, 224),
+                 (-40, -40, 10, 10), (600, 300, 5, 5)]:
+        eb = orc.enlarge_bbox(bbox, (H, W, 3))
+        y0, y1 = orc.slice_extent(eb[1], eb[3], H)
+        x0, x1 = orc.slice_extent(eb[0], eb[2], W)
+        assert capi.crop_rect(bbox, H, W) == (x0, y0, max(x1 - x0, 0), max(y1 - y0, 0)), bbox
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from pcm import capi
+    with pytest.raises(capi.PcmError) as e:
+        capi.Handle(0)
+    assert "no CUDA device" in str(e.value) and "no CPU path" in str(e.value)
+    from maskers import getMaskerByName
+    with pytest.raises(capi.PcmError):
+        getMaskerByName("PC", debug=False, frame=None, config=dict(multi_selection=False, params=dict(
+            features="8 hsv_lab", over_segmentation="quickshift")), poly_roi=None, update_mask=False)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "non-rigid-object-tracking_b200")
+    bad = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                t = open(os.path.join(d, f), errors="ignore").read()
+                if re.search(r"^\s*(import|from)\s+(oracle|pcm_oracle|ref_port|quickshift_oracle)\b", t, flags=re.M) or \
+                        re.search(r"sys\.path.*oracle", t):
+                    bad.append(os.path.join(d, f))
+            elif f.endswith((".cu", ".cuh", ".h", ".cpp")):
+                t = open(os.path.join(d, f), errors="ignore").read()
+                if re.search(r"#\s*include\s*[\"<][^\">]*oracle", t):
+                    bad.append(os.path.join(d, f))
+    assert not bad, "product files referring to oracle/: %s" % bad
