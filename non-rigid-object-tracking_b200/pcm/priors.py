@@ -5,30 +5,61 @@ SURVEY.md §8): only used when `prior_weight != 0` and `index > 0`.
 A label gets prior +1 when a SIFT keypoint of the current crop that matches a
 keypoint inside the previous foreground mask (Lowe ratio 0.7, 90th-percentile
 displacement filter) falls on it; every other label keeps -1.
+
+The reference runs SIFT twice per frame: on the previous crop with the previous mask, and on
+the current crop.  The previous crop IS the crop of the previous call, and OpenCV applies the
+mask only as a keypoint filter after detection (KeyPointsFilter::runByPixelsMask) and before
+the per-keypoint descriptors, so the masked result is the subset of the unmasked one computed a
+frame earlier: that one is kept and filtered here instead of being recomputed (`reuse=True`).
 """
 import cv2 as cv
 import numpy as np
 
 
 class SiftPrior:
-    def __init__(self):
+    def __init__(self, reuse=True):
         self.sift = cv.SIFT_create()
         self.flann = cv.FlannBasedMatcher(dict(algorithm=1, trees=5), dict(checks=50))
+        self.reuse = reuse
+        self._last = None          # (crop array object, keypoint xy float32 [n,2], descriptors)
+
+    @staticmethod
+    def _pts(kps):
+        return np.array([k.pt for k in kps], np.float32).reshape(-1, 2)
+
+    def features(self, prev_crop, prev_mask, crop):
+        """(pts1, des1) of the previous crop inside prev_mask, (pts2, des2) of the current crop."""
+        if self.reuse and self._last is not None and self._last[0] is prev_crop:
+            pts, des = self._last[1], self._last[2]
+            if len(pts):
+                # KeyPointsFilter::runByPixelsMask: keep mask[(int)(y + 0.5f), (int)(x + 0.5f)] != 0
+                yy = (pts[:, 1] + np.float32(0.5)).astype(np.int32)
+                xx = (pts[:, 0] + np.float32(0.5)).astype(np.int32)
+                keep = prev_mask[yy, xx] != 0
+                pts1, des1 = pts[keep], (des[keep] if des is not None else None)
+            else:
+                pts1, des1 = pts, des
+        else:
+            kp1, des1 = self.sift.detectAndCompute(np.ascontiguousarray(prev_crop), np.ascontiguousarray(prev_mask))
+            pts1 = self._pts(kp1)
+        kp2, des2 = self.sift.detectAndCompute(np.ascontiguousarray(crop), None)
+        pts2 = self._pts(kp2)
+        self._last = (crop, pts2, des2)
+        return pts1, des1, pts2, des2
 
     def __call__(self, prev_crop, prev_mask, crop, segments, n_labels):
         priors = np.full(n_labels, -1, np.float32)
         if prev_crop is None or prev_mask is None:
             return priors
-        kp1, des1 = self.sift.detectAndCompute(np.ascontiguousarray(prev_crop), np.ascontiguousarray(prev_mask))
-        kp2, des2 = self.sift.detectAndCompute(np.ascontiguousarray(crop), None)
-        if len(kp1) == 0 or len(kp2) < 2:
+        pts1, des1, pts2, des2 = self.features(prev_crop, prev_mask, crop)
+        if len(pts1) == 0 or len(pts2) < 2:
             return priors
         good = [m for m, n in (pair for pair in self.flann.knnMatch(des1, des2, k=2) if len(pair) == 2)
                 if m.distance < 0.7 * n.distance]
         if not good:
             return priors
-        p1 = np.array([kp1[m.queryIdx].pt for m in good])
-        p2 = np.array([kp2[m.trainIdx].pt for m in good])
+        p1 = np.array([pts1[m.queryIdx] for m in good], np.float64)
+        p2 = np.array([pts2[m.trainIdx] for m in good], np.float64)
         dist = np.sqrt(((p2 - p1) ** 2).sum(axis=1))
         keep = dist <= np.percentile(dist, 90)
         for px, py in p2[keep]:

@@ -44,6 +44,7 @@ def resolve_path(p):
 
 
 _clip_cache = {}
+_truth_box_cache = {}
 
 
 def read_clip(path, resize_factor=1, cache=True):
@@ -125,7 +126,10 @@ def make_tracker(config, frame0, first_boxes, truth_frames, provider=None):
     if provider == "truth":
         if truth_frames is None:
             raise ValueError("tracker_provider 'truth' needs input_truth")
-        boxes = providers.truth_boxes(truth_frames, first_boxes[0])
+        key = (id(truth_frames), len(truth_frames), tuple(int(v) for v in first_boxes[0]))
+        if key not in _truth_box_cache:            # the clip cache hands out the same list per video
+            _truth_box_cache[key] = providers.truth_boxes(truth_frames, first_boxes[0])
+        boxes = _truth_box_cache[key]
 
         def factory(frame, start_boxes, start_index=0):
             t = providers.ScriptedBoxTracker([boxes])
@@ -144,6 +148,7 @@ def run_sequence(config, device=0, out_path=None, segment_fn=None, prior_fn=None
     """Run one sequence (one video, one hyper-parameter set).  Returns a dict with `mean_iou`,
     `seconds` (the reference's tot_time: the frame loop only, main.py:275,364), `iou` (per box
     per frame), `n_frames`, `n_updates`, `train_seconds`, `tracker`."""
+    t_wall = time.time()
     rf = config.get("resize_factor") or 1
     frames = read_clip(resolve_path(config["input_video"]), rf)
     if not frames:
@@ -158,6 +163,7 @@ def run_sequence(config, device=0, out_path=None, segment_fn=None, prior_fn=None
     if config.get("manual_roi_selection"):
         raise ValueError("manual_roi_selection needs a GUI (main.py:167-245); use the `pts` polygons")
 
+    t_decode = time.time() - t_wall
     t_train = time.time()
     maskers, bboxes, colors = [], [], []
     for n_target, target_selection in enumerate(pts):
@@ -220,4 +226,4 @@ def run_sequence(config, device=0, out_path=None, segment_fn=None, prior_fn=None
         if hasattr(m, "close"):
             m.close()
     return dict(mean_iou=mean_iou, seconds=seconds, iou=ious, n_frames=n, n_updates=n_updates,
-                train_seconds=t_train, tracker=tracker_name)
+                train_seconds=t_train, tracker=tracker_name, decode_seconds=t_decode, wall_seconds=time.time() - t_wall)

@@ -176,8 +176,9 @@ def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, ou
         train_jobs = max(1, (os.cpu_count() or 1) // max(world, 1))
     t0 = time.time()
     local = run_shard(shards[rank], base, polygons, device=local_rank, max_frames=max_frames, train_jobs=train_jobs,
-                      progress=(lambda k, n, sid, r: log("[rank %d] %d/%d seq %d iou %.3f %.2fs (train %.2fs)" %
-                                                         (rank, k, n, sid, r["mean_iou"], r["seconds"], r["train_seconds"])))
+                      progress=(lambda k, n, sid, r: log("[rank %d] %d/%d seq %d iou %.3f %.2fs (train %.2fs, decode %.2fs, wall %.2fs)" %
+                                                         (rank, k, n, sid, r["mean_iou"], r["seconds"], r["train_seconds"],
+                                                          r["decode_seconds"], r["wall_seconds"])))
                       if log else None)
     t_local = time.time() - t0
     all_rows = gather(local, world, dist, dev)
