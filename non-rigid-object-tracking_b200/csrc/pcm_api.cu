@@ -85,19 +85,65 @@ struct HostTrace {
 // ---------------------------------------------------------------------------------
 // grow-only buffers
 // ---------------------------------------------------------------------------------
+// Blocks released by a handle are parked in a process-wide cache and handed to the next handle
+// that asks for that much memory: a sweep creates and destroys one handle per sequence, and
+// cudaFree / cudaFreeHost / cudaMallocHost cost far more than a whole short sequence.
+#include <mutex>
+class BlockCache {
+public:
+    static BlockCache& instance() { static BlockCache c; return c; }
+    // smallest parked block of `device` (or pinned: device = -1) with capacity in [bytes, 4 * bytes]
+    bool take(int device, size_t bytes, void** p, size_t* cap) {
+        std::lock_guard<std::mutex> lk(m_);
+        int best = -1;
+        for (int i = 0; i < (int)blocks_.size(); ++i) {
+            const Block& b = blocks_[i];
+            if (b.device == device && b.cap >= bytes && b.cap <= 4 * bytes + (1u << 16) &&
+                (best < 0 || b.cap < blocks_[best].cap))
+                best = i;
+        }
+        if (best < 0) return false;
+        *p = blocks_[best].p;
+        *cap = blocks_[best].cap;
+        total_[device < 0] -= blocks_[best].cap;
+        blocks_.erase(blocks_.begin() + best);
+        return true;
+    }
+    // returns false when the cache is full and the caller has to free the block itself
+    bool park(int device, void* p, size_t cap) {
+        std::lock_guard<std::mutex> lk(m_);
+        const size_t limit = device < 0 ? ((size_t)1 << 30) : ((size_t)4 << 30);
+        if (total_[device < 0] + cap > limit || blocks_.size() >= 512) return false;
+        blocks_.push_back({device, p, cap});
+        total_[device < 0] += cap;
+        return true;
+    }
+private:
+    struct Block { int device; void* p; size_t cap; };
+    std::mutex m_;
+    std::vector<Block> blocks_;
+    size_t total_[2] = {0, 0};
+};
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    int device = 0;
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
+        release();
+        cudaGetDevice(&device);
+        if (BlockCache::instance().take(device, bytes, &p, &cap)) return cudaSuccess;
         size_t want = bytes + bytes / 4 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
+        else p = nullptr;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() {
+        if (p && !BlockCache::instance().park(device, p, cap)) cudaFree(p);
+        p = nullptr; cap = 0;
+    }
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
 
@@ -106,14 +152,18 @@ struct PinBuf {
     size_t cap = 0;
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
+        release();
+        if (BlockCache::instance().take(-1, bytes, &p, &cap)) return cudaSuccess;
         size_t want = bytes + bytes / 4 + 256;
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
+        else p = nullptr;
         return e;
     }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    void release() {
+        if (p && !BlockCache::instance().park(-1, p, cap)) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+    }
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
 

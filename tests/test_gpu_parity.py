@@ -429,3 +429,47 @@ def test_4k_multi_object_frame():
     hq = capi.Handle(0)
     assert hq.iou_counts(mask[..., 2], truth) == orc.iou_counts(mask[..., 2], truth)
     hq.close()
+
+
+def test_device_pointer_path_equals_host_path():
+    """pcm_update_device / pcm_iou_device (device-resident frame, labels, mask, truth; what
+    bench.py's `value` leg times) on a crop in the middle of a frame == the host-buffer path."""
+    import torch
+    from pcm import capi
+    from pcm.providers import voronoi_segments
+    rng = np.random.default_rng(77)
+    H, W = 300, 421
+    frame = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    rect = (37, 41, 263, 187)                       # odd offsets and sizes
+    x, y, w, hh = rect
+    seg = voronoi_segments(frame[y:y + hh, x:x + w], 90, seed=5)
+    S = int(seg.max()) + 1
+    F = 3 * 33 * 2
+    trees = _random_forest_arrays(rng, 9, 6, F)
+    truth = (rng.random((H, W)) < 0.4).astype(np.uint8) * 200
+    prm = capi.Handle.make_params(0, dilation_kernel=5)
+
+    h = capi.Handle(0)
+    h.set_features(4, ["lab", "hsv"])
+    h.add_model_arrays(0, trees)
+    want = np.zeros((H, W, 3), np.uint8)
+    h.update(frame, rect, seg, S, None, prm, want)
+    want_counts = h.iou_counts(want[..., 2], truth)
+
+    dev = torch.device("cuda", 0)
+    d_frame = torch.from_numpy(frame).to(dev)
+    d_seg = torch.from_numpy(seg).to(dev)
+    d_mask = torch.zeros((H, W + 11), dtype=torch.uint8, device=dev)       # padded rows
+    d_truth = torch.from_numpy(truth).to(dev)
+    d_counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    h.update_device(d_frame.data_ptr(), H, W, W * 3, rect, d_seg.data_ptr(), S, 0, prm, d_mask.data_ptr(), W + 11)
+    h.iou_device(d_mask.data_ptr(), W + 11, d_truth.data_ptr(), W, 1, H, W, d_counts.data_ptr())
+    h.synchronize()
+    got = d_mask.cpu().numpy()
+    assert not got[:, W:].any()
+    assert np.array_equal(got[:, :W], want[..., 2])
+    assert tuple(int(v) for v in d_counts.cpu()) == want_counts == orc.iou_counts(want[..., 2], truth)
+    h.use_own_stream()
+    h.close()
