@@ -132,6 +132,11 @@ int pcm_update(pcm_handle* h, const uint8_t* frame, int frame_h, int frame_w, in
  * AND the crop pixels are the ones that call left on the device (`frame` and `rect` must be
  * the same as in that call; the frame is not read again).  n_labels is ignored. */
 
+/* pcm_update keeps the previous call's label map (pinned host copy + device copy) and re-sends
+ * only the 1 MiB chunks whose bytes changed.  on = 0 switches that off: every call uploads the
+ * whole map (default: on). */
+int pcm_set_label_cache(pcm_handle* h, int on);
+
 /* Same work on DEVICE buffers, asynchronous on the handle's stream.
  * d_mask is a dense plane (pixel stride 1) of frame_h x frame_w, rows
  * mask_row_stride bytes apart; only the crop rectangle is written. */
@@ -211,6 +216,10 @@ int pcm_debug_tables(pcm_handle* h, uint16_t* gamma, uint16_t* cbrt_tab, int32_t
 
 /* Number of kernel launches issued through this handle so far. */
 int64_t pcm_launch_count(const pcm_handle* h);
+
+/* Bytes the HOST-buffer entry points (pcm_update, pcm_iou, pcm_quickshift) have copied so far:
+ * out[0] host->device, out[1] device->host.  Label chunks that were not re-sent do not count. */
+int pcm_transfer_bytes(const pcm_handle* h, int64_t out[2]);
 
 /* Per-kernel device timing (CUDA events on the handle's stream around every
  * launch while enabled).  Kernel ids: 0 score (fused star features + forests),

@@ -196,6 +196,7 @@ struct pcm_handle {
     Geom geom{};
     std::vector<Model> models;
     int64_t launches = 0;
+    std::atomic<int64_t> bytes_h2d{0}, bytes_d2h{0};   // bytes moved by the host-buffer entry points
 
     // optional per-kernel event timing
     bool profiling = false;
@@ -214,6 +215,7 @@ struct pcm_handle {
     // (label_cache_px elements, 1 MiB chunks); a chunk whose bytes are unchanged is not re-sent
     size_t label_cache_px = 0;
     std::vector<int> label_chunk_max;
+    bool label_cache_on = true;   // pcm_set_label_cache
 
     // quickshift over-segmentation (pcm_quickshift): scratch, the resident label map and the crop
     // it was computed from (pcm_update with labels == NULL continues from here)
@@ -866,6 +868,7 @@ static int finish_host_update(pcm_handle* h, const int rect[4], uint8_t* mask, i
     const size_t npx = (size_t)cw * ch;
     cudaStream_t st = h->stream;
     CUDA_TRY(cudaMemcpyAsync(h->h_mask.p, h->mask.p, npx, cudaMemcpyDeviceToHost, st));
+    h->bytes_d2h += (int64_t)npx + (int64_t)sizeof(int);
     int rc = check_label_error(h, true);
     if (rc) return rc;
     h->trace.lap(HostTrace::UPD_WAIT);
@@ -907,6 +910,7 @@ static int update_from_quickshift(pcm_handle* h, const uint8_t* frame, int H, in
         CUDA_TRY(cudaStreamSynchronize(st));
         memcpy(h->h_priors.p, priors, sizeof(float) * (size_t)h->qs_n_labels);
         CUDA_TRY(cudaMemcpyAsync(h->priors.p, h->h_priors.p, sizeof(float) * (size_t)h->qs_n_labels, cudaMemcpyHostToDevice, st));
+        h->bytes_h2d += (int64_t)(sizeof(float) * (size_t)h->qs_n_labels);
         d_priors = h->priors.as<float>();
     }
     h->trace.lap(HostTrace::UPD_STAGE);
@@ -968,7 +972,7 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
     const int n_frame_items = (ch + rows_per_chunk - 1) / rows_per_chunk;
     const size_t label_bytes = npx * sizeof(int32_t);
     const int n_label_items = (int)((label_bytes + CHUNK - 1) / CHUNK);
-    const bool cache_ok = h->label_cache_px == npx && old_hl == h->h_labels.p && old_dl == h->labels.p &&
+    const bool cache_ok = h->label_cache_on && h->label_cache_px == npx && old_hl == h->h_labels.p && old_dl == h->labels.p &&
                           (int)h->label_chunk_max.size() == n_label_items;
     if (!cache_ok) h->label_chunk_max.assign(n_label_items, -1);
     h->label_cache_px = 0;                 // invalid until every chunk is staged
@@ -990,6 +994,7 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
                 memcpy(hf + (size_t)r * row_bytes, frame + (size_t)(cy + r) * stride + (size_t)cx * 3, row_bytes);
             e = cudaMemcpyAsync(df + (size_t)r0 * row_bytes, hf + (size_t)r0 * row_bytes, (size_t)(r1 - r0) * row_bytes,
                                 cudaMemcpyHostToDevice, st);
+            h->bytes_h2d += (int64_t)((size_t)(r1 - r0) * row_bytes);
         } else {
             const int c = item - n_frame_items;
             const size_t o = (size_t)c * CHUNK, len = std::min(CHUNK, label_bytes - o);
@@ -1001,6 +1006,7 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
                 for (size_t i = 0; i < n; ++i) { const int32_t v = src[i]; dst[i] = v; mx = v > mx ? v : mx; }
                 chunk_max[c] = mx;
                 e = cudaMemcpyAsync(dl + o, hl + o, len, cudaMemcpyHostToDevice, st);
+                h->bytes_h2d += (int64_t)len;
             }
         }
         if (e != cudaSuccess) cuda_err.store((int)e);
@@ -1020,6 +1026,7 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
         CUDA_TRY(h->priors.reserve(sizeof(float) * (size_t)n_labels));
         memcpy(h->h_priors.p, priors, sizeof(float) * (size_t)n_labels);
         CUDA_TRY(cudaMemcpyAsync(h->priors.p, h->h_priors.p, sizeof(float) * (size_t)n_labels, cudaMemcpyHostToDevice, st));
+        h->bytes_h2d += (int64_t)(sizeof(float) * (size_t)n_labels);
         d_priors = h->priors.as<float>();
     }
     const int crop_rect[4] = {0, 0, cw, ch};
@@ -1075,8 +1082,8 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
     // one pool dispatch: an item is a band of rows of the truth or of the mask; the worker packs
     // it densely into pinned memory and queues its own H2D copy
     const size_t trow = (size_t)width * truth_channels;
-    const int rows_t = std::max(1, (int)((1u << 20) / std::max<size_t>(trow, 1)));
-    const int rows_m = std::max(1, (int)((1u << 20) / (size_t)width));
+    const int rows_t = std::max(1, (int)((1u << 18) / std::max<size_t>(trow, 1)));   // 256 KiB bands: enough items for
+    const int rows_m = std::max(1, (int)((1u << 18) / (size_t)width));               // every pool thread at 1080p
     const int n_t = (height + rows_t - 1) / rows_t, n_m = (height + rows_m - 1) / rows_m;
     std::atomic<int> cuda_err{0};
     const int device = h->device;
@@ -1088,6 +1095,7 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
             for (int r = r0; r < r1; ++r) memcpy(ht + (size_t)r * trow, truth + (size_t)r * truth_row_stride, trow);
             e = cudaMemcpyAsync(dt + (size_t)r0 * trow, ht + (size_t)r0 * trow, (size_t)(r1 - r0) * trow,
                                 cudaMemcpyHostToDevice, st);
+            h->bytes_h2d += (int64_t)((size_t)(r1 - r0) * trow);
         } else {
             const int r0 = (item - n_t) * rows_m, r1 = std::min(height, r0 + rows_m);
             for (int r = r0; r < r1; ++r) {
@@ -1097,6 +1105,7 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
             }
             e = cudaMemcpyAsync(dm + (size_t)r0 * width, hm + (size_t)r0 * width, (size_t)(r1 - r0) * width,
                                 cudaMemcpyHostToDevice, st);
+            h->bytes_h2d += (int64_t)((size_t)(r1 - r0) * width);
         }
         if (e != cudaSuccess) cuda_err.store((int)e);
     });
@@ -1108,6 +1117,7 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
     if (rc) return rc;
     int64_t* hc = h->h_small.as<int64_t>() + 2;
     CUDA_TRY(cudaMemcpyAsync(hc, h->counts.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    h->bytes_d2h += 2 * (int64_t)sizeof(int64_t);
     CUDA_TRY(cudaStreamSynchronize(st));
     h->trace.lap(HostTrace::IOU_WAIT);
     counts[0] = hc[0];
@@ -1251,10 +1261,12 @@ extern "C" int pcm_quickshift(pcm_handle* h, const uint8_t* frame, int H, int W,
                 memcpy(hf + (size_t)r * row_bytes, frame + (size_t)(cy + r) * stride + (size_t)cx * 3, row_bytes);
             e = cudaMemcpyAsync(df + (size_t)r0 * row_bytes, hf + (size_t)r0 * row_bytes, (size_t)(r1 - r0) * row_bytes,
                                 cudaMemcpyHostToDevice, st);
+            h->bytes_h2d += (int64_t)((size_t)(r1 - r0) * row_bytes);
         } else {
             const size_t o = (size_t)(item - n_frame_items) * CHUNK, len = std::min(CHUNK, noise_bytes - o);
             memcpy(hn + o, nsrc + o, len);
             e = cudaMemcpyAsync(dn + o, hn + o, len, cudaMemcpyHostToDevice, st);
+            h->bytes_h2d += (int64_t)len;
         }
         if (e != cudaSuccess) cuda_err.store((int)e);
     });
@@ -1266,6 +1278,7 @@ extern "C" int pcm_quickshift(pcm_handle* h, const uint8_t* frame, int H, int W,
         CUDA_TRY(h->h_labels.reserve(npx * sizeof(int32_t)));
         h->label_cache_px = 0;                        // the pinned label buffer no longer mirrors `labels`
         CUDA_TRY(cudaMemcpyAsync(h->h_labels.p, h->qs_labels.p, npx * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        h->bytes_d2h += (int64_t)(npx * sizeof(int32_t));
     }
     rc = read_qs_count(h, n_labels_out);
     if (rc) return rc;
@@ -1384,6 +1397,19 @@ extern "C" int pcm_debug_tables(pcm_handle* h, uint16_t* gamma, uint16_t* cbrt_t
 }
 
 extern "C" int64_t pcm_launch_count(const pcm_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int pcm_set_label_cache(pcm_handle* h, int on) {
+    if (!h) return fail(PCM_E_INVALID, "pcm_set_label_cache: NULL handle");
+    h->label_cache_on = on != 0;
+    return PCM_OK;
+}
+
+extern "C" int pcm_transfer_bytes(const pcm_handle* h, int64_t out[2]) {
+    if (!h || !out) return fail(PCM_E_INVALID, "pcm_transfer_bytes: NULL argument");
+    out[0] = h->bytes_h2d.load();
+    out[1] = h->bytes_d2h.load();
+    return PCM_OK;
+}
 
 extern "C" int pcm_profile_enable(pcm_handle* h, int on) {
     if (!h) return fail(PCM_E_INVALID, "pcm_profile_enable: NULL handle");

@@ -69,6 +69,8 @@ def load_library():
         "pcm_debug_last": (I, [P, P, P, P, P, P, P]),
         "pcm_debug_tables": (I, [P, P, P, P, P]),
         "pcm_launch_count": (L, [P]),
+        "pcm_transfer_bytes": (I, [P, P]),
+        "pcm_set_label_cache": (I, [P, I]),
         "pcm_profile_enable": (I, [P, I]),
         "pcm_profile_read": (I, [P, P, P, I, I]),
     }
@@ -87,7 +89,7 @@ EXPORTED_SYMBOLS = [
     "pcm_set_features", "pcm_num_features", "pcm_add_model", "pcm_set_novelty", "pcm_num_models", "pcm_crop_rect",
     "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device",
     "pcm_convert", "pcm_gather_features",
-    "pcm_set_debug", "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_profile_enable", "pcm_profile_read",
+    "pcm_set_debug", "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_transfer_bytes", "pcm_set_label_cache", "pcm_profile_enable", "pcm_profile_read",
 ]
 
 KERNEL_NAMES = ["score", "segment_reduce", "segment_decide", "segment_resolve", "mask_dilate", "iou", "planes"]
@@ -154,6 +156,17 @@ class Handle:
     @property
     def launch_count(self):
         return int(self.lib.pcm_launch_count(self._h))
+
+    @property
+    def transfer_bytes(self):
+        """(host->device, device->host) bytes copied by the host-buffer entry points so far."""
+        out = np.zeros(2, np.int64)
+        self._check(self.lib.pcm_transfer_bytes(self._h, _ptr(out)))
+        return int(out[0]), int(out[1])
+
+    def set_label_cache(self, on=True):
+        """Re-send only changed 1 MiB chunks of the label map between update() calls (default on)."""
+        self._check(self.lib.pcm_set_label_cache(self._h, int(bool(on))))
 
     def set_stream(self, cuda_stream):
         """Enqueue on this cudaStream_t (integer handle; 0 = legacy default stream)."""
