@@ -519,7 +519,8 @@ def run_sweep(args, rank, world):
         polygons = yaml.full_load(f)
     summary, table = sweep.run(base, polygons, limit=args.sweep_limit or None, max_frames=args.sweep_max_frames or None,
                                out_csv=os.path.join(ROOT, "gpurun_out", "benchmark_results.csv") if rank == 0 and
-                               os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None, log=log)
+                               os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None, log=log,
+                               seq_workers=args.sweep_workers or None)
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         dist.barrier()
@@ -532,7 +533,7 @@ def run_sweep(args, rank, world):
             "scaling": "strong", "vs_baseline": None, "dtype": "u8/f64", "data": "SegTrack2 clips shipped with the reference",
             "config": {"workload": "benchmark.py grid: %d of 256 sequences (64 hyper-parameter combos x soldier/frog/"
                                    "worm/bmx), sharded by forest group, one final all_gather" % summary["n_sequences"],
-                       "per_rank_sequences": summary["per_rank_sequences"], "train_jobs": summary["train_jobs"],
+                       "per_rank_sequences": summary["per_rank_sequences"], "train_jobs": summary["train_jobs"], "seq_workers": summary["seq_workers"],
                        "max_frames": args.sweep_max_frames or None},
             "mean_iou": float(np.nanmean(table["avg_benchmark"])) if table is not None else None, "impl": "b200"}
 
@@ -551,6 +552,7 @@ def main():
                     help="1080p: frames/s (default, the driver's metric); sweep: benchmark.py grid, sequences/s")
     ap.add_argument("--sweep-limit", type=int, default=0, help="only the first N sequences of the 256")
     ap.add_argument("--sweep-max-frames", type=int, default=0)
+    ap.add_argument("--sweep-workers", type=int, default=0, help="sequence threads per rank (0: cores_per_rank / 3, at most 6)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.e2e_only:

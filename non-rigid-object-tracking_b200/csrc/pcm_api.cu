@@ -331,10 +331,24 @@ static Geom make_geom(int n, int n_spaces, const int* ids) {
     g.K = 1 + 8 * n;
     g.F = 3 * g.K * n_spaces;
     g.n_planes = 3 * n_spaces + 1;
-    g.HX = 16;
     g.PH = TILE_H + 2 * n;
-    g.RS = TILE_W + 2 * g.HX;
-    g.PS = g.RS * g.PH;
+    // 2-byte samples (one half-precision compare per node, no threshold unpacking: 5 instead of 6
+    // instructions per node visit, 2 instead of 4 on the ALU pipe) are built and tested but OFF by
+    // default: measured on B200 the kernel is bound by shared-memory instruction issue (1 LDS per
+    // clock per SM), which this does not change, and the larger planes cost K0 2 us
+    // (score 105.9 vs 106.8 us, planes 17.0 vs 14.9 us).  PCM_TILE_F16=1 turns them on when every
+    // tap offset fits the 16-bit field of a node.
+    auto layout = [&](int es) {
+        g.es = es;
+        g.HX = (es == 2 && n <= 8) ? 8 : 16;
+        g.RS = TILE_W + 2 * g.HX;
+        g.PS = g.RS * g.PH;
+    };
+    layout(2);
+    bool f16 = (long long)g.es * g.n_planes * g.PS < (1 << 16);
+    const char* e = getenv("PCM_TILE_F16");
+    f16 = f16 && e && e[0] == '1';
+    if (!f16) layout(1);
     return g;
 }
 
@@ -398,7 +412,7 @@ struct Encoder {
             if (++visited > (size_t)n + 1) { err = "tree is not a tree"; return false; }
             const int i = it.node;
             if (left[i] == -1) {
-                out.nodes[it.entry] = make_node(0u, LEAF_THR, (unsigned)it.entry);
+                out.nodes[it.entry] = make_node(0u, g.es == 2 ? 0x7c00u /* +inf */ : LEAF_THR, (unsigned)it.entry);
                 out.values[it.entry] = value1[i];
                 out.n_leaf++;
                 out.depth = std::max(out.depth, it.depth);
@@ -411,8 +425,9 @@ struct Encoder {
             int plane = 3 * q + ch;
             int thr = tint[i];
             if (thr == -1) { plane = vplane; thr = 0; }   // "tap is outside the crop"
-            const unsigned off = (unsigned)(plane * g.PS + (dr + g.n) * g.RS + (dc + g.HX));
+            const unsigned off = (unsigned)g.es * (unsigned)(plane * g.PS + (dr + g.n) * g.RS + (dc + g.HX));
             if (off >= (1u << 16)) { err = "tap offset overflow"; return false; }
+            if (g.es == 2) thr |= 0x6400;                     // half-precision 1024 + thr
             const int child = (int)out.nodes.size();
             out.nodes.resize(child + 2, make_node(0, 0, 0));
             out.values.resize(child + 2, 0.0);
@@ -439,22 +454,23 @@ static void free_model(Model& m) {
 // for the depths the reference's configs use (config.yaml:26 -> 5; benchmark.py:44 -> 7, 10)
 // or taken from the arguments (DEPTH = 0).
 typedef void (*ScoreFn)(const CUtensorMap, const ScoreArgs);
-struct ScoreVariant { bool smem; int depth; ScoreFn fn; const char* name; };
-constexpr int N_SCORE_VARIANTS = 8;
+struct ScoreVariant { bool smem; int depth; bool f16; ScoreFn fn; const char* name; };
+constexpr int N_SCORE_VARIANTS = 16;
+#define PCM_SV(S, D, F) {S, D, F, score_kernel<S, D, F>, "score_kernel<" #S "," #D "," #F ">"}
 static const ScoreVariant& score_variant(int i) {
     static const ScoreVariant v[N_SCORE_VARIANTS] = {
-        {true, 5, score_kernel<true, 5>, "score_kernel<smem,5>"},   {true, 7, score_kernel<true, 7>, "score_kernel<smem,7>"},
-        {true, 10, score_kernel<true, 10>, "score_kernel<smem,10>"}, {true, 0, score_kernel<true, 0>, "score_kernel<smem,dyn>"},
-        {false, 5, score_kernel<false, 5>, "score_kernel<global,5>"}, {false, 7, score_kernel<false, 7>, "score_kernel<global,7>"},
-        {false, 10, score_kernel<false, 10>, "score_kernel<global,10>"}, {false, 0, score_kernel<false, 0>, "score_kernel<global,dyn>"},
+        PCM_SV(true, 5, false),  PCM_SV(true, 7, false),  PCM_SV(true, 10, false),  PCM_SV(true, 0, false),
+        PCM_SV(false, 5, false), PCM_SV(false, 7, false), PCM_SV(false, 10, false), PCM_SV(false, 0, false),
+        PCM_SV(true, 5, true),   PCM_SV(true, 7, true),   PCM_SV(true, 10, true),   PCM_SV(true, 0, true),
+        PCM_SV(false, 5, true),  PCM_SV(false, 7, true),  PCM_SV(false, 10, true),  PCM_SV(false, 0, true),
     };
     return v[i];
 }
-static const ScoreVariant& pick_score_variant(bool smem, int depth) {
+static const ScoreVariant& pick_score_variant(bool smem, int depth, bool f16) {
     int dyn = -1;
     for (int i = 0; i < N_SCORE_VARIANTS; ++i) {
         const ScoreVariant& v = score_variant(i);
-        if (v.smem != smem) continue;
+        if (v.smem != smem || v.f16 != f16) continue;
         if (v.depth == depth) return v;
         if (v.depth == 0) dyn = i;
     }
@@ -717,8 +733,8 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
 
     // ---- K0: BGR crop -> planar colour planes (+ validity plane) ------------------------
     const Geom& g = h->geom;
-    const long long pitch = ((long long)cw + 127) / 128 * 128;
-    const long long plane_stride = pitch * ch;
+    const long long pitch = ((long long)cw + 127) / 128 * 128;        // samples
+    const long long plane_stride = pitch * ch * g.es;                  // bytes
     CUDA_TRY(h->planes.reserve((size_t)plane_stride * g.n_planes));
     CUDA_TRY(h->sched.reserve(64));
     PlanesArgs pa{};
@@ -749,9 +765,11 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
         KernelTimer kt(h, 6);
         const int mode = (g.n_spaces == 2 && g.space_id[0] == PCM_SPACE_HSV && g.space_id[1] == PCM_SPACE_LAB) ? 1
                          : (g.n_spaces == 1 && g.space_id[0] == PCM_SPACE_LAB) ? 2 : 0;
-        if (mode == 1) planes_kernel<1><<<std::max(blocks, 1), 256, 0, st>>>(pa);
-        else if (mode == 2) planes_kernel<2><<<std::max(blocks, 1), 256, 0, st>>>(pa);
-        else planes_kernel<0><<<std::max(blocks, 1), 256, 0, st>>>(pa);
+        typedef void (*PlanesFn)(const PlanesArgs);
+        static const PlanesFn table[3][2] = {{planes_kernel<0, false>, planes_kernel<0, true>},
+                                             {planes_kernel<1, false>, planes_kernel<1, true>},
+                                             {planes_kernel<2, false>, planes_kernel<2, true>}};
+        table[mode][g.es == 2]<<<std::max(blocks, 1), 256, 0, st>>>(pa);
     }
     CHECK_LAUNCH(h, "planes_kernel");
 
@@ -759,10 +777,11 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     CUtensorMap tmap;
     {
         const cuuint64_t gdim[3] = {(cuuint64_t)cw, (cuuint64_t)ch, (cuuint64_t)g.n_planes};
-        const cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)plane_stride};
+        const cuuint64_t gstr[2] = {(cuuint64_t)(pitch * g.es), (cuuint64_t)plane_stride};   // bytes
         const cuuint32_t box[3] = {(cuuint32_t)g.RS, (cuuint32_t)g.PH, (cuuint32_t)g.n_planes};
         const cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = h->encode_tiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->planes.p, gdim, gstr, box, estr,
+        CUresult r = h->encode_tiled(&tmap, g.es == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                                     h->planes.p, gdim, gstr, box, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(PCM_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d crop", (int)r, cw, ch);
@@ -803,7 +822,7 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     if (!forest_smem) ls = score_smem_layout(a.g, a.f0, a.f1, a.blend, a.novelty, false);
     if ((int)ls.total > h->max_smem_optin)
         return fail(PCM_E_LIMIT, "update: tile needs %u B of shared memory (> %d)", ls.total, h->max_smem_optin);
-    const ScoreVariant& sv = pick_score_variant(forest_smem, a.depth);
+    const ScoreVariant& sv = pick_score_variant(forest_smem, a.depth, g.es == 2);
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sv.fn, NTHREADS, ls.total));
     occ = std::max(occ, 1);

@@ -48,11 +48,15 @@ struct Geom {
     int K;            // 1 + 8 n taps
     int F;            // 3 K Q features
     int n_planes;     // 3 Q + 1 (last plane = in-crop validity)
-    int HX;           // horizontal halo of the smem tile: 16, because the TMA box must start on a
-                      // 16-byte boundary of the row (measured: any other x faults on sm_100a)
+    int es;           // bytes per tile sample: 1 = u8 value v; 2 = the half-precision number
+                      // 1024 + v stored as 0x6400 | v (thresholds are stored the same way, so a node
+                      // test is one half-precision compare with no unpacking; 0 outside the crop)
+    int HX;           // horizontal halo of the smem tile in samples: the TMA box must start on a
+                      // 16-byte boundary of the row (measured: any other x faults on sm_100a), so 16
+                      // samples for u8 and 8 (n <= 8) or 16 for 2-byte samples
     int PH;           // tile rows incl. vertical halo: TILE_H + 2 n
-    int RS;           // plane row stride in the smem tile (bytes) = TMA box width = TILE_W + 2 HX
-    int PS;           // plane stride in the smem tile (bytes)
+    int RS;           // plane row stride in the smem tile (samples) = TMA box width = TILE_W + 2 HX
+    int PS;           // plane stride in the smem tile (samples)
 };
 
 __host__ __device__ inline void star_tap(int k, int& dr, int& dc) {

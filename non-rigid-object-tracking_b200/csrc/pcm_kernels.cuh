@@ -36,21 +36,8 @@ namespace pcm {
 // The crop-border sentinel -1 of the reference (:263) is handled by the encoder:
 // nodes with integer threshold -1 test the validity plane instead (0 outside the crop).
 // ------------------------------------------------------------------------------
-#ifndef PCM_NODE16
-#define PCM_NODE16 0
-#endif
-#if PCM_NODE16
-// 16-byte entries {tap, thr, left, -}: one LDS.128 delivers the three fields unpacked, so a
-// node visit is LDS.128, add (tap address), LDS.U8, compare, predicated add -- no shift/mask
-// work on the ALU pipe (2 cycles per warp instruction on sm_100).
-typedef uint4 NodeT;
-__host__ __device__ inline NodeT make_node(unsigned tap, unsigned thr, unsigned left) { return make_uint4(tap, thr, left, 0u); }
-__host__ __device__ inline unsigned node_tap(const NodeT& n) { return n.x; }
-__host__ __device__ inline unsigned node_thr(const NodeT& n) { return n.y; }
-__host__ __device__ inline unsigned node_left(const NodeT& n) { return n.z; }
-__host__ __device__ inline void node_set_left(NodeT& n, unsigned v) { n.z = v; }
-constexpr unsigned LEAF_THR = 0xffffffffu;
-#else
+// 8-byte entries; a 16-byte {tap, thr, left, -} layout (LDS.128, one ALU op fewer per visit) was
+// measured 22 % slower: the shared-memory pipe saturates (profiles/README.md).
 typedef uint2 NodeT;   // {tap << 16 | thr, left}
 __host__ __device__ inline NodeT make_node(unsigned tap, unsigned thr, unsigned left) { return make_uint2((tap << 16) | thr, left); }
 __host__ __device__ inline unsigned node_tap(const NodeT& n) { return n.x >> 16; }
@@ -58,7 +45,6 @@ __host__ __device__ inline unsigned node_thr(const NodeT& n) { return n.x & 0xff
 __host__ __device__ inline unsigned node_left(const NodeT& n) { return n.y; }
 __host__ __device__ inline void node_set_left(NodeT& n, unsigned v) { n.y = v; }
 constexpr unsigned LEAF_THR = 0xffffu;
-#endif
 constexpr unsigned NODE_BYTES = sizeof(NodeT);
 
 struct DevForest {
@@ -95,8 +81,8 @@ struct PlanesArgs {
     Geom g;
     const ColorTables* tables;
     uint8_t* planes;
-    long long pitch;          // bytes between rows
-    long long plane_stride;   // bytes between planes
+    long long pitch;          // SAMPLES between rows
+    long long plane_stride;   // BYTES between planes
     unsigned* tile_counter;   // reset here for K1's dynamic tile scheduler
     // per-label accumulators of K2, reset here (saves three memset launches per frame)
     int n_labels;
@@ -112,7 +98,8 @@ struct PlanesArgs {
 // MODE 1: features "<n> hsv_lab" (config.yaml:30), MODE 2: "<n> lab" (benchmark.py:48), MODE 0: any
 // combination (space ids read per pixel).  FULL groups (four pixels inside the crop, 4-byte aligned
 // source) take a path without per-pixel bounds checks.
-template <int MODE>
+// F16: samples are written as the half-precision numbers 1024 + v (0x6400 | v), two bytes each.
+template <int MODE, bool F16>
 __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
     __shared__ ColorTables tab;
     for (int i = threadIdx.x; i < (int)(sizeof(ColorTables) / 4); i += blockDim.x)
@@ -200,11 +187,28 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
                 }
             }
         }
-        uint8_t* dst = a.planes + (long long)r * a.pitch + c0;
+        if (!F16) {
+            uint8_t* dst = a.planes + (long long)r * a.pitch + c0;
 #pragma unroll
-        for (int p = 0; p < NOUT; ++p)
-            if (p < nch) *reinterpret_cast<uint32_t*>(dst + p * a.plane_stride) = out[p];
-        *reinterpret_cast<uint32_t*>(dst + nch * a.plane_stride) = valid;
+            for (int p = 0; p < NOUT; ++p)
+                if (p < nch) *reinterpret_cast<uint32_t*>(dst + p * a.plane_stride) = out[p];
+            *reinterpret_cast<uint32_t*>(dst + nch * a.plane_stride) = valid;
+        } else {
+            // bytes [b0 b1 b2 b3] -> halves [64b0 64b1] [64b2 64b3]; pixels outside the crop stay 0
+            const uint32_t m = valid * 0xffu;                         // 0xff per valid pixel
+            const uint32_t mlo = __byte_perm(m, 0u, 0x1100), mhi = __byte_perm(m, 0u, 0x3322);
+            uint8_t* dst = a.planes + ((long long)r * a.pitch + c0) * 2;
+#pragma unroll
+            for (int p = 0; p < NOUT + 1; ++p) {
+                if (p < nch || p == NOUT) {
+                    const uint32_t w = p == NOUT ? valid : out[p < NOUT ? p : 0];
+                    uint2 h;
+                    h.x = __byte_perm(w, 0x64u, 0x4140) & mlo;
+                    h.y = __byte_perm(w, 0x64u, 0x4342) & mhi;
+                    *reinterpret_cast<uint2*>(dst + (p == NOUT ? nch : p) * a.plane_stride) = h;
+                }
+            }
+        }
         w3[0] = nx[0]; w3[1] = nx[1]; w3[2] = nx[2];
     }
 }
@@ -244,12 +248,11 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
-__device__ __forceinline__ NodeT lds_node(uint32_t a) {
-#if PCM_NODE16
-    return lds_v4(a);
-#else
-    return lds_v2(a);
-#endif
+__device__ __forceinline__ NodeT lds_node(uint32_t a) { return lds_v2(a); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
 }
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
     uint32_t v;
@@ -337,20 +340,42 @@ struct ScoreArgs {
 // Branch-free: the PIX_PER_THREAD pointer chases are issued level by level so that
 // their dependent shared-memory loads overlap.  SM = forest staged in shared memory
 // (node links are absolute shared addresses); otherwise nodes/leaves are read through L1.
-// ref + NODE_BYTES (the adjacent right child) iff v > thr: one compare + one predicated add
-__device__ __forceinline__ uint32_t step_child(uint32_t left, uint32_t v, uint32_t thr) {
-#if PCM_NODE16
-    asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 16;\n\t}" : "+r"(left) : "r"(v), "r"(thr));
-#else
-    asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 8;\n\t}" : "+r"(left) : "r"(v), "r"(thr));
-#endif
+// ---- node test -------------------------------------------------------------------------------
+// F16 = false: tile samples are u8 values v, node word x = tap << 16 | thr; right iff v > thr.
+// F16 = true : tile samples and thresholds are the half-precision numbers 1024 + v / 1024 + thr
+//              (0x6400 | v); the low half of x IS the threshold, so the test is one HSETP2 on
+//              the packed word -- no mask on the ALU pipe, and the compare itself leaves it.
+template <bool F16>
+__device__ __forceinline__ uint32_t ld_sample(uint32_t a) { return F16 ? lds_u16(a) : lds_u8(a); }
+
+template <bool F16>
+__device__ __forceinline__ bool goes_right(uint32_t v, uint32_t x) {
+    if (F16) {
+        uint32_t r;
+        asm("{\n\t.reg .pred p;\n\t.reg .b16 a, b, c;\n\tcvt.u16.u32 a, %1;\n\tmov.b32 {b, c}, %2;\n\t"
+            "setp.gt.f16 p, a, b;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(r) : "r"(v), "r"(x));
+        return r != 0;
+    }
+    return v > (x & 0xffffu);
+}
+
+// left + NODE_BYTES (the adjacent right child) iff the sample goes right: one compare + one predicated add
+template <bool F16>
+__device__ __forceinline__ uint32_t step_child(uint32_t left, uint32_t v, uint32_t x) {
+    if (F16) {
+        asm("{\n\t.reg .pred p;\n\t.reg .b16 a, b, c;\n\tcvt.u16.u32 a, %1;\n\tmov.b32 {b, c}, %2;\n\t"
+            "setp.gt.f16 p, a, b;\n\t@p add.u32 %0, %0, 8;\n\t}" : "+r"(left) : "r"(v), "r"(x));
+    } else {
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, 0xffff;\n\tsetp.gt.u32 p, %1, t;\n\t@p add.u32 %0, %0, 8;\n\t}"
+            : "+r"(left) : "r"(v), "r"(x));
+    }
     return left;
 }
 
 // DEPTH > 0: every tree of the forest is walked DEPTH levels (compile-time, fully unrolled);
 // DEPTH == 0: `depth` levels (kernel-uniform run-time value).  Walking a tree deeper than it is
 // costs nothing but time -- leaves self-loop -- so one depth serves the whole forest.
-template <bool SM, int DEPTH>
+template <bool SM, int DEPTH, bool F16>
 __device__ __forceinline__ void traverse_forest(const uint32_t nodes_s, const uint32_t leaves_s,
                                                 const uint8_t* __restrict__ nodes_g,
                                                 const uint8_t* __restrict__ leaves_g,
@@ -359,9 +384,7 @@ __device__ __forceinline__ void traverse_forest(const uint32_t nodes_s, const ui
                                                 const uint32_t (&pix)[PIX_PER_THREAD],
                                                 double (&acc)[PIX_PER_THREAD]) {
     const uint32_t base = SM ? nodes_s : 0u;
-    // leaf value of entry at `ref`: leaves + (ref - base) * 8 / NODE_BYTES
-    constexpr int VSH = (NODE_BYTES == 16) ? 1 : 0;
-    const uint32_t vdelta = leaves_s - (nodes_s >> VSH);   // shared path: value address = (ref >> VSH) + vdelta
+    const uint32_t vdelta = leaves_s - nodes_s;   // shared path: leaf value of the entry at ref = [ref + vdelta]
 
     auto descend = [&](uint32_t (&ref)[PIX_PER_THREAD], const int levels) {
         auto level = [&]() {
@@ -371,9 +394,9 @@ __device__ __forceinline__ void traverse_forest(const uint32_t nodes_s, const ui
             for (int g = 0; g < PIX_PER_THREAD; ++g)
                 nd[g] = SM ? lds_node(ref[g]) : __ldg(reinterpret_cast<const NodeT*>(nodes_g + ref[g]));
 #pragma unroll
-            for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = lds_u8(pix[g] + node_tap(nd[g]));
+            for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = ld_sample<F16>(pix[g] + node_tap(nd[g]));
 #pragma unroll
-            for (int g = 0; g < PIX_PER_THREAD; ++g) ref[g] = step_child(node_left(nd[g]), v[g], node_thr(nd[g]));
+            for (int g = 0; g < PIX_PER_THREAD; ++g) ref[g] = step_child<F16>(node_left(nd[g]), v[g], nd[g].x);
         };
         if (DEPTH > 0) {
 #pragma unroll
@@ -384,8 +407,8 @@ __device__ __forceinline__ void traverse_forest(const uint32_t nodes_s, const ui
         }
 #pragma unroll
         for (int g = 0; g < PIX_PER_THREAD; ++g) {
-            const double leaf = SM ? lds_f64((ref[g] >> VSH) + vdelta)
-                                   : __ldg(reinterpret_cast<const double*>(leaves_g + (ref[g] >> VSH)));
+            const double leaf = SM ? lds_f64(ref[g] + vdelta)
+                                   : __ldg(reinterpret_cast<const double*>(leaves_g + ref[g]));
             acc[g] = __dadd_rn(acc[g], leaf);
         }
     };
@@ -398,26 +421,19 @@ __device__ __forceinline__ void traverse_forest(const uint32_t nodes_s, const ui
         // levels 0 and 1 from warp-uniform operands; also right for trees of depth < 2 because a
         // leaf pseudo-node selects itself
         const NodeT e0 = top.n[t][0], eL = top.n[t][1], eR = top.n[t][2];
-        uint32_t ref[PIX_PER_THREAD], v[PIX_PER_THREAD], tap1[PIX_PER_THREAD], thr1[PIX_PER_THREAD];
+        uint32_t ref[PIX_PER_THREAD], v[PIX_PER_THREAD], x1[PIX_PER_THREAD];
 #pragma unroll
-        for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = lds_u8(pix[g] + node_tap(e0));
+        for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = ld_sample<F16>(pix[g] + node_tap(e0));
 #pragma unroll
         for (int g = 0; g < PIX_PER_THREAD; ++g) {
-            const bool right = v[g] > node_thr(e0);
-#if PCM_NODE16
-            tap1[g] = right ? eR.x : eL.x;
-            thr1[g] = right ? eR.y : eL.y;
-#else
-            tap1[g] = right ? eR.x : eL.x;   // packed tap | thr
-            thr1[g] = tap1[g] & 0xffffu;
-            tap1[g] >>= 16;
-#endif
+            const bool right = goes_right<F16>(v[g], e0.x);
+            x1[g] = right ? eR.x : eL.x;   // packed tap | thr of the level-1 node
             ref[g] = (right ? node_left(eR) : node_left(eL)) + base;
         }
 #pragma unroll
-        for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = lds_u8(pix[g] + tap1[g]);
+        for (int g = 0; g < PIX_PER_THREAD; ++g) v[g] = ld_sample<F16>(pix[g] + (x1[g] >> 16));
 #pragma unroll
-        for (int g = 0; g < PIX_PER_THREAD; ++g) ref[g] = step_child(ref[g], v[g], thr1[g]);
+        for (int g = 0; g < PIX_PER_THREAD; ++g) ref[g] = step_child<F16>(ref[g], v[g], x1[g]);
         descend(ref, DEPTH > 0 ? (DEPTH > 2 ? DEPTH - 2 : 0) : rest);
     }
 #pragma unroll 1
@@ -436,8 +452,9 @@ __device__ __forceinline__ void novelty_error(const double* __restrict__ comp, c
                                               const int* __restrict__ sp, const Geom& g,
                                               const uint32_t (&pix)[PIX_PER_THREAD],
                                               double (&err)[PIX_PER_THREAD]) {
+    // sp[k] and the plane offsets are BYTE offsets; the low byte of a 2-byte sample (0x6400 | v) is v
     const int nch = 3 * g.n_spaces;
-    const int vplane = nch * g.PS;
+    const int vplane = nch * g.PS * g.es;
     double t[PIX_PER_THREAD];
 #pragma unroll
     for (int i = 0; i < PIX_PER_THREAD; ++i) t[i] = 0.0;
@@ -449,7 +466,7 @@ __device__ __forceinline__ void novelty_error(const double* __restrict__ comp, c
             for (int i = 0; i < PIX_PER_THREAD; ++i) ok |= (unsigned)(lds_u8(pix[i] + vplane + so) != 0) << i;
             for (int p = 0; p < nch; ++p) {
                 const int f = (p / 3) * 3 * g.K + 3 * k + (p % 3);
-                const uint32_t off = (uint32_t)(p * g.PS + so);
+                const uint32_t off = (uint32_t)(p * g.PS * g.es + so);
                 if (pass == 0) {
                     const double c255 = comp255[f];
 #pragma unroll
@@ -479,10 +496,10 @@ __device__ __forceinline__ double blend2(double a, double b, double w0, double w
     return __ddiv_rn(__dadd_rn(__dmul_rn(a, w0), __dmul_rn(b, w1)), __dadd_rn(w0, w1));
 }
 
-#ifndef PCM_TILE_BUFS
-#define PCM_TILE_BUFS 2
-#endif
-constexpr int N_TILE_BUF = PCM_TILE_BUFS;   // 2: TMA of tile i+1 overlaps scoring of tile i; 1: rely on co-resident CTAs
+// Tile buffers per CTA: 2 = the TMA load of tile i+1 overlaps the scoring of tile i (u8 tiles);
+// 1 = the twice as large 2-byte tiles, single-buffered so that two CTAs still fit an SM -- the
+// co-resident CTA scores while this one waits for its tile.
+__host__ __device__ constexpr int tile_buffers(int es) { return es == 2 ? 1 : 2; }
 
 struct ScoreSmem {
     uint32_t tiles, bars, sched, sp, f0_nodes, f0_leaves, f0_trees, f1_nodes, f1_leaves, f1_trees, pca0, pca1, total;
@@ -495,9 +512,10 @@ __host__ __device__ inline ScoreSmem score_smem_layout(const Geom& g, const DevF
                                                        bool blend, bool novelty, bool forest_smem) {
     ScoreSmem s;
     uint32_t o = 0;
-    s.tiles = o;  o = align_up(o + N_TILE_BUF * align_up(g.n_planes * g.PS, 128), 128);
-    s.bars = o;   o += 8 * N_TILE_BUF;
-    s.sched = o;  o = align_up(o + 4 * N_TILE_BUF, 16);
+    const int nbuf = tile_buffers(g.es);
+    s.tiles = o;  o = align_up(o + nbuf * align_up(g.n_planes * g.PS * g.es, 128), 128);
+    s.bars = o;   o += 8 * nbuf;
+    s.sched = o;  o = align_up(o + 4 * nbuf, 16);
     s.sp = o;     o = align_up(o + 4 * g.K, 16);
     s.f0_nodes = s.f0_leaves = s.f1_nodes = s.f1_leaves = 0;
     s.f0_trees = o;  o = align_up(o + 16 * f0.n_trees, 16);
@@ -538,19 +556,21 @@ __device__ __forceinline__ void stage_nodes(uint8_t* dst, const NodeT* __restric
 // K1 -----------------------------------------------------------------------------
 // Persistent CTAs; tiles are handed out by an atomic counter and arrive through a
 // two-stage TMA pipeline (the box of tile i+1 is in flight while tile i is scored).
-template <bool FOREST_SMEM, int DEPTH>
+template <bool FOREST_SMEM, int DEPTH, bool F16>
 __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __grid_constant__ CUtensorMap tmap, const ScoreArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const Geom& g = a.g;
     const ScoreSmem L = score_smem_layout(g, a.f0, a.f1, a.blend != 0, a.novelty != 0, FOREST_SMEM);
-    const uint32_t tile_bytes = align_up(g.n_planes * g.PS, 128);
+    constexpr int ES = F16 ? 2 : 1;                  // == g.es (the host picks the instantiation)
+    constexpr int N_TILE_BUF = tile_buffers(ES);
+    const uint32_t tile_bytes = align_up(g.n_planes * g.PS * ES, 128);
     const uint32_t tiles_s = smem_u32(smem + L.tiles);
     const uint32_t bars_s = smem_u32(smem + L.bars);
     volatile int* sched = reinterpret_cast<volatile int*>(smem + L.sched);
     int* sp = reinterpret_cast<int*>(smem + L.sp);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_tiles = a.tiles_x * a.tiles_y;
-    const uint32_t box_bytes = (uint32_t)(g.n_planes * g.PS);
+    const uint32_t box_bytes = (uint32_t)(g.n_planes * g.PS * ES);
 
     auto issue = [&](int buf) {   // thread 0: claim the next tile and start its TMA load
         const int t = (int)atomicAdd(a.tile_counter, 1u);
@@ -574,7 +594,7 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
     for (int k = tid; k < g.K; k += NTHREADS) {
         int dr, dc;
         star_tap(k, dr, dc);
-        sp[k] = (dr + g.n) * g.RS + (dc + g.HX);
+        sp[k] = ((dr + g.n) * g.RS + (dc + g.HX)) * ES;
     }
     copy_to_smem(reinterpret_cast<int4*>(smem + L.f0_trees), a.f0.trees, a.f0.n_trees);
     if (a.blend) copy_to_smem(reinterpret_cast<int4*>(smem + L.f1_trees), a.f1.trees, a.f1.n_trees);
@@ -630,7 +650,7 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
         const int ox = tx0 + col;
         uint32_t pix[PIX_PER_THREAD];
 #pragma unroll
-        for (int i = 0; i < PIX_PER_THREAD; ++i) pix[i] = tiles_s + buf * tile_bytes + (row0 + i) * g.RS + col;
+        for (int i = 0; i < PIX_PER_THREAD; ++i) pix[i] = tiles_s + buf * tile_bytes + ((row0 + i) * g.RS + col) * ES;
 
         // labels of the thread's pixels: requested now, consumed in the epilogue (their HBM/L2
         // latency hides behind the forest traversal)
@@ -644,7 +664,7 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
         double p[PIX_PER_THREAD];
 #pragma unroll
         for (int i = 0; i < PIX_PER_THREAD; ++i) p[i] = 0.0;
-        traverse_forest<FOREST_SMEM, DEPTH>(f0n_s, f0l_s, f0n_g, f0l_g, f0t, a.f0.n_trees, a.depth, a.top0, pix, p);
+        traverse_forest<FOREST_SMEM, DEPTH, F16>(f0n_s, f0l_s, f0n_g, f0l_g, f0t, a.f0.n_trees, a.depth, a.top0, pix, p);
         const double T0 = (double)a.f0.n_trees;
 #pragma unroll
         for (int i = 0; i < PIX_PER_THREAD; ++i) p[i] = __ddiv_rn(p[i], T0);
@@ -652,7 +672,7 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
             double q[PIX_PER_THREAD];
 #pragma unroll
             for (int i = 0; i < PIX_PER_THREAD; ++i) q[i] = 0.0;
-            traverse_forest<FOREST_SMEM, DEPTH>(f1n_s, f1l_s, f1n_g, f1l_g, f1t, a.f1.n_trees, a.depth, a.top1, pix, q);
+            traverse_forest<FOREST_SMEM, DEPTH, F16>(f1n_s, f1l_s, f1n_g, f1l_g, f1t, a.f1.n_trees, a.depth, a.top1, pix, q);
             const double T1 = (double)a.f1.n_trees;
 #pragma unroll
             for (int i = 0; i < PIX_PER_THREAD; ++i) p[i] = blend2(p[i], __ddiv_rn(q[i], T1), a.w0, a.w1);

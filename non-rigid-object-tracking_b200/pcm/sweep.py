@@ -10,6 +10,7 @@ reference's columns (`<video>_benchmark`, `<video>_time`, `avg_benchmark`).
 """
 import itertools
 import os
+import threading
 import time
 
 import numpy as np
@@ -96,17 +97,48 @@ def sequence_config(base, polygons, video, params, videos_path, truth_path):
 
 
 def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Video", truth_path="Input/SegTrack2/Truth",
-              max_frames=None, train_jobs=None, progress=None):
-    """Run this rank's sequences; returns float64 [n, 3] = (sequence id, mean IoU, seconds)."""
-    cache = {}
+              max_frames=None, train_jobs=None, progress=None, seq_workers=1):
+    """Run this rank's sequences; returns float64 [n, 3] = (sequence id, mean IoU, seconds).
+
+    With seq_workers > 1 whole forest groups (the sequences that share their fitted forests) are
+    handed to a small thread pool: one group's scikit-learn fits and SIFT priors (host, GIL
+    released) overlap another group's masker updates (GPU).  Every masker owns its own native
+    context and stream; results do not depend on the schedule."""
     out = np.zeros((len(items), 3), np.float64)
-    for k, (sid, i, v, params) in enumerate(items):
-        cfg = sequence_config(base, polygons, v, params, videos_path, truth_path)
-        cfg["train_jobs"] = train_jobs
-        r = seq_mod.run_sequence(cfg, device=device, model_cache=cache, cache_tag=v, max_frames=max_frames)
-        out[k] = (sid, r["mean_iou"], r["seconds"])
-        if progress:
-            progress(k + 1, len(items), sid, r)
+    groups = {}
+    for k, it in enumerate(items):
+        groups.setdefault(forest_key(it), []).append(k)
+    done = [0]
+    lock = threading.Lock()
+
+    def run_group(indices):
+        cache = {}                                  # rows / forests / PCAs of this group
+        for k in indices:
+            sid, i, v, params = items[k]
+            cfg = sequence_config(base, polygons, v, params, videos_path, truth_path)
+            cfg["train_jobs"] = train_jobs
+            r = seq_mod.run_sequence(cfg, device=device, model_cache=cache, cache_tag=v, max_frames=max_frames)
+            out[k] = (sid, r["mean_iou"], r["seconds"])
+            with lock:
+                done[0] += 1
+                if progress:
+                    progress(done[0], len(items), sid, r)
+
+    order = sorted(groups.values(), key=lambda ix: -sum(item_cost(items[k]) for k in ix))
+    if seq_workers <= 1 or len(order) <= 1:
+        for ix in order:
+            run_group(ix)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        from . import capi
+        capi.load_library()                                             # dlopen once, before the threads
+        for v in sorted({items[k][2] for k in range(len(items))}):      # decode every clip once, up front
+            cfg = sequence_config(base, polygons, v, items[0][3], videos_path, truth_path)
+            seq_mod.read_clip(seq_mod.resolve_path(cfg["input_video"]), cfg.get("resize_factor") or 1)
+            seq_mod.read_clip(seq_mod.resolve_path(cfg["input_truth"]), cfg.get("resize_factor") or 1)
+        with ThreadPoolExecutor(max_workers=seq_workers) as pool:
+            for f in [pool.submit(run_group, ix) for ix in order]:
+                f.result()
     return out
 
 
@@ -148,7 +180,7 @@ def results_table(all_rows, videos=None, hyper=None):
 
 
 def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, out_csv=None, backend=None,
-        train_jobs=None, log=None):
+        train_jobs=None, log=None, seq_workers=None):
     """Entry point used by benchmark.py / bench.py --workload sweep.  Reads RANK / WORLD_SIZE /
     LOCAL_RANK; returns (summary dict, table or None) -- the table on rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -172,10 +204,19 @@ def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, ou
         elif not dist.is_initialized():
             dist.init_process_group(backend)
         dist.barrier()
+    cores = max(1, (os.cpu_count() or 1) // max(world, 1))        # host cores of this rank
+    if seq_workers is None:
+        seq_workers = max(1, min(6, cores // 3))
     if train_jobs is None:
-        train_jobs = max(1, (os.cpu_count() or 1) // max(world, 1))
+        train_jobs = max(1, cores // seq_workers)
+    try:
+        import cv2
+        cv2.setNumThreads(max(1, cores // seq_workers))             # SIFT's internal parallel_for
+    except Exception:
+        pass
     t0 = time.time()
     local = run_shard(shards[rank], base, polygons, device=local_rank, max_frames=max_frames, train_jobs=train_jobs,
+                      seq_workers=seq_workers,
                       progress=(lambda k, n, sid, r: log("[rank %d] %d/%d seq %d iou %.3f %.2fs (train %.2fs, decode %.2fs, wall %.2fs)" %
                                                          (rank, k, n, sid, r["mean_iou"], r["seconds"], r["train_seconds"],
                                                           r["decode_seconds"], r["wall_seconds"])))
@@ -188,7 +229,8 @@ def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, ou
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_all = float(t.item())
     summary = dict(n_sequences=len(items), seconds=t_all, sequences_per_s=len(items) / t_all if t_all > 0 else 0.0,
-                   n_gpus=world, per_rank_sequences=[len(s) for s in shards], train_jobs=train_jobs)
+                   n_gpus=world, per_rank_sequences=[len(s) for s in shards], train_jobs=train_jobs,
+                   seq_workers=seq_workers, host_cores=os.cpu_count())
     table = None
     if rank == 0:
         table = results_table(all_rows, videos, hyper)

@@ -473,3 +473,18 @@ def test_device_pointer_path_equals_host_path():
     assert tuple(int(v) for v in d_counts.cpu()) == want_counts == orc.iou_counts(want[..., 2], truth)
     h.use_own_stream()
     h.close()
+
+
+def test_two_byte_tile_variant_in_a_subprocess():
+    """PCM_TILE_F16=1 (2-byte tile samples, half-precision node tests, single-buffered tiles) is an
+    opt-in K1/K0 variant: the forest-shape, random-forest and golden-sequence parity cases must
+    hold for it as well."""
+    import subprocess
+    import sys
+    env = dict(os.environ, PCM_TILE_F16="1")
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                          "forest_shapes or random_forests or update_sequence or full_hd or priors"],
+                         env=env, capture_output=True, text=True, timeout=1200,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert " passed" in res.stdout

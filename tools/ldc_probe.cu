@@ -1,53 +1,51 @@
-// ldc_probe.cu -- throughput of indexed constant-bank loads (LDC.64) vs shared loads
-// (LDS.64) for the node fetch of the forest traversal.  Debug/measurement aid.
+// ldc_probe.cu -- does a DIVERGENT indexed constant-bank load (LDC.64, <= 4 distinct addresses per
+// warp) ride for free next to a kernel that saturates the shared-memory/LSU pipe?
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ldc_probe tools/ldc_probe.cu && tools/ldc_probe
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
 
-__constant__ uint2 c_nodes[4096];
+struct Table { uint2 n[48][8]; };
 
-template <int MODE>   // 0 = LDC, 1 = LDS
-__global__ void chase(const uint2* g_nodes, int iters, int spread, unsigned* out) {
-    __shared__ uint2 s_nodes[4096];
-    for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_nodes[i] = g_nodes[i];
+template <int MODE>   // 0: 2 LDS.64 / iter; 1: + LDC.64 divergent(4); 2: + third LDS.64 instead; 3: + LDC.64 uniform
+__global__ void __launch_bounds__(256, 2) probe(const __grid_constant__ Table tab, uint32_t* out, int iters) {
+    __shared__ uint2 sm[2048];
+    for (int i = threadIdx.x; i < 2048; i += 256) sm[i] = make_uint2(i * 8 + 8, (i * 37) & 2047);
     __syncthreads();
-    // 8 independent chains per thread, like the traversal; `spread` distinct start nodes per warp
-    unsigned ref[8], acc = 0;
-    for (int g = 0; g < 8; ++g) ref[g] = ((threadIdx.x & 31) % spread) * 64 + g;
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            uint2 nd = MODE == 0 ? c_nodes[ref[g]] : s_nodes[ref[g]];
-            acc += nd.y;
-            ref[g] = nd.x;
-        }
+    uint32_t a = threadIdx.x & 2047, b = (threadIdx.x * 7) & 2047, c = (threadIdx.x * 13) & 2047, acc = 0;
+    uint32_t sel = threadIdx.x & 3;
+    for (int i = 0; i < iters; ++i) {
+        const uint2 x = sm[a], y = sm[b];
+        a = x.y; b = y.y;
+        if (MODE == 1) { const uint2 z = tab.n[i % 48][4 + sel]; acc += z.x; sel = (sel + z.y) & 3; }
+        if (MODE == 2) { const uint2 z = sm[c]; c = z.y; acc += z.x; }
+        if (MODE == 3) { const uint2 z = tab.n[i % 48][4 + (i & 3)]; acc += z.x + z.y; }
+        acc += x.x ^ y.x;
     }
-    if (acc == 0xdeadbeef) out[0] = acc + ref[0];
-    out[1 + blockIdx.x * blockDim.x + threadIdx.x] = ref[3] + acc;
+    out[blockIdx.x * 256 + threadIdx.x] = acc + a + b + c + sel;
 }
 
 int main() {
-    uint2 h[4096];
-    for (int i = 0; i < 4096; ++i) { h[i].x = (i / 64) * 64 + (i * 7 + 3) % 64; h[i].y = i; }
-    cudaMemcpyToSymbol(c_nodes, h, sizeof h);
-    uint2* g; cudaMalloc(&g, sizeof h); cudaMemcpy(g, h, sizeof h, cudaMemcpyHostToDevice);
-    unsigned* out; cudaMalloc(&out, 4 * (1 + 148 * 8 * 256));
-    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    const int iters = 2000, blocks = 148 * 2, threads = 256;
-    for (int mode = 0; mode < 2; ++mode)
-        for (int spread : {1, 2, 4, 8, 32}) {
-            for (int rep = 0; rep < 2; ++rep) {
-                cudaEventRecord(a);
-                if (mode == 0) chase<0><<<blocks, threads>>>(g, iters, spread, out);
-                else chase<1><<<blocks, threads>>>(g, iters, spread, out);
-                cudaEventRecord(b);
-                cudaEventSynchronize(b);
-            }
-            float ms; cudaEventElapsedTime(&ms, a, b);
-            double loads = (double)blocks * threads / 32 * iters * 8;   // warp-level loads
-            double per_sm_per_clk = loads / 148 / (ms * 1e-3 * 1.965e9);
-            printf("%s spread %2d: %.3f ms, %.3f warp-loads/clk/SM (%s)\n", mode == 0 ? "LDC.64" : "LDS.64", spread, ms,
-                   per_sm_per_clk, cudaGetErrorString(cudaGetLastError()));
+    Table t;
+    for (int i = 0; i < 48; ++i) for (int j = 0; j < 8; ++j) t.n[i][j] = make_uint2(i * 8 + j, (i + j) & 3);
+    uint32_t* out; cudaMalloc(&out, 148 * 2 * 256 * 4);
+    const int iters = 20000;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int mode = 0; mode < 4; ++mode) {
+        float best = 1e9f;
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(e0);
+            if (mode == 0) probe<0><<<296, 256>>>(t, out, iters);
+            if (mode == 1) probe<1><<<296, 256>>>(t, out, iters);
+            if (mode == 2) probe<2><<<296, 256>>>(t, out, iters);
+            if (mode == 3) probe<3><<<296, 256>>>(t, out, iters);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); best = ms < best ? ms : best;
         }
+        // warp-iterations per SM per clock: 16 warps/SM * iters / (ms * clock)
+        printf("mode %d: %.3f ms  (%.2f SM-cycles per warp-iteration at 1.965 GHz)\n", mode, best,
+               best * 1e-3 * 1.965e9 / (16.0 * iters));
+    }
+    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
