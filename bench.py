@@ -399,7 +399,7 @@ def run_b200(args, rank, world, local_rank):
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "k1_ms": k1_ms, "kernel_share_of_step": k1_ms / step_kernel_ms if step_kernel_ms else None,
                 "per_kernel_ms": {k: (v[0] / v[1] if v[1] else 0.0) for k, v in prof.items()},
-                "limiter": "issue slots / shared-memory wavefronts of the forest traversal (see DESIGN.md)"}
+                "limiter": "shared-memory instruction rate (1 LDS/clk/SM; 9.07 LDS per pixel-tree), see DESIGN.md section 4"}
     traffic_file = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.isfile(traffic_file):
         try:
