@@ -131,6 +131,9 @@ struct DevBuf {
     int device = 0;
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        // growing: kernels queued by an asynchronous entry point may still use the old block, and a
+        // parked block can be handed to another handle at once -- wait for the device first (rare)
+        if (p) cudaDeviceSynchronize();
         release();
         cudaGetDevice(&device);
         if (BlockCache::instance().take(device, bytes, &p, &cap)) return cudaSuccess;
@@ -816,7 +819,7 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     a.seg.sum = pa.sum; a.seg.asum = pa.asum; a.seg.area = pa.area;
     a.seg.rmin = pa.rmin; a.seg.rmax = pa.rmax; a.seg.err = pa.err;
 
-    // forests live in shared memory when two CTAs per SM still fit, else they are read through L1
+    // forests live in shared memory whenever one CTA's tiles + forests fit, else they are read through L1
     ScoreSmem ls = score_smem_layout(a.g, a.f0, a.f1, a.blend, a.novelty, true);
     const bool forest_smem = (int)ls.total <= h->max_smem_optin;
     if (!forest_smem) ls = score_smem_layout(a.g, a.f0, a.f1, a.blend, a.novelty, false);
