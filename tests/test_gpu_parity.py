@@ -488,3 +488,61 @@ def test_two_byte_tile_variant_in_a_subprocess():
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
     assert " passed" in res.stdout
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_geometry_forest_labels(seed):
+    """Random feature geometry (n, colour spaces), crop position / size (incl. widths that are not
+    multiples of 4 and crops touching frame borders), forest size / depth, label maps, dilation
+    kernel, blend weights and priors: P(fg) bit-equal, mask equal to the oracle's decision on the
+    device's probabilities + dilation."""
+    from pcm import capi
+    from pcm.providers import grid_segments, voronoi_segments
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 13))
+    spaces = list(rng.permutation(["rgb", "hsv", "lab"])[:int(rng.integers(1, 4))])
+    F = 3 * (1 + 8 * n) * len(spaces)
+    H, W = int(rng.integers(40, 200)), int(rng.integers(40, 260))
+    frame = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    w, hh = int(rng.integers(1, W + 1)), int(rng.integers(1, H + 1))
+    x, y = int(rng.integers(0, W - w + 1)), int(rng.integers(0, H - hh + 1))
+    rect = (x, y, w, hh)
+    crop = frame[y:y + hh, x:x + w]
+    t0 = _random_forest_arrays(rng, int(rng.integers(1, 25)), int(rng.integers(0, 9)), F)
+    t1 = _random_forest_arrays(rng, int(rng.integers(1, 25)), int(rng.integers(0, 9)), F)
+    seg = grid_segments(crop, int(rng.integers(2, 12))) if seed % 2 else voronoi_segments(crop, int(rng.integers(1, 60)), seed)
+    S = int(seg.max()) + 1
+    k = int(rng.integers(1, 10))
+    blend = bool(seed % 3)
+    tau = float(rng.random())
+    pw = float(rng.choice([0.0, 0.1, 0.3]))
+    priors = rng.choice(np.array([-1, 1], np.float32), S) if pw else None
+    h = capi.Handle(0, debug=True)
+    h.set_features(n, spaces)
+    h.add_model_arrays(0, t0)
+    h.add_model_arrays(7, t1)
+    prm = capi.Handle.make_params(0, 1 if blend else -1, 1 - tau if blend else 1.0, tau if blend else 0.0,
+                                  dilation_kernel=k, prior_weight=pw)
+    mask = np.zeros((H, W, 3), np.uint8)
+    h.update(frame, rect, seg, S, priors, prm, mask)
+    d = h.debug_last(hh, w, S)
+    X = orc.get_features_int(orc.build_planes(crop, spaces), n)
+    p0 = orc.forest_p1(orc.forest_from_arrays(t0, F), X)
+    want = p0
+    if blend:
+        p1 = orc.forest_p1(orc.forest_from_arrays(t1, F), X)
+        want = (p0 * (1 - tau) + p1 * tau) / ((1 - tau) + tau)
+    assert np.array_equal(d["p1"], want), (n, spaces, rect)
+    scores, areas = orc.saliency_scores(d["p1"], np.zeros(hh * w), seg, 0.0,
+                                        priors if priors is not None else np.full(S, -1, np.float32), pw)
+    assert np.array_equal(d["areas"], areas)
+    # labels away from 0.5 keep the parallel float64 sum (last-ulp differences from the sequential
+    # float32 one); labels inside the guard band are re-evaluated exactly -- decisions are equal
+    np.testing.assert_allclose(d["scores"], scores, rtol=1e-5, atol=1e-7)
+    pre = orc.saliency_mask(scores, seg)
+    assert np.array_equal(d["pre"], pre)
+    assert np.array_equal(mask[y:y + hh, x:x + w, 2], orc.dilate(pre, k))
+    out = mask.copy()
+    out[y:y + hh, x:x + w, 2] = 0
+    assert not out.any(), "wrote outside the crop or outside channel 2"
+    h.close()
