@@ -30,8 +30,20 @@ COLORS = [(0, 0, 255), (0, 255, 0), (255, 0, 0), (0, 255, 255), (255, 0, 255), (
 
 
 def load_config(path):
+    """YAML config with the reference's keys (config.yaml:1-37).  `polygons: <clip>` pulls pts /
+    pts_frame_numbers / bboxes_roni of that clip from polygons.yaml next to the config (or the
+    package's) unless they are given inline."""
     with open(path) as f:
-        return yaml.full_load(f)
+        cfg = yaml.full_load(f)
+    name = cfg.get("polygons")
+    if name and cfg.get("pts") is None:
+        for d in (os.path.dirname(os.path.abspath(path)), PKG):
+            pp = os.path.join(d, "polygons.yaml")
+            if os.path.isfile(pp):
+                with open(pp) as f:
+                    cfg.update(yaml.full_load(f)[name])
+                break
+    return cfg
 
 
 def resolve_path(p):
