@@ -54,10 +54,16 @@ private:
         int n = 0;
         if (const char* e = getenv("PCM_HOST_THREADS")) n = atoi(e);
         if (n <= 0) {
-            // measured on the 16-vCPU B200 host: staging saturates with 4-6 threads
+            // measured on the 16-vCPU B200 host: staging saturates with 4-6 threads.  Under a
+            // one-process-per-GPU launcher the cores are shared by LOCAL_WORLD_SIZE ranks.
             const unsigned hw = std::thread::hardware_concurrency();
-            n = (int)(hw / 3);
+            int ranks = 1;
+            if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e);
+            if (ranks < 1) ranks = 1;
+            const int cores = (int)hw / ranks;
+            n = cores * 3 / 4;
             if (n > 6) n = 6;
+            if (cores < 4) spin_us_ = 50;     // no spare core to spin on
         }
         if (const char* e = getenv("PCM_HOST_SPIN_US")) spin_us_ = atoi(e);
         if (n < 1) n = 1;
