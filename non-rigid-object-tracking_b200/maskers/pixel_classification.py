@@ -29,18 +29,21 @@ from .masker import Masker
 
 class PixelClassificationNonRigidMasker(Masker):
     def __init__(self, poly_roi=None, update_mask=None, segment_fn=None, prior_fn=None, device=0,
-                 model_cache=None, cache_tag=None, train_jobs=None, **args):
+                 model_cache=None, cache_tag=None, train_jobs=None, fit_estimators=None, **args):
         """Reference keywords: debug, frame, config, poly_roi, update_mask (main.py:138-144).
         Extra, all optional: `segment_fn(crop) -> int32 labels` and `prior_fn` (providers for the
         stages outside the hot path), `device` (CUDA ordinal), `model_cache` + `cache_tag` (a dict
         shared between maskers of a hyper-parameter sweep: training rows, fitted forests and PCAs
         are reused when (tag, frame, features, n_estimators, max_depth) repeat -- fits are
         deterministic, random_state=42), `train_jobs` (sklearn n_jobs for the fit; the fitted
-        forest does not depend on it)."""
+        forest does not depend on it), `fit_estimators` (a sweep's largest n_estimators: the forest
+        is fitted once with that many trees and every smaller n_estimators uses its first trees --
+        with random_state=42 tree i is the same tree in both, tests/test_sweep_host.py)."""
         Masker.__init__(self, **args)
         self.model_cache = model_cache
         self.cache_tag = cache_tag
         self.train_jobs = train_jobs
+        self.fit_estimators = fit_estimators
         self.poly_roi = copy.deepcopy(poly_roi)
         self.index = 0
         self.models = []
@@ -73,49 +76,55 @@ class PixelClassificationNonRigidMasker(Masker):
             raise ValueError("bbox_roni is required (the reference opens a GUI selector here, :287)")
         params = self.config["params"]
         cache = self.model_cache if self.model_cache is not None and self.cache_tag is not None else None
-        kx = (self.cache_tag, n_frame, params["features"], "rows")
-        if cache is not None and kx in cache:
-            X, labels = cache[kx]
-        else:
+
+        def cached(key, make):
+            """cache[key], computing it at most once (also across threads when the cache offers get_or_compute)."""
+            if cache is None:
+                return make()
+            if hasattr(cache, "get_or_compute"):
+                return cache.get_or_compute(key, make)
+            if key not in cache:
+                cache[key] = make()
+            return cache[key]
+
+        def make_rows():
             x, y, w, h = [int(v) for v in bbox]
             roi = np.zeros((h, w), np.uint8)
             cv.fillPoly(roi, np.array([[(p[0] - x, p[1] - y) for p in poly_roi]], dtype=np.int32), 255)
             X = self._rows(frame, (x, y, w, h))
             labels = (roi.reshape(-1) > 0).astype(np.int64)
             Xn = self._rows(frame, tuple(int(v) for v in bbox_roni))
-            X = np.concatenate([X, Xn], axis=0)
-            labels = np.concatenate([labels, np.zeros(len(Xn), np.int64)])
-            if cache is not None:
-                cache[kx] = (X, labels)
+            return np.concatenate([X, Xn], axis=0), np.concatenate([labels, np.zeros(len(Xn), np.int64)])
 
-        kf = (self.cache_tag, n_frame, params["features"], params["n_estimators"], params["max_depth"], "forest")
-        if cache is not None and kf in cache:
-            clf = cache[kf]
-        else:
-            clf = RandomForestClassifier(random_state=42, n_estimators=params["n_estimators"],
-                                         max_depth=params["max_depth"], n_jobs=self.train_jobs).fit(X, labels)
-            print("F1 score classifier for frame {}= {}".format(n_frame, round(f1_score(labels, clf.predict(X)), 2)))
-            if cache is not None:
-                cache[kf] = clf
+        X, labels = cached((self.cache_tag, n_frame, params["features"], "rows"), make_rows)
+
+        n_trees = int(params["n_estimators"])
+        n_fit = max(n_trees, int(self.fit_estimators or 0))
+
+        def make_forest():
+            clf = RandomForestClassifier(random_state=42, n_estimators=n_fit, max_depth=params["max_depth"],
+                                         n_jobs=self.train_jobs).fit(X, labels)
+            if n_fit == n_trees:
+                print("F1 score classifier for frame {}= {}".format(n_frame, round(f1_score(labels, clf.predict(X)), 2)))
+            return clf
+
+        clf = cached((self.cache_tag, n_frame, params["features"], n_fit, params["max_depth"], "forest"), make_forest)
+
         if params["novelty_detection"]:
-            kp = (self.cache_tag, n_frame, params["features"], params["n_components"], "pca")
-            if cache is not None and kp in cache:
-                pca, threshold = cache[kp]
-            else:
+            def make_pca():
                 pca = PCA(n_components=params["n_components"]).fit(X[labels == 1])
                 if pca.components_.shape[0] != 1:
                     raise ValueError("the native novelty path supports n_components == 1 (config.yaml:27)")
                 residual = np.sum(np.sqrt(np.power(X - pca.inverse_transform(pca.transform(X)), 2)), axis=1)
-                threshold = np.percentile(residual, 90)
-                if cache is not None:
-                    cache[kp] = (pca, threshold)
+                return pca, np.percentile(residual, 90)
+            pca, threshold = cached((self.cache_tag, n_frame, params["features"], params["n_components"], "pca"), make_pca)
         else:
             pca, threshold = None, 0.0
 
-        m = self.native.add_forest(n_frame, clf)
+        m = self.native.add_forest(n_frame, clf, n_trees)
         if pca is not None:
             self.native.set_novelty(m, pca.mean_, pca.components_[0])
-        self.models.append({"n_frame": n_frame, "model": clf})
+        self.models.append({"n_frame": n_frame, "model": clf, "n_trees": n_trees})
         self.novelty_det.append({"n_frame": n_frame, "model": pca, "threshold": threshold})
         return bbox_roni
 

@@ -191,12 +191,13 @@ class Handle:
                                            _ptr(thr), _ptr(left), _ptr(right), _ptr(val), C.byref(idx)))
         return idx.value
 
-    def add_forest(self, n_frame, clf):
-        """Export a fitted sklearn RandomForestClassifier (binary, classes {0,1})."""
+    def add_forest(self, n_frame, clf, n_trees=None):
+        """Export a fitted sklearn RandomForestClassifier (binary, classes {0,1}); `n_trees`: only
+        its first n_trees estimators (with a fixed random_state they ARE the smaller forest)."""
         if list(clf.classes_) != [0, 1]:
             raise ValueError("forest must be a binary {0,1} classifier (the reference indexes probs[:,1])")
         arrays = []
-        for est in clf.estimators_:
+        for est in clf.estimators_[:n_trees]:
             t = est.tree_
             arrays.append((t.feature, t.threshold, t.children_left, t.children_right, t.value[:, 0, 1]))
         return self.add_model_arrays(n_frame, arrays)

@@ -184,7 +184,7 @@ def run_sequence(config, device=0, out_path=None, segment_fn=None, prior_fn=None
         if config.get("masker") == "PC":
             extra = dict(segment_fn=segment_fn, prior_fn=prior_fn, device=device, model_cache=model_cache,
                          cache_tag=(cache_tag, n_target) if cache_tag is not None else None,
-                         train_jobs=config.get("train_jobs"))
+                         train_jobs=config.get("train_jobs"), fit_estimators=config.get("fit_estimators"))
         maskers.append(getMaskerByName(config.get("masker"), debug=debug, frame=frames[0], config=config,
                                        poly_roi=pts[n_target][0], update_mask=config.get("update_mask"), **extra))
         for n_selection, selection in enumerate(target_selection):

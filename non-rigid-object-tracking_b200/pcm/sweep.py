@@ -64,13 +64,42 @@ def forest_key(item):
     return (v, p["features"], p["n_estimators"], p["max_depth"])
 
 
+def fit_key(item):
+    """Sequences with equal fit_key train on the same rows and share ONE fit: the forest is fitted with
+    the grid's largest n_estimators and smaller forests are its first trees."""
+    _, _, v, p = item
+    return (v, p["features"], p["max_depth"])
+
+
+class ModelCache:
+    """Rank-wide cache of training rows, fitted forests and PCAs, safe for the sequence threads:
+    a value is computed once, by the first thread that asks for it."""
+
+    def __init__(self):
+        self.values, self.locks, self.guard = {}, {}, threading.Lock()
+
+    def get_or_compute(self, key, make):
+        with self.guard:
+            if key in self.values:
+                return self.values[key]
+            lock = self.locks.setdefault(key, threading.Lock())
+        with lock:
+            with self.guard:
+                if key in self.values:
+                    return self.values[key]
+            value = make()
+            with self.guard:
+                self.values[key] = value
+            return value
+
+
 def partition(items, world):
-    """Longest-processing-time assignment of GROUPS of sequences that share their forests
-    (same video, features, n_estimators, max_depth) so that every fit happens on one rank only.
+    """Longest-processing-time assignment of GROUPS of sequences that share their fits
+    (same video, features, max_depth) so that every fit happens on one rank only.
     Returns `world` lists of items; deterministic."""
     groups = {}
     for it in items:
-        groups.setdefault(forest_key(it), []).append(it)
+        groups.setdefault(fit_key(it), []).append(it)
     order = sorted(groups.items(), key=lambda kv: (-sum(item_cost(i) for i in kv[1]), str(kv[0])))
     # more ranks than groups: split the heaviest groups until every rank has work
     while len(order) < world and any(len(g) > 1 for _, g in order):
@@ -111,12 +140,15 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
     done = [0]
     lock = threading.Lock()
 
+    cache = ModelCache()                            # rows / forests / PCAs, shared by the threads of this rank
+    fit_estimators = max([int(it[3]["n_estimators"]) for it in items] or [0])
+
     def run_group(indices):
-        cache = {}                                  # rows / forests / PCAs of this group
         for k in indices:
             sid, i, v, params = items[k]
             cfg = sequence_config(base, polygons, v, params, videos_path, truth_path)
             cfg["train_jobs"] = train_jobs
+            cfg["fit_estimators"] = fit_estimators
             r = seq_mod.run_sequence(cfg, device=device, model_cache=cache, cache_tag=v, max_frames=max_frames)
             out[k] = (sid, r["mean_iou"], r["seconds"])
             with lock:

@@ -102,3 +102,41 @@ def test_gather_single_rank_needs_no_collective():
     local = np.array([[3, 0.1, 1.0], [1, 0.2, 2.0]])
     out = sweep.gather(local, 1)
     assert np.array_equal(out[:, 0], [1, 3])
+
+
+def test_smaller_forest_is_a_prefix_of_the_larger_one():
+    """What `fit_estimators` relies on: with random_state=42 (the reference's, :199) tree i of a
+    20-tree forest IS tree i of the 30-tree forest of the same depth on the same rows."""
+    from sklearn.ensemble import RandomForestClassifier
+    rng = np.random.default_rng(3)
+    X = rng.integers(-1, 256, (3000, 60)).astype(np.float64) / 255
+    y = ((X[:, 5] > 0.5) ^ (X[:, 17] > 0.3)).astype(np.int64)
+    small = RandomForestClassifier(random_state=42, n_estimators=20, max_depth=7).fit(X, y)
+    large = RandomForestClassifier(random_state=42, n_estimators=30, max_depth=7, n_jobs=3).fit(X, y)
+    for a, b in zip(small.estimators_, large.estimators_[:20]):
+        ta, tb = a.tree_, b.tree_
+        assert np.array_equal(ta.feature, tb.feature) and np.array_equal(ta.threshold, tb.threshold)
+        assert np.array_equal(ta.children_left, tb.children_left) and np.array_equal(ta.value, tb.value)
+    # and the probability of the small forest is the mean over that prefix
+    p = np.mean([e.predict_proba(X)[:, 1] for e in large.estimators_[:20]], axis=0)
+    np.testing.assert_allclose(p, small.predict_proba(X)[:, 1], rtol=0, atol=1e-15)
+
+
+def test_model_cache_computes_once_under_threads():
+    import threading
+    import time
+    from pcm.sweep import ModelCache
+    cache, calls = ModelCache(), []
+
+    def make():
+        calls.append(1)
+        time.sleep(0.05)
+        return object()
+    out = []
+    ts = [threading.Thread(target=lambda: out.append(cache.get_or_compute(("k", 1), make))) for _ in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert len(calls) == 1 and all(o is out[0] for o in out)
+    assert cache.get_or_compute(("k", 2), make) is not out[0] and len(calls) == 2
