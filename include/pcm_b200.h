@@ -183,6 +183,17 @@ int pcm_quickshift_device(pcm_handle* h, const uint8_t* d_frame, int frame_h, in
                           const int rect[4], double ratio, double kernel_size, double max_dist,
                           const double* d_noise, int32_t* d_labels_out, int* n_labels_out);
 
+/* skimage.segmentation.felzenszwalb(crop, scale, sigma, min_size) of scikit-image 0.17.2 (:72-73) on
+ * the crop `rect` of a HOST frame.  HOST code (no handle, no device): the edge-ordered merge is
+ * inherently sequential, and it is not part of the per-frame hot path.  Edges of equal cost are
+ * processed in a fixed order (right, down, down-right, up-right; raster order within each).
+ *   kernel      2 * kernel_radius + 1 Gaussian weights (scipy's _gaussian_kernel1d), or NULL to
+ *               compute them from sigma
+ *   labels_out  h*w int32, labels numbered like np.unique(root, return_inverse=True) */
+int pcm_felzenszwalb(const uint8_t* frame, int frame_h, int frame_w, int64_t frame_stride, const int rect[4],
+                     double scale, double sigma, int min_size, const double* kernel, int kernel_radius,
+                     int32_t* labels_out, int* n_labels_out);
+
 /* ---- parity taps (tests, smoke; not needed by the reference flow) -------- */
 
 /* cv.cvtColor(img, BGR2HSV / BGR2LAB) of an h x w x 3 host image with the same

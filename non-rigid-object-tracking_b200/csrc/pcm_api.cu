@@ -25,6 +25,9 @@ using namespace pcm;
 namespace pcm {   // pcm_host_simd.cpp
 void gather_strided(const uint8_t* src, int64_t stride, uint8_t* dst, int n);
 void scatter_strided(const uint8_t* src, uint8_t* dst, int64_t stride, int n);
+// pcm_felzenszwalb.cpp
+int felzenszwalb(const uint8_t* frame, int64_t stride, int cx, int cy, int w, int h, double scale, double sigma,
+                 int min_size, const double* kernel, int radius, int32_t* labels_out);
 }
 
 // ---------------------------------------------------------------------------------
@@ -1309,6 +1312,21 @@ extern "C" int pcm_quickshift(pcm_handle* h, const uint8_t* frame, int H, int W,
     h->qs_frame_ptr = frame;
     memcpy(h->qs_rect, rect, sizeof h->qs_rect);
     h->qs_valid = true;
+    return PCM_OK;
+}
+
+extern "C" int pcm_felzenszwalb(const uint8_t* frame, int H, int W, int64_t stride, const int rect[4], double scale,
+                                double sigma, int min_size, const double* kernel, int kernel_radius,
+                                int32_t* labels_out, int* n_labels_out) {
+    if (!frame || !rect || !labels_out) return fail(PCM_E_INVALID, "pcm_felzenszwalb: NULL argument");
+    if (rect[2] <= 0 || rect[3] <= 0 || rect[0] < 0 || rect[1] < 0 || rect[0] + rect[2] > W || rect[1] + rect[3] > H)
+        return fail(PCM_E_INVALID, "pcm_felzenszwalb: rect outside the frame");
+    if ((long long)rect[2] * rect[3] > (1LL << 28)) return fail(PCM_E_LIMIT, "pcm_felzenszwalb: crop too large");
+    if (kernel && kernel_radius < 0) return fail(PCM_E_INVALID, "pcm_felzenszwalb: kernel_radius %d", kernel_radius);
+    const int n = felzenszwalb(frame, stride, rect[0], rect[1], rect[2], rect[3], scale, sigma, min_size, kernel,
+                               kernel_radius, labels_out);
+    if (n < 0) return fail(PCM_E_INVALID, "pcm_felzenszwalb: bad arguments");
+    if (n_labels_out) *n_labels_out = n;
     return PCM_OK;
 }
 

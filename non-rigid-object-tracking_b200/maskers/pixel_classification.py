@@ -57,10 +57,12 @@ class PixelClassificationNonRigidMasker(Masker):
         self.spaces = tokens[1].split("_")
         self.native = capi.Handle(device)
         self.native.set_features(self.n_neighbors, self.spaces)
-        # over-segmentation (:70-75): quickshift runs on the GPU (pcm_quickshift);
-        # felzenszwalb / SLIC have no native implementation yet and use a stand-in provider
+        # over-segmentation (:70-75), SURVEY §8 f-1: quickshift runs on the GPU (pcm_quickshift),
+        # felzenszwalb in the library's host code (pcm_felzenszwalb: inherently sequential); SLIC has
+        # no native implementation and uses a stand-in provider
         self.native_quickshift = segment_fn is None and params["over_segmentation"] == "quickshift"
-        self.segment_fn = segment_fn or (None if self.native_quickshift
+        self.native_felzenszwalb = segment_fn is None and params["over_segmentation"] == "felzenszwalb"
+        self.segment_fn = segment_fn or (None if (self.native_quickshift or self.native_felzenszwalb)
                                          else make_segment_provider(params["over_segmentation"]))
         self._qs_noise_shape = None
         self.prior_fn = prior_fn or SiftPrior()
@@ -159,7 +161,11 @@ class PixelClassificationNonRigidMasker(Masker):
                 priors = self.prior_fn(self.prevFrame, self.prevForegroundMask, crop, segments, n_labels)
             segments = None                    # update() continues from the device-resident map
         else:
-            segments = np.ascontiguousarray(self.segment_fn(crop), np.int32)
+            if self.native_felzenszwalb:
+                # felzenszwalb(crop, scale=100, sigma=0.5, min_size=50) (:73)
+                segments, n_labels = capi.felzenszwalb(frame, (x, y, w, h), scale=100, sigma=0.5, min_size=50)
+            else:
+                segments = np.ascontiguousarray(self.segment_fn(crop), np.int32)
             if want_prior:
                 n_labels = int(segments.max()) + 1
                 priors = self.prior_fn(self.prevFrame, self.prevForegroundMask, crop, segments, n_labels)

@@ -8,13 +8,13 @@ import sys
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.environ.get("PCM_LIB_PATH") or os.path.join(PKG, "libpcm_b200.so")
-SOURCES = ["pcm_api.cu", "pcm_host_simd.cpp"]
-DEPS = ["pcm_api.cu", "pcm_kernels.cuh", "pcm_device.cuh", "pcm_host.h", "pcm_host_simd.cpp", os.path.join("..", "..", "include", "pcm_b200.h")]
+SOURCES = ["pcm_api.cu", "pcm_host_simd.cpp", "pcm_felzenszwalb.cpp"]
+DEPS = ["pcm_api.cu", "pcm_kernels.cuh", "pcm_device.cuh", "pcm_host.h", "pcm_host_simd.cpp", "pcm_felzenszwalb.cpp", "pcm_quickshift.cuh", os.path.join("..", "..", "include", "pcm_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-Xcompiler", "-ffp-contract=off", "-shared",
     "-Xptxas", "-v",
 ]
 

@@ -63,6 +63,7 @@ def load_library():
         "pcm_iou_device": (I, [P, P, L, P, L, I, I, I, P]),
         "pcm_quickshift": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
         "pcm_quickshift_device": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
+        "pcm_felzenszwalb": (I, [P, I, I, L, P, D, D, I, P, I, P, C.POINTER(I)]),
         "pcm_convert": (I, [P, P, I, I, L, I, P, L]),
         "pcm_gather_features": (I, [P, P, I, I, L, P, P]),
         "pcm_set_debug": (I, [P, I]),
@@ -87,7 +88,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_use_own_stream", "pcm_synchronize",
     "pcm_set_features", "pcm_num_features", "pcm_add_model", "pcm_set_novelty", "pcm_num_models", "pcm_crop_rect",
-    "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device",
+    "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device", "pcm_felzenszwalb",
     "pcm_convert", "pcm_gather_features",
     "pcm_set_debug", "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_transfer_bytes", "pcm_set_label_cache", "pcm_profile_enable", "pcm_profile_read",
 ]
@@ -108,6 +109,29 @@ def crop_rect(bbox, frame_h, frame_w):
     if rc:
         raise PcmError(rc, lib.pcm_last_error().decode())
     return tuple(out)
+
+
+def felzenszwalb(frame, rect, scale=100, sigma=0.5, min_size=50):
+    """Felzenszwalb-Huttenlocher segmentation of the crop `rect` (defaults = the reference's call,
+    pixel_classification.py:73).  Host code in the library; returns (labels int32 HxW, n_labels).
+    The Gaussian weights are computed here the way scipy.ndimage does."""
+    lib = load_library()
+    if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3 or frame.strides[2] != 1 or frame.strides[1] != 3:
+        frame = np.ascontiguousarray(frame, np.uint8)
+    r = (C.c_int * 4)(*[int(v) for v in rect])
+    kernel, radius = None, 0
+    if sigma > 0:
+        radius = int(4.0 * float(sigma) + 0.5)
+        x = np.arange(-radius, radius + 1)
+        phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+        kernel = np.ascontiguousarray(phi / phi.sum(), np.float64)
+    out = np.empty((rect[3], rect[2]), np.int32)
+    n = C.c_int(0)
+    rc = lib.pcm_felzenszwalb(_ptr(frame), frame.shape[0], frame.shape[1], frame.strides[0], r, float(scale), float(sigma),
+                              int(min_size), _ptr(kernel), radius, _ptr(out), C.byref(n))
+    if rc:
+        raise PcmError(rc, lib.pcm_last_error().decode())
+    return out, n.value
 
 
 class Handle:

@@ -55,7 +55,8 @@ def make_segment_provider(name, **kw):
         sites = int(name.split(":")[1]) if ":" in name else kw.get("n_sites", 200)
         return lambda crop: voronoi_segments(crop, sites, kw.get("seed", 0))
     if name in ("quickshift", "felzenszwalb", "SLIC"):
-        # 'quickshift' normally never gets here: the masker runs it on the GPU (pcm_quickshift)
+        # 'quickshift' and 'felzenszwalb' normally never get here: the masker runs them natively
+        # (pcm_quickshift on the GPU, pcm_felzenszwalb in the library's host code)
         block = {"quickshift": 6, "felzenszwalb": 10, "SLIC": 12}[name]
         return lambda crop: grid_segments(crop, block)
     raise ValueError("unknown over_segmentation %r" % name)
