@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <numeric>
 #include <vector>
 
@@ -23,34 +24,64 @@ static inline int reflect(int i, int n) {      // scipy 'reflect': d c b a | a b
 }
 
 // out = gaussian along one axis of an h x w x 3 float64 image (centre tap first, then the pairs
-// from the outside in: the summation order of scipy's symmetric correlate1d)
+// from the outside in: the summation order of scipy's symmetric correlate1d).  `idx` maps a
+// position of the padded line [-radius, n + radius) to the reflected source position.
 static void smooth_axis(const std::vector<double>& in, std::vector<double>& out, int h, int w, int axis,
                         const double* k, int radius) {
     const int n = axis == 0 ? h : w;
+    std::vector<int> idx((size_t)n + 2 * radius);
+    for (int p = -radius; p < n + radius; ++p) idx[p + radius] = reflect(p, n);
+    const size_t step = axis == 0 ? (size_t)w * 3 : 3;       // distance between neighbours along the axis
     for (int r = 0; r < h; ++r)
         for (int c = 0; c < w; ++c) {
             const int pos = axis == 0 ? r : c;
-            for (int ch = 0; ch < 3; ++ch) {
-                auto at = [&](int p) { return axis == 0 ? in[((size_t)reflect(p, n) * w + c) * 3 + ch]
-                                                        : in[((size_t)r * w + reflect(p, n)) * 3 + ch]; };
-                double acc = at(pos) * k[radius];
-                for (int j = radius; j >= 1; --j) acc = acc + (at(pos - j) + at(pos + j)) * k[radius - j];
-                out[((size_t)r * w + c) * 3 + ch] = acc;
+            const size_t line0 = axis == 0 ? (size_t)c * 3 : (size_t)r * w * 3;   // element 0 of this line
+            const double* ctr = &in[line0 + (size_t)pos * step];
+            double* o = &out[((size_t)r * w + c) * 3];
+            double a0 = ctr[0] * k[radius], a1 = ctr[1] * k[radius], a2 = ctr[2] * k[radius];
+            for (int j = radius; j >= 1; --j) {
+                const double* lo = &in[line0 + (size_t)idx[pos - j + radius] * step];
+                const double* hi = &in[line0 + (size_t)idx[pos + j + radius] * step];
+                const double wj = k[radius - j];
+                a0 = a0 + (lo[0] + hi[0]) * wj;
+                a1 = a1 + (lo[1] + hi[1]) * wj;
+                a2 = a2 + (lo[2] + hi[2]) * wj;
             }
+            o[0] = a0; o[1] = a1; o[2] = a2;
         }
 }
 
-static int find_root(std::vector<int>& parent, int i) {
-    while (parent[i] != i) i = parent[i];
+// path halving: shortens later searches; the partition (all that matters) is unchanged
+static inline int find_root(std::vector<int>& parent, int i) {
+    while (parent[i] != i) {
+        parent[i] = parent[parent[i]];
+        i = parent[i];
+    }
     return i;
 }
-static void join(std::vector<int>& parent, int n, int m) {
-    const int rn = find_root(parent, n), rm = find_root(parent, m);
+// the smaller root index wins, as in scikit-image's join_trees
+static inline int join(std::vector<int>& parent, int rn, int rm) {
     const int root = rn < rm ? rn : rm;
-    for (int start : {n, m}) {
-        int i = start;
-        while (parent[i] != i) { const int nx = parent[i]; parent[i] = root; i = nx; }
-        parent[i] = root;
+    parent[rn] = root;
+    parent[rm] = root;
+    return root;
+}
+
+struct Edge { double cost; int a, b; };
+
+// stable LSD radix sort by cost: non-negative doubles order like their bit patterns
+static void sort_edges(std::vector<Edge>& e) {
+    std::vector<Edge> tmp(e.size());
+    auto key = [](const Edge& x) { uint64_t u; memcpy(&u, &x.cost, 8); return u; };
+    for (int shift = 0; shift < 64; shift += 11) {
+        size_t count[2049] = {0};
+        for (const Edge& x : e) count[((key(x) >> shift) & 2047) + 1]++;
+        bool single = false;
+        for (int i = 1; i <= 2048; ++i) if (count[i] == e.size()) single = true;
+        if (single) continue;                                   // every key has the same digit here
+        for (int i = 1; i <= 2048; ++i) count[i] += count[i - 1];
+        for (const Edge& x : e) tmp[count[(key(x) >> shift) & 2047]++] = x;
+        e.swap(tmp);
     }
 }
 
@@ -80,7 +111,6 @@ int felzenszwalb(const uint8_t* frame, int64_t stride, int cx, int cy, int w, in
     }
     const double sc = scale / 255.0;
     // edges in scikit-image's order: right, down, down-right, up-right
-    struct Edge { double cost; int a, b; };
     std::vector<Edge> edges;
     edges.reserve(4 * n);
     auto cost = [&](int r0, int c0, int r1, int c1) {
@@ -93,7 +123,7 @@ int felzenszwalb(const uint8_t* frame, int64_t stride, int cx, int cy, int w, in
     for (int r = 1; r < h; ++r) for (int c = 0; c < w; ++c) edges.push_back({cost(r, c, r - 1, c), r * w + c, (r - 1) * w + c});
     for (int r = 1; r < h; ++r) for (int c = 1; c < w; ++c) edges.push_back({cost(r, c, r - 1, c - 1), r * w + c, (r - 1) * w + c - 1});
     for (int r = 1; r < h; ++r) for (int c = 1; c < w; ++c) edges.push_back({cost(r, c - 1, r - 1, c), (r - 1) * w + c, r * w + c - 1});
-    std::stable_sort(edges.begin(), edges.end(), [](const Edge& x, const Edge& y) { return x.cost < y.cost; });
+    sort_edges(edges);
 
     std::vector<int> parent(n), size(n, 1);
     std::vector<double> cint(n, 0.0);
@@ -102,9 +132,9 @@ int felzenszwalb(const uint8_t* frame, int64_t stride, int cx, int cy, int w, in
         const int s0 = find_root(parent, e.a), s1 = find_root(parent, e.b);
         if (s0 == s1) continue;
         if (e.cost < std::min(cint[s0] + sc / size[s0], cint[s1] + sc / size[s1])) {
-            join(parent, s0, s1);
-            const int r = find_root(parent, s0);
-            size[r] = size[s0] + size[s1];
+            const int total = size[s0] + size[s1];
+            const int r = join(parent, s0, s1);
+            size[r] = total;
             cint[r] = e.cost;
         }
     }
@@ -112,9 +142,8 @@ int felzenszwalb(const uint8_t* frame, int64_t stride, int cx, int cy, int w, in
         const int s0 = find_root(parent, e.a), s1 = find_root(parent, e.b);
         if (s0 == s1) continue;
         if (size[s0] < min_size || size[s1] < min_size) {
-            join(parent, s0, s1);
-            const int r = find_root(parent, s0);
-            size[r] = size[s0] + size[s1];
+            const int total = size[s0] + size[s1];
+            size[join(parent, s0, s1)] = total;
         }
     }
     // np.unique(root, return_inverse=True)[1]: rank of the root index

@@ -162,8 +162,16 @@ class PixelClassificationNonRigidMasker(Masker):
             segments = None                    # update() continues from the device-resident map
         else:
             if self.native_felzenszwalb:
-                # felzenszwalb(crop, scale=100, sigma=0.5, min_size=50) (:73)
-                segments, n_labels = capi.felzenszwalb(frame, (x, y, w, h), scale=100, sigma=0.5, min_size=50)
+                # felzenszwalb(crop, scale=100, sigma=0.5, min_size=50) (:73).  In a sweep the label map
+                # of (clip, frame, crop) is the same for every hyper-parameter combination: shared
+                # through the model cache when the caller says the frames are the clip's (cache_tag)
+                def segment():
+                    return capi.felzenszwalb(frame, (x, y, w, h), scale=100, sigma=0.5, min_size=50)
+                cache = self.model_cache if self.cache_tag is not None else None
+                if cache is not None and hasattr(cache, "get_or_compute"):
+                    segments, n_labels = cache.get_or_compute((self.cache_tag, "felzenszwalb", self.index, (x, y, w, h)), segment)
+                else:
+                    segments, n_labels = segment()
             else:
                 segments = np.ascontiguousarray(self.segment_fn(crop), np.int32)
             if want_prior:
