@@ -26,6 +26,9 @@ def test_gather_scatter_strided(tmp_path):
     subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-o", str(so), str(drv),
                     os.path.join(PKG, "csrc", "pcm_host_simd.cpp")], check=True)
     lib = C.CDLL(str(so))
+    lib.t_gather.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]      # addresses are 64-bit
+    lib.t_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+    lib.t_gather.restype = lib.t_scatter.restype = None
     rng = np.random.default_rng(5)
     for stride in (1, 3, 4):
         for n in (0, 1, 15, 16, 17, 18, 33, 48, 100, 1920):
@@ -33,7 +36,7 @@ def test_gather_scatter_strided(tmp_path):
             src = rng.integers(0, 256, max((n - 1) * stride + 1, 1) + 64, dtype=np.uint8)
             src[(n - 1) * stride + 1 if n else 0:] = 0xAB
             dst = np.full(n + 64, 0xCD, np.uint8)
-            lib.t_gather(src.ctypes.data, C.c_int64(stride), dst.ctypes.data, n)
+            lib.t_gather(src.ctypes.data, stride, dst.ctypes.data, n)
             assert np.array_equal(dst[:n], src[:n * stride:stride][:n]), (stride, n)
             assert (dst[n:] == 0xCD).all(), "gather wrote past the end"
             plane = rng.integers(0, 256, n + 8, dtype=np.uint8)
@@ -41,5 +44,5 @@ def test_gather_scatter_strided(tmp_path):
             want = img.copy()
             if n:
                 want[:(n - 1) * stride + 1:stride] = plane[:n]
-            lib.t_scatter(plane.ctypes.data, img.ctypes.data, C.c_int64(stride), n)
+            lib.t_scatter(plane.ctypes.data, img.ctypes.data, stride, n)
             assert np.array_equal(img, want), (stride, n)
