@@ -145,6 +145,12 @@ class PixelClassificationNonRigidMasker(Masker):
         cur = self.current_model
 
         want_prior = self.index != 0 and params["prior_weight"] != 0.0
+
+        def prior(segs, n):
+            if isinstance(self.prior_fn, SiftPrior) and self.cache_tag is not None:
+                return self.prior_fn(self.prevFrame, self.prevForegroundMask, crop, segs, n, cache=self.model_cache,
+                                     key=(self.cache_tag, self.index, (x, y, w, h)))
+            return self.prior_fn(self.prevFrame, self.prevForegroundMask, crop, segs, n)
         n_labels, priors = 0, None             # 0: the library takes max(label) + 1 while staging
         if self.native_quickshift:
             # quickshift(crop, kernel_size=3, max_dist=6, ratio=0.5, random_seed=42) (:71); the label
@@ -158,7 +164,7 @@ class PixelClassificationNonRigidMasker(Masker):
             segments, n_labels = self.native.quickshift(frame, (x, y, w, h), ratio=0.5, kernel_size=3, max_dist=6,
                                                         noise=noise, want_labels=want_prior)
             if want_prior:
-                priors = self.prior_fn(self.prevFrame, self.prevForegroundMask, crop, segments, n_labels)
+                priors = prior(segments, n_labels)
             segments = None                    # update() continues from the device-resident map
         else:
             if self.native_felzenszwalb:
@@ -176,7 +182,7 @@ class PixelClassificationNonRigidMasker(Masker):
                 segments = np.ascontiguousarray(self.segment_fn(crop), np.int32)
             if want_prior:
                 n_labels = int(segments.max()) + 1
-                priors = self.prior_fn(self.prevFrame, self.prevForegroundMask, crop, segments, n_labels)
+                priors = prior(segments, n_labels)
 
         blend = bool(self.multi_selection) and len(self.models) > cur + 1
         w_cur, w_next = 1.0, 0.0

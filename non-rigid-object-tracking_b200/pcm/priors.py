@@ -27,8 +27,11 @@ class SiftPrior:
     def _pts(kps):
         return np.array([k.pt for k in kps], np.float32).reshape(-1, 2)
 
-    def features(self, prev_crop, prev_mask, crop):
-        """(pts1, des1) of the previous crop inside prev_mask, (pts2, des2) of the current crop."""
+    def features(self, prev_crop, prev_mask, crop, cache=None, key=None):
+        """(pts1, des1) of the previous crop inside prev_mask, (pts2, des2) of the current crop.
+        `cache` / `key`: a sweep's shared cache (get_or_compute) and an identifier of the current
+        crop (clip, frame, rectangle) -- its unmasked SIFT result is the same for every
+        hyper-parameter combination of the sweep."""
         if self.reuse and self._last is not None and self._last[0] is prev_crop:
             pts, des = self._last[1], self._last[2]
             if len(pts):
@@ -42,16 +45,21 @@ class SiftPrior:
         else:
             kp1, des1 = self.sift.detectAndCompute(np.ascontiguousarray(prev_crop), np.ascontiguousarray(prev_mask))
             pts1 = self._pts(kp1)
-        kp2, des2 = self.sift.detectAndCompute(np.ascontiguousarray(crop), None)
-        pts2 = self._pts(kp2)
+        def detect():
+            kp2, des2 = self.sift.detectAndCompute(np.ascontiguousarray(crop), None)
+            return self._pts(kp2), des2
+        if cache is not None and key is not None and hasattr(cache, "get_or_compute"):
+            pts2, des2 = cache.get_or_compute(("sift",) + tuple(key), detect)
+        else:
+            pts2, des2 = detect()
         self._last = (crop, pts2, des2)
         return pts1, des1, pts2, des2
 
-    def __call__(self, prev_crop, prev_mask, crop, segments, n_labels):
+    def __call__(self, prev_crop, prev_mask, crop, segments, n_labels, cache=None, key=None):
         priors = np.full(n_labels, -1, np.float32)
         if prev_crop is None or prev_mask is None:
             return priors
-        pts1, des1, pts2, des2 = self.features(prev_crop, prev_mask, crop)
+        pts1, des1, pts2, des2 = self.features(prev_crop, prev_mask, crop, cache, key)
         if len(pts1) == 0 or len(pts2) < 2:
             return priors
         good = [m for m, n in (pair for pair in self.flann.knnMatch(des1, des2, k=2) if len(pair) == 2)
