@@ -62,6 +62,10 @@ SEQUENCES = {
         video="parachute", multi_selection=True, segments="voronoi:120", n_frames=24, dump=[0, 5, 16, 20],
         params=dict(n_estimators=30, max_depth=10, n_components=1, novelty_detection=True,
                     over_segmentation="felzenszwalb", features="6 lab", dilation_kernel=7, prior_weight=0.0)),
+    "frog_sweep": dict(
+        video="frog", multi_selection=True, segments="voronoi:150", n_frames=14, dump=[0, 9],
+        params=dict(n_estimators=30, max_depth=7, n_components=1, novelty_detection=True,
+                    over_segmentation="felzenszwalb", features="8 hsv_lab", dilation_kernel=7, prior_weight=0.0)),
     "worm_rgb3": dict(
         video="worm", multi_selection=False, segments="grid:5", n_frames=6, dump=[0, 3],
         params=dict(n_estimators=8, max_depth=7, n_components=1, novelty_detection=False,

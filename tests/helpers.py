@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "non-rigid-object-tracking_b200")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-SEQ_NAMES = ["soldier_default", "parachute_novelty", "worm_rgb3"]
+SEQ_NAMES = ["soldier_default", "parachute_novelty", "worm_rgb3", "frog_sweep"]
 
 
 def sha1(a):
