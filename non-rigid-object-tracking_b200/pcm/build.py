@@ -38,8 +38,9 @@ def build(force=False, verbose=False):
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed (%d): %s" % (res.returncode, " ".join(cmd)))
-    with open(os.path.join(PKG, "csrc", "ptxas_info.txt"), "w") as f:
-        f.write(res.stderr)
+    if LIB.endswith("libpcm_b200.so"):       # registers / spills / shared memory per kernel (ptxas -v), without timings
+        with open(os.path.join(PKG, "csrc", "ptxas_info.txt"), "w") as f:
+            f.write("".join(l for l in res.stderr.splitlines(True) if "Compile time" not in l))
     return LIB
 
 
