@@ -140,3 +140,48 @@ def test_model_cache_computes_once_under_threads():
         t.join()
     assert len(calls) == 1 and all(o is out[0] for o in out)
     assert cache.get_or_compute(("k", 2), make) is not out[0] and len(calls) == 2
+
+
+def _run_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from pcm import sequence, sweep
+
+    def fake_run_sequence(cfg, device=0, model_cache=None, cache_tag=None, max_frames=None, **kw):
+        # stands in for the GPU work of one sequence: a score that depends on the config only
+        p = cfg["params"]
+        iou = 0.5 + 0.001 * p["n_estimators"] + 0.01 * p["max_depth"] + (0.05 if "frog" in cfg["input_video"] else 0.0)
+        return dict(mean_iou=iou, seconds=0.25, train_seconds=0.0, decode_seconds=0.0, wall_seconds=0.25)
+    sequence.run_sequence = fake_run_sequence
+    hyper = dict(n_estimators=[20, 30], max_depth=[7, 10], features=["6 lab"], prior_weight=[0.0])
+    summary, table = sweep.run({"masker": "PC"}, {"soldier": {}, "frog": {}}, videos=["soldier", "frog"], hyper=hyper,
+                               backend="gloo", seq_workers=2)
+    q.put((rank, summary, None if table is None else table.to_dict()))
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sweep_run_world_size_2_gloo_end_to_end():
+    """sweep.run() with two ranks over gloo (sequence work stubbed out): sharding, the sequence
+    threads, the single gather, the max-over-ranks time and rank 0's results table."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_run_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict((g[0], g[1:]) for g in [q.get(timeout=180) for _ in procs])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    s0, t0 = got[0]
+    s1, t1 = got[1]
+    assert t1 is None and t0 is not None                      # the table lives on rank 0
+    assert s0["n_sequences"] == 8 and s0["n_gpus"] == 2 and sum(s0["per_rank_sequences"]) == 8
+    assert s0["seconds"] == s1["seconds"] > 0                 # max over ranks, the same on both
+    assert t0["soldier_benchmark"][0] == pytest.approx(0.5 + 0.02 + 0.07)
+    assert t0["frog_benchmark"][3] == pytest.approx(0.5 + 0.03 + 0.10 + 0.05)
+    assert t0["avg_benchmark"][0] == pytest.approx((0.59 + 0.64) / 2)
+    assert all(v == 0.25 for v in t0["frog_time"].values())
