@@ -144,9 +144,8 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
 
     // 4 pixels = 12 bytes: three aligned words when possible, byte loads otherwise.  The words of
     // the thread's NEXT group are requested before the current group is converted.
-    auto fetch = [&](int i, uint32_t (&w3)[3]) {
-        const int r = i / groups_per_row;
-        const int c0 = (i - r * groups_per_row) * 4;
+    auto fetch = [&](int r, int g, uint32_t (&w3)[3]) {      // group g of crop row r
+        const int c0 = g * 4;
         const uint8_t* src = a.frame + (long long)(a.cy + r) * a.stride + (long long)(a.cx + c0) * 3;
         w3[0] = w3[1] = w3[2] = 0u;
         if (c0 + 3 < a.cw && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
@@ -158,14 +157,19 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
                 if (c0 + q / 3 < a.cw) w3[q / 4] |= (uint32_t)__ldg(src + q) << (8 * (q % 4));
         }
     };
+    // (row, group) of the thread's current and next group advance by a constant (dr, dg) per
+    // iteration: no integer division in the loop
     const int stride = gridDim.x * blockDim.x;
+    const int dr = stride / groups_per_row, dg = stride - dr * groups_per_row;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = i / groups_per_row, g = i - r * groups_per_row;
+    int rn = r + dr, gn = g + dg;
+    if (gn >= groups_per_row) { gn -= groups_per_row; ++rn; }
     uint32_t w3[3], nx[3] = {0u, 0u, 0u};
-    if (i < n_groups) fetch(i, w3);
+    if (i < n_groups) fetch(r, g, w3);
     for (; i < n_groups; i += stride) {
-        if (i + stride < n_groups) fetch(i + stride, nx);
-        const int r = i / groups_per_row;
-        const int c0 = (i - r * groups_per_row) * 4;
+        if (i + stride < n_groups) fetch(rn, gn, nx);
+        const int c0 = g * 4;
         uint32_t out[NOUT];
 #pragma unroll
         for (int p = 0; p < NOUT; ++p) out[p] = 0;
@@ -210,6 +214,9 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
             }
         }
         w3[0] = nx[0]; w3[1] = nx[1]; w3[2] = nx[2];
+        r = rn; g = gn;
+        rn += dr; gn += dg;
+        if (gn >= groups_per_row) { gn -= groups_per_row; ++rn; }
     }
 }
 
