@@ -506,7 +506,10 @@ __device__ __forceinline__ double blend2(double a, double b, double w0, double w
 // Tile buffers per CTA: 2 = the TMA load of tile i+1 overlaps the scoring of tile i (u8 tiles);
 // 1 = the twice as large 2-byte tiles, single-buffered so that two CTAs still fit an SM -- the
 // co-resident CTA scores while this one waits for its tile.
-__host__ __device__ constexpr int tile_buffers(int es) { return es == 2 ? 1 : 2; }
+#ifndef PCM_U8_TILE_BUFS
+#define PCM_U8_TILE_BUFS 2          // tuning experiments: 1 = single-buffered u8 tiles
+#endif
+__host__ __device__ constexpr int tile_buffers(int es) { return es == 2 ? 1 : PCM_U8_TILE_BUFS; }
 
 struct ScoreSmem {
     uint32_t tiles, bars, sched, sp, f0_nodes, f0_leaves, f0_trees, f1_nodes, f1_leaves, f1_trees, pca0, pca1, total;
