@@ -234,7 +234,8 @@ int pcm_transfer_bytes(const pcm_handle* h, int64_t out[2]);
 
 /* Per-kernel device timing (CUDA events on the handle's stream around every
  * launch while enabled).  Kernel ids: 0 score (fused star features + forests),
- * 1 segment_reduce, 2 segment_decide, 3 segment_resolve, 4 mask_dilate, 5 iou,
+ * 1 (retired: the per-label reduction is K1's epilogue), 2 segment_decide, 3 (retired: the exact
+ * re-evaluation is part of segment_decide), 4 mask_dilate, 5 iou,
  * 6 planes (colour conversion to planar tiles).
  * pcm_profile_read synchronises the stream, adds the finished launches to the
  * running totals and returns them (ms_sum[i], count[i] for i < n <= PCM_NUM_KERNELS);

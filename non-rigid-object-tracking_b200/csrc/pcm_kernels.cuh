@@ -250,11 +250,6 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t a) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
-__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
 __device__ __forceinline__ NodeT lds_node(uint32_t a) { return lds_v2(a); }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
     uint32_t v;
