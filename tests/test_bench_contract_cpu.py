@@ -1,0 +1,48 @@
+"""bench.py's contract where it can be checked without a GPU: the reference arm (CPU port on host
+cores) prints exactly one JSON line with the agreed keys; the default arm refuses to run without
+a CUDA device instead of falling back to anything."""
+import json
+import os
+import subprocess
+import sys
+
+from helpers import ROOT
+
+
+def test_sequence_state_follows_the_reference_schedule():
+    sys.path.insert(0, ROOT)
+    import bench
+    mf = [0, 100, 200]
+    assert bench.sequence_state(0, mf) == (0, 1, 1.0, 0.0)
+    cur, nxt, w0, w1 = bench.sequence_state(150, mf)
+    assert (cur, nxt) == (1, 2) and abs(w0 - 0.5) < 1e-12 and abs(w1 - 0.5) < 1e-12     # :84-87
+    assert bench.sequence_state(100, mf)[:2] == (1, 2)                                   # switch at n_frame (:117)
+    assert bench.sequence_state(250, mf) == (2, -1, 1.0, 0.0)                            # last model: no blend
+    w, h = bench.sample_dims(33000)
+    assert w % 16 == 0 and h % 16 == 0 and 16384 <= w * h <= 40000
+
+
+def test_reference_arm_prints_one_json_line():
+    env = dict(os.environ, PCM_REF_CORES="2")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout[-1000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "PC masker frames/sec at 1080p" and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 2 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_default_arm_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                         timeout=300, cwd=ROOT)
+    assert res.returncode != 0 and "no CUDA device" in (res.stderr + res.stdout)
+    assert not res.stdout.strip(), "nothing may be reported without a GPU"
