@@ -18,6 +18,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <string>
+#include <utility>
 #include <vector>
 
 using namespace pcm;
@@ -275,6 +276,33 @@ static bool debug_sync_enabled() {
                 return fail(PCM_E_CUDA, "kernel %s faulted: %s", name, cudaGetErrorString(e2__)); \
         }                                                                                       \
     } while (0)
+
+// ---------------------------------------------------------------------------------
+// Programmatic dependent launch: the five kernels of a frame run back to back on one stream.
+// Launched with this attribute a kernel's CTAs may become resident while the previous kernel
+// drains; each kernel executes `griddepcontrol.wait` (grid_dependency_wait) before it touches
+// anything its predecessor wrote -- K1 only after it has staged its forests -- so the launch
+// latency and K1's prologue overlap the predecessor's tail.  PCM_PDL=0 switches it off.
+// ---------------------------------------------------------------------------------
+static bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PCM_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---------------------------------------------------------------------------------
 // per-kernel timing
@@ -775,7 +803,7 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
         static const PlanesFn table[3][2] = {{planes_kernel<0, false>, planes_kernel<0, true>},
                                              {planes_kernel<1, false>, planes_kernel<1, true>},
                                              {planes_kernel<2, false>, planes_kernel<2, true>}};
-        table[mode][g.es == 2]<<<std::max(blocks, 1), 256, 0, st>>>(pa);
+        CUDA_TRY(launch_chain(table[mode][g.es == 2], dim3(std::max(blocks, 1)), dim3(256), 0, st, pa));
     }
     CHECK_LAUNCH(h, "planes_kernel");
 
@@ -836,7 +864,7 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     const int grid = std::min(n_tiles, h->sm_count * occ);
     {
         KernelTimer kt(h, 0);
-        sv.fn<<<grid, NTHREADS, ls.total, st>>>(tmap, a);
+        CUDA_TRY(launch_chain(sv.fn, dim3(grid), dim3(NTHREADS), ls.total, st, tmap, a));
     }
     CHECK_LAUNCH(h, sv.name);
 
@@ -852,7 +880,7 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     da.n_flagged = reinterpret_cast<int*>(seg + sl.nflag);
     {
         KernelTimer kt(h, 2);
-        segment_decide_kernel<<<(S + 255) / 256, 256, 0, st>>>(da);
+        CUDA_TRY(launch_chain(segment_decide_kernel, dim3((S + 255) / 256), dim3(256), 0, st, da));
     }
     CHECK_LAUNCH(h, "segment_decide_kernel");
 
@@ -876,7 +904,7 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
              {mask_dilate_kernel<false, true, 0>, mask_dilate_kernel<false, true, 7>}},
             {{mask_dilate_kernel<true, false, 0>, mask_dilate_kernel<true, false, 7>},
              {mask_dilate_kernel<true, true, 0>, mask_dilate_kernel<true, true, 7>}}};
-        table[vec][dl.pre != nullptr][dl.k == 7]<<<dg, 256, 0, st>>>(dl);
+        CUDA_TRY(launch_chain(table[vec][dl.pre != nullptr][dl.k == 7], dg, dim3(256), 0, st, dl));
     }
     CHECK_LAUNCH(h, "mask_dilate_kernel");
 
@@ -1072,9 +1100,9 @@ extern "C" int pcm_iou_device(pcm_handle* h, const uint8_t* d_mask, int64_t mask
     const int blocks = (int)std::min<long long>((work + 255) / 256, (long long)h->sm_count * 8);
     {
         KernelTimer kt(h, 5);
-        iou_kernel<<<std::max(blocks, 1), 256, 0, h->stream>>>(d_mask, mask_row_stride, d_truth, truth_row_stride,
-                                                              truth_channels, height, width,
-                                                              reinterpret_cast<unsigned long long*>(d_counts));
+        CUDA_TRY(launch_chain(iou_kernel, dim3(std::max(blocks, 1)), dim3(256), 0, h->stream, d_mask, (long long)mask_row_stride,
+                              d_truth, (long long)truth_row_stride, truth_channels, height, width,
+                              reinterpret_cast<unsigned long long*>(d_counts)));
     }
     CUDA_TRY(cudaGetLastError());
     h->launches++;

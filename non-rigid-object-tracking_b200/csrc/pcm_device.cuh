@@ -75,6 +75,13 @@ __host__ __device__ inline void star_tap(int k, int& dr, int& dc) {
     }
 }
 
+// Programmatic dependent launch: returns once the preceding kernel of the stream has completed and
+// its writes are visible (a no-op for a kernel launched without the attribute).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the NEXT kernel of the stream start once every CTA of this grid has got here: its CTAs take
+// the slots this grid frees, run whatever precedes their own grid_dependency_wait(), and wait.
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- BGR -> HSV (OpenCV RGB2HSV_b, hrange 180) ----------------------------------
 __device__ __forceinline__ void bgr2hsv_px(int b, int g, int r, const int32_t* __restrict__ sdiv,
                                            const int32_t* __restrict__ hdiv, int& H, int& S, int& V) {

@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
     __shared__ ColorTables tab;
     for (int i = threadIdx.x; i < (int)(sizeof(ColorTables) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&tab)[i] = reinterpret_cast<const uint32_t*>(a.tables)[i];
+    grid_dependency_wait();     // everything below overwrites buffers the previous frame's kernels used
+    grid_launch_dependents();
     if (blockIdx.x == 0 && threadIdx.x == 0) { *a.tile_counter = 0; *a.n_flagged = 0; *a.err = 0; }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_labels; i += gridDim.x * blockDim.x) {
         a.sum[i] = 0.0; a.asum[i] = 0.0; a.area[i] = 0; a.rmin[i] = 0x7fffffff; a.rmax[i] = -1;
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
 }
 
 // ---- PTX helpers: mbarrier, TMA tile load, shared-memory loads --------------------------
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -588,14 +591,8 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
         }
     };
 
-    if (tid == 0) {
-        for (int b = 0; b < N_TILE_BUF; ++b) mbar_init(bars_s + 8 * b, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (N_TILE_BUF > 1) issue(0);
-    }
-
-    // ---- once per CTA: tap offsets, forests, PCA vectors -> smem (overlaps the first TMA) ----
+    // ---- once per CTA: tap offsets, forests, PCA vectors -> smem.  None of it depends on the
+    //      preceding kernel (K0), so under programmatic dependent launch it overlaps K0's tail ----
     for (int k = tid; k < g.K; k += NTHREADS) {
         int dr, dc;
         star_tap(k, dr, dc);
@@ -628,6 +625,15 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
             p1c = d1; p1c255 = d1 + g.F; p1m = d1 + 2 * g.F;
         }
     }
+    grid_dependency_wait();     // K0's planes, tile counter and per-label resets are complete and visible
+    grid_launch_dependents();
+    if (tid == 0) {
+        for (int b = 0; b < N_TILE_BUF; ++b) mbar_init(bars_s + 8 * b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (N_TILE_BUF > 1) issue(0);
+    }
+
     __syncthreads();
 
     const uint32_t f0n_s = smem_u32(smem + L.f0_nodes), f0l_s = smem_u32(smem + L.f0_leaves);
@@ -754,6 +760,8 @@ struct DecideArgs {
 };
 
 __global__ void __launch_bounds__(256) segment_decide_kernel(const DecideArgs a) {
+    grid_dependency_wait();
+    grid_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const double w = a.prior_weight;
@@ -836,6 +844,8 @@ template <bool VEC, bool PRE, int KF>
 __global__ void __launch_bounds__(256) mask_dilate_kernel(const DilateArgs a) {
     __shared__ __align__(16) uint8_t s0[DIL_SH_MAX * DIL_PITCH];
     __shared__ __align__(16) uint8_t s1[DIL_SH_MAX * DIL_TW];
+    grid_dependency_wait();
+    grid_launch_dependents();
     const int k = KF > 0 ? KF : a.k, before = k / 2, after = k - 1 - before, SH = DIL_TH + k - 1;
     const int pad = (4 - (before & 3)) & 3;         // s0 column of tile column x is x - tx0 + before + pad
     const int tx0 = blockIdx.x * DIL_TW, ty0 = blockIdx.y * DIL_TH;
@@ -947,6 +957,8 @@ __global__ void __launch_bounds__(256) iou_kernel(const uint8_t* __restrict__ ma
                                                   const uint8_t* __restrict__ truth, long long truth_stride,
                                                   int truth_channels, int h, int w,
                                                   unsigned long long* __restrict__ counts) {
+    grid_dependency_wait();
+    grid_launch_dependents();
     unsigned inter = 0, uni = 0;
     const bool vec = truth_channels == 1 && (w % 16 == 0) && (mask_stride % 16 == 0) && (truth_stride % 16 == 0) &&
                      ((reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(truth)) & 15) == 0;
