@@ -104,7 +104,11 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
     __shared__ ColorTables tab;
     for (int i = threadIdx.x; i < (int)(sizeof(ColorTables) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&tab)[i] = reinterpret_cast<const uint32_t*>(a.tables)[i];
-    grid_dependency_wait();     // everything below overwrites buffers the previous frame's kernels used
+    // Programmatic dependent launch: K0 does NOT wait for its predecessor before it works.  It can only
+    // have been started by a mask_dilate / iou kernel that is already running, i.e. after the previous
+    // frame's K2 has completed (K3 releases its dependents after its own wait, K5 at its very start), and
+    // nothing K0 writes (planes, per-label accumulators, tile counter) is touched by K3 or K5.  It waits
+    // at its END instead, so that "K0 complete" still implies "everything before K0 complete" for K1.
     grid_launch_dependents();
     if (blockIdx.x == 0 && threadIdx.x == 0) { *a.tile_counter = 0; *a.n_flagged = 0; *a.err = 0; }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_labels; i += gridDim.x * blockDim.x) {
@@ -220,6 +224,7 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
         rn += dr; gn += dg;
         if (gn >= groups_per_row) { gn -= groups_per_row; ++rn; }
     }
+    grid_dependency_wait();
 }
 
 // ---- PTX helpers: mbarrier, TMA tile load, shared-memory loads --------------------------
@@ -957,8 +962,8 @@ __global__ void __launch_bounds__(256) iou_kernel(const uint8_t* __restrict__ ma
                                                   const uint8_t* __restrict__ truth, long long truth_stride,
                                                   int truth_channels, int h, int w,
                                                   unsigned long long* __restrict__ counts) {
+    grid_launch_dependents();   // the next frame's K0 may start now: it touches nothing K3 or this kernel uses
     grid_dependency_wait();
-    grid_launch_dependents();
     unsigned inter = 0, uni = 0;
     const bool vec = truth_channels == 1 && (w % 16 == 0) && (mask_stride % 16 == 0) && (truth_stride % 16 == 0) &&
                      ((reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(truth)) & 15) == 0;
