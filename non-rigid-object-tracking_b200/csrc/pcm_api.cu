@@ -585,6 +585,7 @@ extern "C" int pcm_use_own_stream(pcm_handle* h) {
 
 static int check_label_error(pcm_handle* h, bool sync) {
     if (!h->seg.p || !h->last_valid) return PCM_OK;
+    CUDA_TRY(h->h_small.reserve(64));      // the device-pointer entry points never touch the pinned scratch
     int* hs = h->h_small.as<int>();
     const SegLayout l = seg_layout(h->last_S);
     CUDA_TRY(cudaMemcpyAsync(hs, h->seg.as<char>() + l.err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));

@@ -546,3 +546,63 @@ def test_fuzz_geometry_forest_labels(seed):
     out[y:y + hh, x:x + w, 2] = 0
     assert not out.any(), "wrote outside the crop or outside channel 2"
     h.close()
+
+
+_PDL_SCRIPT = r'''
+import hashlib, sys
+sys.path[:0] = [%r, %r, %r]
+import numpy as np, torch
+from pcm import capi
+from pcm.providers import voronoi_segments
+from test_gpu_parity import _random_forest_arrays
+rng = np.random.default_rng(5)
+H, W, n, spaces = 360, 640, 8, ["hsv", "lab"]
+F = 3 * (1 + 8 * n) * len(spaces)
+frames = rng.integers(0, 256, (6, H, W, 3), dtype=np.uint8)
+truth = (rng.random((6, H, W)) < 0.3).astype(np.uint8) * 255
+h = capi.Handle(0)
+h.set_features(n, spaces)
+h.add_model_arrays(0, _random_forest_arrays(rng, 20, 5, F))
+h.add_model_arrays(9, _random_forest_arrays(rng, 20, 5, F))
+rect = (0, 0, W, H)
+seg = voronoi_segments(frames[0], 300, 1)
+S = int(seg.max()) + 1
+dev = torch.device("cuda", 0)
+d_frames, d_truth, d_seg = torch.from_numpy(frames).to(dev), torch.from_numpy(truth).to(dev), torch.from_numpy(seg).to(dev)
+d_mask = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+d_counts = torch.zeros((60, 2), dtype=torch.int64, device=dev)
+torch.cuda.synchronize()
+h.set_stream(torch.cuda.current_stream().cuda_stream)
+digest = hashlib.sha1()
+for s in range(60):                      # back to back, no synchronisation between frames
+    f = s %% 6
+    prm = capi.Handle.make_params(0, 1, 1 - s / 60, s / 60, dilation_kernel=7)
+    h.update_device(d_frames[f].data_ptr(), H, W, W * 3, rect, d_seg.data_ptr(), S, 0, prm, d_mask.data_ptr(), W)
+    h.iou_device(d_mask.data_ptr(), W, d_truth[f].data_ptr(), W, 1, H, W, d_counts[s].data_ptr())
+    if s %% 7 == 0:
+        h.synchronize()
+        digest.update(d_mask.cpu().numpy().tobytes())
+h.synchronize()
+digest.update(d_counts.cpu().numpy().tobytes())
+print("DIGEST", digest.hexdigest(), int(d_counts[:, 1].min()))
+'''
+
+
+def test_dependent_launch_chain_changes_nothing():
+    """The per-frame kernels overlap under programmatic dependent launch (the next frame's K0 runs
+    under the previous frame's K3/K5): 60 back-to-back frames on the device path give bit-identical
+    masks and IoU counts with PCM_PDL=1 and PCM_PDL=0."""
+    import subprocess
+    import sys
+    from helpers import PKG
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = {}
+    for pdl in ("1", "0"):
+        res = subprocess.run([sys.executable, "-c", _PDL_SCRIPT % (PKG, here, os.path.join(os.path.dirname(here), "oracle"))],
+                             env=dict(os.environ, PCM_PDL=pdl),
+                             capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        line = [l for l in res.stdout.splitlines() if l.startswith("DIGEST")][0].split()
+        out[pdl] = line[1]
+        assert int(line[2]) > 0, "empty union: the test frames must produce masks"
+    assert out["1"] == out["0"]
