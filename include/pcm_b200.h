@@ -60,6 +60,10 @@ void pcm_destroy(pcm_handle* h);
  * pcm_use_own_stream switches back. */
 int pcm_set_stream(pcm_handle* h, void* cuda_stream);
 int pcm_use_own_stream(pcm_handle* h);
+/* The stream work is currently enqueued on (cudaStream_t as void*), e.g. to record timing events on the
+ * handle's private stream from another runtime. */
+int pcm_get_stream(const pcm_handle* h, void** cuda_stream_out);
+/* Waits for the stream; reports (once) an out-of-range label met by ANY update queued since the last check. */
 int pcm_synchronize(pcm_handle* h);
 
 /* ---- configuration (config.yaml `params.features`, :300-308) ---------- */

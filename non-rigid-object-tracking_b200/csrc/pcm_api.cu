@@ -198,6 +198,10 @@ struct pcm_handle {
     cudaStream_t stream = nullptr;
     ColorTables* d_tables = nullptr;
     ColorTables h_tables;
+    int* d_err = nullptr;         // sticky "label out of range" word: set by K1, cleared by the host once reported
+    // true while the last thing this handle queued on its PRIVATE stream is its own K3 / K5: only then may
+    // the next K0 start before its predecessor has finished (PlanesArgs::early)
+    bool chain_tail = false;
     PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;   // driver entry point (no libcuda link)
     bool features_set = false;
     Geom geom{};
@@ -243,9 +247,9 @@ struct pcm_handle {
     HostTrace trace;
 };
 
-// seg buffer layout: [sum S f64][asum S f64][area S i32][n_flagged i32][err i32]
+// seg buffer layout: [sum S f64][asum S f64][area S i32][n_flagged i32]
 struct SegLayout {
-    size_t sum, asum, area, nflag, err, total;
+    size_t sum, asum, area, nflag, total;
 };
 static SegLayout seg_layout(int S) {
     SegLayout l;
@@ -254,8 +258,7 @@ static SegLayout seg_layout(int S) {
     l.area = l.asum + sizeof(double) * (size_t)S;
     l.nflag = l.area + sizeof(int) * (size_t)S;
     l.nflag = (l.nflag + 7) / 8 * 8;
-    l.err = l.nflag + sizeof(int);
-    l.total = l.err + sizeof(int);
+    l.total = l.nflag + 2 * sizeof(int);
     return l;
 }
 
@@ -543,6 +546,8 @@ extern "C" int pcm_create(int device, pcm_handle** out) {
     build_tables(h->h_tables);
     CUDA_TRY(cudaMalloc(&h->d_tables, sizeof(ColorTables)));
     CUDA_TRY(cudaMemcpy(h->d_tables, &h->h_tables, sizeof(ColorTables), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&h->d_err, sizeof(int)));
+    CUDA_TRY(cudaMemset(h->d_err, 0, sizeof(int)));
     for (int i = 0; i < N_SCORE_VARIANTS; ++i)
         CUDA_TRY(cudaFuncSetAttribute(score_variant(i).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
     CUDA_TRY(cudaFuncSetAttribute(qs_window_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
@@ -567,6 +572,7 @@ extern "C" void pcm_destroy(pcm_handle* h) {
     for (auto& t : h->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : h->free_events) cudaEventDestroy(e);
     if (h->d_tables) cudaFree(h->d_tables);
+    if (h->d_err) cudaFree(h->d_err);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -574,31 +580,42 @@ extern "C" void pcm_destroy(pcm_handle* h) {
 extern "C" int pcm_set_stream(pcm_handle* h, void* cuda_stream) {
     if (!h) return fail(PCM_E_INVALID, "pcm_set_stream: NULL handle");
     h->stream = static_cast<cudaStream_t>(cuda_stream);
+    h->chain_tail = false;
     return PCM_OK;
 }
 
 extern "C" int pcm_use_own_stream(pcm_handle* h) {
     if (!h) return fail(PCM_E_INVALID, "pcm_use_own_stream: NULL handle");
     h->stream = h->own_stream;
+    h->chain_tail = false;
     return PCM_OK;
 }
 
-static int check_label_error(pcm_handle* h, bool sync) {
-    if (!h->seg.p || !h->last_valid) return PCM_OK;
+extern "C" int pcm_get_stream(const pcm_handle* h, void** out) {
+    if (!h || !out) return fail(PCM_E_INVALID, "pcm_get_stream: NULL argument");
+    *out = static_cast<void*>(h->stream);
+    return PCM_OK;
+}
+
+// The error word is sticky on the device (no kernel clears it): an out-of-range label in ANY frame queued
+// since the last check is reported here, then the word is cleared.
+static int check_label_error(pcm_handle* h) {
     CUDA_TRY(h->h_small.reserve(64));      // the device-pointer entry points never touch the pinned scratch
     int* hs = h->h_small.as<int>();
-    const SegLayout l = seg_layout(h->last_S);
-    CUDA_TRY(cudaMemcpyAsync(hs, h->seg.as<char>() + l.err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    if (sync) CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (*hs) return fail(PCM_E_LABEL, "label outside [0, n_labels) in the label map");
+    CUDA_TRY(cudaMemcpyAsync(hs, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->chain_tail = false;
+    if (*hs) {
+        CUDA_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
+        return fail(PCM_E_LABEL, "label outside [0, n_labels) in the label map");
+    }
     return PCM_OK;
 }
 
 extern "C" int pcm_synchronize(pcm_handle* h) {
     if (!h) return fail(PCM_E_INVALID, "pcm_synchronize: NULL handle");
     CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return check_label_error(h, true);
+    return check_label_error(h);
 }
 
 // ---------------------------------------------------------------------------------
@@ -790,7 +807,7 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     pa.rmin = h->rmin.as<int>();
     pa.rmax = h->rmax.as<int>();
     pa.n_flagged = reinterpret_cast<int*>(seg + sl.nflag);
-    pa.err = reinterpret_cast<int*>(seg + sl.err);
+    pa.early = (pdl_enabled() && st == h->own_stream && h->chain_tail) ? 1 : 0;
     {
         // persistent blocks: the 6.6 KB of lookup tables are staged once per block, so a block
         // should convert many pixel groups
@@ -849,7 +866,7 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     a.seg.n_labels = S;
     a.seg.thr = p->outlier_threshold;
     a.seg.sum = pa.sum; a.seg.asum = pa.asum; a.seg.area = pa.area;
-    a.seg.rmin = pa.rmin; a.seg.rmax = pa.rmax; a.seg.err = pa.err;
+    a.seg.rmin = pa.rmin; a.seg.rmax = pa.rmax; a.seg.err = h->d_err;
 
     // forests live in shared memory whenever one CTA's tiles + forests fit, else they are read through L1
     ScoreSmem ls = score_smem_layout(a.g, a.f0, a.f1, a.blend, a.novelty, true);
@@ -913,6 +930,7 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     h->last_novelty = a.novelty;
     h->last_valid = true;
     h->last_pre = want_pre;
+    h->chain_tail = true;
     return PCM_OK;
 }
 
@@ -923,7 +941,7 @@ static int finish_host_update(pcm_handle* h, const int rect[4], uint8_t* mask, i
     cudaStream_t st = h->stream;
     CUDA_TRY(cudaMemcpyAsync(h->h_mask.p, h->mask.p, npx, cudaMemcpyDeviceToHost, st));
     h->bytes_d2h += (int64_t)npx + (int64_t)sizeof(int);
-    int rc = check_label_error(h, true);
+    int rc = check_label_error(h);
     if (rc) return rc;
     h->trace.lap(HostTrace::UPD_WAIT);
     const uint8_t* hm = h->h_mask.as<uint8_t>();
@@ -994,6 +1012,7 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
     if (!h || !frame || !mask) return fail(PCM_E_INVALID, "pcm_update: NULL argument");
     if (!labels) return update_from_quickshift(h, frame, H, W, stride, rect, priors, params, mask, mask_row_stride, mask_pixel_stride);
     h->qs_valid = false;                               // the resident crop is about to be replaced
+    h->chain_tail = false;
     const bool auto_labels = n_labels <= 0;            // n_labels = max(label) + 1, found while staging
     if (auto_labels && priors) return fail(PCM_E_INVALID, "pcm_update: priors need an explicit n_labels");
     int rc = validate_update(h, H, W, rect, auto_labels ? 1 : n_labels, params);
@@ -1127,6 +1146,7 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
     CUDA_TRY(h->h_small.reserve(64));
     CUDA_TRY(cudaStreamSynchronize(st));
     h->qs_valid = false;                               // the frame scratch is reused for the truth image
+    h->chain_tail = false;
     h->trace.start();
     HostPool& pool = HostPool::instance();
     uint8_t* hm = h->h_mask.as<uint8_t>();
@@ -1192,6 +1212,7 @@ static int enqueue_quickshift(pcm_handle* h, const uint8_t* d_frame, int64_t str
     const size_t n = (size_t)cw * ch;
     if (n > (1u << 30)) return fail(PCM_E_LIMIT, "quickshift: crop too large");
     cudaStream_t st = h->stream;
+    h->chain_tail = false;
     CUDA_TRY(h->qs_lab.reserve(3 * n * sizeof(double)));
     CUDA_TRY(h->qs_dens.reserve(n * sizeof(double)));
     CUDA_TRY(h->qs_parent.reserve(n * sizeof(int)));
@@ -1369,6 +1390,7 @@ extern "C" int pcm_convert(pcm_handle* h, const uint8_t* bgr, int height, int wi
     if (height <= 0 || width <= 0) return fail(PCM_E_INVALID, "pcm_convert: bad size");
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t bytes = (size_t)height * width * 3;
+    h->chain_tail = false;
     DevBuf in, o;
     CUDA_TRY(in.reserve(bytes));
     CUDA_TRY(o.reserve(bytes));
@@ -1396,6 +1418,7 @@ extern "C" int pcm_gather_features(pcm_handle* h, const uint8_t* frame, int H, i
     CUDA_TRY(cudaSetDevice(h->device));
     const int cw = rect[2], ch = rect[3];
     const size_t npx = (size_t)cw * ch, xbytes = npx * h->geom.F * sizeof(int16_t);
+    h->chain_tail = false;
     DevBuf in, o;
     CUDA_TRY(in.reserve(npx * 3));
     CUDA_TRY(o.reserve(xbytes));

@@ -92,7 +92,7 @@ struct PlanesArgs {
     int* rmin;
     int* rmax;
     int* n_flagged;
-    int* err;
+    int early;                // 1: the predecessor on the stream is this handle's own K3 / K5 (see below)
 };
 
 // MODE 1: features "<n> hsv_lab" (config.yaml:30), MODE 2: "<n> lab" (benchmark.py:48), MODE 0: any
@@ -104,13 +104,18 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
     __shared__ ColorTables tab;
     for (int i = threadIdx.x; i < (int)(sizeof(ColorTables) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&tab)[i] = reinterpret_cast<const uint32_t*>(a.tables)[i];
-    // Programmatic dependent launch: K0 does NOT wait for its predecessor before it works.  It can only
-    // have been started by a mask_dilate / iou kernel that is already running, i.e. after the previous
-    // frame's K2 has completed (K3 releases its dependents after its own wait, K5 at its very start), and
-    // nothing K0 writes (planes, per-label accumulators, tile counter) is touched by K3 or K5.  It waits
-    // at its END instead, so that "K0 complete" still implies "everything before K0 complete" for K1.
+    // Programmatic dependent launch.  a.early == 1 (the library enqueued this launch on the handle's
+    // PRIVATE stream right behind its own mask_dilate / iou kernel): K0 does not wait for its
+    // predecessor before it works.  It can only have been started by a K3 / K5 that is already running,
+    // i.e. after the previous frame's K2 has completed (K3 releases its dependents after its own wait,
+    // K5 at its very start), nothing K0 writes (planes, per-label accumulators, tile counter) is touched
+    // by K3 or K5, and nobody else can have queued a producer of `frame` on that stream.  It waits at
+    // its END instead, so that "K0 complete" still implies "everything before K0 complete" for K1.
+    // a.early == 0 (caller-provided stream, or anything else queued last): the predecessor may be a
+    // foreign kernel that writes `frame`, so K0 waits before it reads or resets anything.
+    if (!a.early) grid_dependency_wait();
     grid_launch_dependents();
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *a.tile_counter = 0; *a.n_flagged = 0; *a.err = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *a.tile_counter = 0; *a.n_flagged = 0; }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_labels; i += gridDim.x * blockDim.x) {
         a.sum[i] = 0.0; a.asum[i] = 0.0; a.area[i] = 0; a.rmin[i] = 0x7fffffff; a.rmax[i] = -1;
     }
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
         rn += dr; gn += dg;
         if (gn >= groups_per_row) { gn -= groups_per_row; ++rn; }
     }
-    grid_dependency_wait();
+    if (a.early) grid_dependency_wait();
 }
 
 // ---- PTX helpers: mbarrier, TMA tile load, shared-memory loads --------------------------
@@ -289,7 +294,7 @@ struct SegAcc {
     int* area;                 // [S]
     int* rmin;                 // [S] init INT_MAX
     int* rmax;                 // [S] init -1
-    int* err;                  // set to 1 on an out-of-range label
+    int* err;                  // STICKY per-handle word: set to 1 on an out-of-range label, cleared by the host once read
 };
 
 __device__ __forceinline__ double contribution(double p1, double sa, double thr) {
@@ -741,9 +746,10 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
 
 // K2b ----------------------------------------------------------------------------
 // score = f32( (acc/area) * (1-w) + prior * w ) > 0.5 (:241-242), acc being the
-// reference's sequential float32 accumulator.  The parallel float64 sum differs from
-// it by at most 2^-24 * sum|d| per unit area; a label whose score is that close to
-// 0.5 is re-evaluated EXACTLY by its warp: float32 accumulator, each `+=` evaluated in
+// reference's sequential float32 accumulator.  Every one of its `area` adds rounds a partial sum of
+// magnitude <= sum|d| to float32 (relative error 2^-24), so acc differs from the exact sum by at most
+// area * 2^-24 * sum|d| and the score by 2^-24 * sum|d| * |1-w|; a label whose score is that close to
+// 0.5 (plus the roundings of the score expression itself) is re-evaluated EXACTLY by its warp: float32 accumulator, each `+=` evaluated in
 // float64 and rounded to float32, pixels in raster order (:235-238).
 struct DecideArgs {
     const double* p1;
@@ -783,7 +789,7 @@ __global__ void __launch_bounds__(256) segment_decide_kernel(const DecideArgs a)
         else {
             prior = pr;
             const double sc = __dadd_rn(__dmul_rn(__ddiv_rn(sum, (double)area), omw), __dmul_rn(prior, w));
-            const double band = 2.0 * 5.9604644775390625e-08 * (asum / (double)area) * fabs(omw) + 2.4e-7;
+            const double band = 5.9604644775390625e-08 * asum * fabs(omw) * 1.0000001 + 2.4e-7;
             flagged = fabs(sc - 0.5) <= band;
             a.decision[s] = sc > 0.5;
             a.scores[s] = (float)sc;

@@ -50,6 +50,7 @@ def load_library():
         "pcm_destroy": (None, [P]),
         "pcm_set_stream": (I, [P, P]),
         "pcm_use_own_stream": (I, [P]),
+        "pcm_get_stream": (I, [P, C.POINTER(P)]),
         "pcm_synchronize": (I, [P]),
         "pcm_set_features": (I, [P, I, I, P]),
         "pcm_num_features": (I, [P]),
@@ -86,7 +87,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_use_own_stream", "pcm_synchronize",
+    "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_use_own_stream", "pcm_get_stream", "pcm_synchronize",
     "pcm_set_features", "pcm_num_features", "pcm_add_model", "pcm_set_novelty", "pcm_num_models", "pcm_crop_rect",
     "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device", "pcm_felzenszwalb",
     "pcm_convert", "pcm_gather_features",
@@ -98,6 +99,21 @@ KERNEL_NAMES = ["score", "segment_reduce", "segment_decide", "segment_resolve", 
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def class1_fraction(tree):
+    """Per-node P(class 1) as `DecisionTreeClassifier.predict_proba` reports it.  scikit-learn >= 1.4 stores
+    class FRACTIONS in `tree_.value` and returns them unchanged; older versions (the reference pins 0.24.1,
+    environment.yaml:14) store weighted class COUNTS and predict_proba divides by their sum
+    (`normalizer[normalizer == 0.0] = 1.0; proba /= normalizer`).  Both are reproduced bit for bit: values
+    whose rows all sum to 1 are fractions (or single-sample counts, for which the division is the identity)
+    and are taken as they are; anything else is normalised exactly like the old predict_proba."""
+    v = np.asarray(tree.value[:, 0, :], np.float64)
+    s = v.sum(axis=1)
+    if np.all(np.abs(s - 1.0) < 1e-9):
+        return v[:, 1].copy()
+    s[s == 0.0] = 1.0
+    return v[:, 1] / s
 
 
 def crop_rect(bbox, frame_h, frame_w):
@@ -199,6 +215,13 @@ class Handle:
     def use_own_stream(self):
         self._check(self.lib.pcm_use_own_stream(self._h))
 
+    @property
+    def stream(self):
+        """cudaStream_t (integer) the handle currently enqueues on."""
+        out = C.c_void_p()
+        self._check(self.lib.pcm_get_stream(self._h, C.byref(out)))
+        return int(out.value or 0)
+
     def synchronize(self):
         self._check(self.lib.pcm_synchronize(self._h))
 
@@ -223,7 +246,7 @@ class Handle:
         arrays = []
         for est in clf.estimators_[:n_trees]:
             t = est.tree_
-            arrays.append((t.feature, t.threshold, t.children_left, t.children_right, t.value[:, 0, 1]))
+            arrays.append((t.feature, t.threshold, t.children_left, t.children_right, class1_fraction(t)))
         return self.add_model_arrays(n_frame, arrays)
 
     def set_novelty(self, model_index, mean, component):

@@ -8,7 +8,8 @@
 What differs from the reference is only what cannot run on a headless GPU box: the GUI
 branches (manual ROI selection, imshow / waitKey, video writers) are not built, and the
 rigid tracker is a provider (`pcm.providers`): `cv.legacy` CSRT/KCF when the OpenCV build has
-it, else boxes derived from the ground-truth clip, else OpenCV's MIL tracker.
+it, else OpenCV's MIL tracker; boxes derived from the ground-truth clip only on request
+(`tracker_provider: truth`, which the shipped sweep config asks for and reports).
 The per-frame arithmetic is the CUDA path behind `maskers.getMaskerByName("PC")`; the IoU is
 `pcm_iou` (benchmark.py:8-14).
 """
@@ -129,12 +130,10 @@ def make_tracker(config, frame0, first_boxes, truth_frames, provider=None):
     """-> (factory(frame, boxes) -> tracker with .update(frame) -> (ok, boxes), name)."""
     provider = provider or config.get("tracker_provider") or "auto"
     if provider == "auto":
-        if hasattr(cv, "legacy"):
-            provider = "cv"
-        elif truth_frames is not None and len(first_boxes) == 1:
-            provider = "truth"
-        else:
-            provider = "cv"
+        # never the ground truth by default: boxes derived from the clip that also scores the masks are an
+        # explicit opt-in (`tracker_provider: truth`).  "cv" = cv.legacy CSRT/KCF/... when the OpenCV build has
+        # it (the reference's tracker, main.py:11-32), else OpenCV's MIL tracker; the name says which.
+        provider = "cv"
     if provider == "truth":
         if truth_frames is None:
             raise ValueError("tracker_provider 'truth' needs input_truth")
@@ -152,7 +151,8 @@ def make_tracker(config, frame0, first_boxes, truth_frames, provider=None):
         return (lambda frame, start_boxes, start_index=0: providers.ScriptedBoxTracker([[b] for b in start_boxes])), "static"
     if callable(provider):
         return provider, "custom"
-    return (lambda frame, start_boxes, start_index=0: _CvMultiTracker(config.get("tracker"), frame, start_boxes)), "cv"
+    name = "cv.legacy:%s" % (config.get("tracker") or "CSRT") if hasattr(cv, "legacy") else "cv:MIL"
+    return (lambda frame, start_boxes, start_index=0: _CvMultiTracker(config.get("tracker"), frame, start_boxes)), name
 
 
 def run_sequence(config, device=0, out_path=None, segment_fn=None, prior_fn=None, tracker_provider=None,

@@ -232,16 +232,28 @@ def forest_from_arrays(tree_arrays, n_features):
     return dict(trees=trees, n_features=int(n_features))
 
 
+def class1_fraction(tree):
+    """P(class 1) per node as predict_proba reports it: tree_.value holds class fractions from
+    scikit-learn 1.4 on (returned unchanged) and weighted class counts before (the reference pins
+    0.24.1), where predict_proba divides by the row sum with a zero sum replaced by 1."""
+    v = np.asarray(tree.value[:, 0, :], np.float64)
+    s = v.sum(axis=1)
+    if np.all(np.abs(s - 1.0) < 1e-9):
+        return v[:, 1].copy()
+    s[s == 0.0] = 1.0
+    return v[:, 1] / s
+
+
 def sklearn_tree_arrays(clf):
     """Raw per-tree arrays of a fitted sklearn RandomForestClassifier (estimators_ order);
-    value1 = tree_.value[node,0,1], the class-1 fraction (sklearn >= 1.3 stores fractions)."""
+    value1 = P(class 1) of the node as predict_proba reports it (class1_fraction)."""
     if list(clf.classes_) != [0, 1]:
         raise ValueError("forest must be a binary {0,1} classifier (reference indexes probs[:,1])")
     out = []
     for est in clf.estimators_:
         t = est.tree_
         out.append((t.feature.copy(), t.threshold.copy(), t.children_left.copy(),
-                    t.children_right.copy(), t.value[:, 0, 1].copy()))
+                    t.children_right.copy(), class1_fraction(t)))
     return out
 
 

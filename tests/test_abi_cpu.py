@@ -69,3 +69,34 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"#\s*include\s*[\"<][^\">]*oracle", t):
                     bad.append(os.path.join(d, f))
     assert not bad, "product files referring to oracle/: %s" % bad
+
+
+def test_forest_export_is_predict_proba_for_fractions_and_counts():
+    """`tree_.value` holds class fractions from scikit-learn 1.4 on and weighted class COUNTS
+    before (the reference pins 0.24.1); the exporter must hand the C ABI what predict_proba reports in
+    both cases (leaf values in [0, 1]; forest_p1 == clf.predict_proba bit for bit)."""
+    import numpy as np
+    from sklearn.ensemble import RandomForestClassifier
+    from pcm import capi
+    import pcm_oracle as orc
+    rng = np.random.default_rng(3)
+    Xi = rng.integers(-1, 256, (600, 27)).astype(np.int16)
+    y = (Xi[:, 3] + Xi[:, 11] > 250).astype(np.int64)
+    clf = RandomForestClassifier(random_state=42, n_estimators=7, max_depth=6).fit(Xi.astype(np.float64) / 255, y)
+    want = clf.predict_proba(Xi.astype(np.float64) / 255)[:, 1]
+    got = orc.forest_p1(orc.export_forest(clf), Xi)
+    assert np.array_equal(got, want)
+    for est in clf.estimators_:
+        v = capi.class1_fraction(est.tree_)
+        assert v.min() >= 0.0 and v.max() <= 1.0
+        assert np.array_equal(v, orc.class1_fraction(est.tree_))
+        # the same tree as an old scikit-learn would store it: weighted class counts per node
+        class Counts:
+            value = est.tree_.value * est.tree_.weighted_n_node_samples[:, None, None]
+        c = capi.class1_fraction(Counts)
+        assert c.min() >= 0.0 and c.max() <= 1.0
+        old = Counts.value[:, 0, :].copy()
+        norm = old.sum(axis=1)[:, None]
+        norm[norm == 0.0] = 1.0
+        assert np.array_equal(c, (old / norm)[:, 1])          # 0.24's predict_proba arithmetic
+        assert np.allclose(c, v, rtol=0, atol=1e-12)

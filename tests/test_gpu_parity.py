@@ -572,12 +572,21 @@ d_frames, d_truth, d_seg = torch.from_numpy(frames).to(dev), torch.from_numpy(tr
 d_mask = torch.zeros((H, W), dtype=torch.uint8, device=dev)
 d_counts = torch.zeros((60, 2), dtype=torch.int64, device=dev)
 torch.cuda.synchronize()
-h.set_stream(torch.cuda.current_stream().cuda_stream)
+import os
+mode = os.environ.get("PCM_TEST_STREAM", "torch")
+if mode != "own":                        # own: the handle's private stream (K0 may start early, PlanesArgs::early)
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+d_frame = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
+zero = torch.zeros((), dtype=torch.uint8, device=dev)
 digest = hashlib.sha1()
 for s in range(60):                      # back to back, no synchronisation between frames
     f = s %% 6
     prm = capi.Handle.make_params(0, 1, 1 - s / 60, s / 60, dilation_kernel=7)
-    h.update_device(d_frames[f].data_ptr(), H, W, W * 3, rect, d_seg.data_ptr(), S, 0, prm, d_mask.data_ptr(), W)
+    src = d_frames[f]
+    if mode == "producer":               # a foreign KERNEL writes the frame right before the update, same stream, no sync
+        torch.bitwise_xor(d_frames[f], zero, out=d_frame)
+        src = d_frame
+    h.update_device(src.data_ptr(), H, W, W * 3, rect, d_seg.data_ptr(), S, 0, prm, d_mask.data_ptr(), W)
     h.iou_device(d_mask.data_ptr(), W, d_truth[f].data_ptr(), W, 1, H, W, d_counts[s].data_ptr())
     if s %% 7 == 0:
         h.synchronize()
@@ -589,20 +598,52 @@ print("DIGEST", digest.hexdigest(), int(d_counts[:, 1].min()))
 
 
 def test_dependent_launch_chain_changes_nothing():
-    """The per-frame kernels overlap under programmatic dependent launch (the next frame's K0 runs
-    under the previous frame's K3/K5): 60 back-to-back frames on the device path give bit-identical
-    masks and IoU counts with PCM_PDL=1 and PCM_PDL=0."""
+    """The per-frame kernels overlap under programmatic dependent launch: 60 back-to-back frames on the
+    device path give bit-identical masks and IoU counts with PCM_PDL=0 and with PCM_PDL=1
+      * on the handle's private stream (the next frame's K0 starts under the previous frame's K3/K5),
+      * on a caller-provided stream (K0 waits for its predecessor first),
+      * on a caller-provided stream where a FOREIGN kernel writes the frame buffer immediately before every
+        update with no synchronisation (VERDICT r1 item 7 / ADVICE: stream order must hold for the frame)."""
     import subprocess
     import sys
     from helpers import PKG
     here = os.path.dirname(os.path.abspath(__file__))
     out = {}
-    for pdl in ("1", "0"):
+    for pdl, mode in (("0", "torch"), ("1", "own"), ("1", "torch"), ("1", "producer"), ("0", "producer")):
         res = subprocess.run([sys.executable, "-c", _PDL_SCRIPT % (PKG, here, os.path.join(os.path.dirname(here), "oracle"))],
-                             env=dict(os.environ, PCM_PDL=pdl),
+                             env=dict(os.environ, PCM_PDL=pdl, PCM_TEST_STREAM=mode),
                              capture_output=True, text=True, timeout=600)
         assert res.returncode == 0, res.stderr[-2000:]
         line = [l for l in res.stdout.splitlines() if l.startswith("DIGEST")][0].split()
-        out[pdl] = line[1]
+        out[(pdl, mode)] = line[1]
         assert int(line[2]) > 0, "empty union: the test frames must produce masks"
-    assert out["1"] == out["0"]
+    assert len(set(out.values())) == 1, out
+
+
+def test_label_error_is_sticky_on_the_async_path():
+    """an out-of-range label in frame n must still be reported when frame n+1 (clean) was queued
+    behind it before anybody synchronised; it is reported once."""
+    import torch
+    from pcm import capi
+    rng = np.random.default_rng(2)
+    H = W = 48
+    frame = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    h = capi.Handle(0)
+    h.set_features(1, ["rgb"])
+    h.add_model_arrays(0, _random_forest_arrays(rng, 2, 2, 27))
+    good = np.zeros((H, W), np.int32)
+    bad = good.copy()
+    bad[3, 4] = 7
+    dev = torch.device("cuda", 0)
+    d_frame, d_good, d_bad = (torch.from_numpy(a).to(dev) for a in (frame, good, bad))
+    d_mask = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    prm = capi.Handle.make_params(0)
+    h.update_device(d_frame.data_ptr(), H, W, W * 3, (0, 0, W, H), d_bad.data_ptr(), 2, 0, prm, d_mask.data_ptr(), W)
+    h.update_device(d_frame.data_ptr(), H, W, W * 3, (0, 0, W, H), d_good.data_ptr(), 2, 0, prm, d_mask.data_ptr(), W)
+    with pytest.raises(capi.PcmError):
+        h.synchronize()
+    h.synchronize()                                  # reported once, then cleared
+    h.update_device(d_frame.data_ptr(), H, W, W * 3, (0, 0, W, H), d_good.data_ptr(), 2, 0, prm, d_mask.data_ptr(), W)
+    h.synchronize()
+    h.close()
