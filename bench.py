@@ -493,6 +493,12 @@ def run_b200(args, rank, world, local_rank):
                          "frames/s by pixel count; the reference path is single-threaded" % (reps, sw, sh, tt),
                "host_cores_available": os.cpu_count()}
 
+    # ---- second half of BASELINE.json's metric: the benchmark.py grid sweep, sharded over the ranks ----
+    sweep_rec = None
+    if not args.no_sweep:
+        h.synchronize()
+        sweep_rec = sweep_record(args, rank, world)
+
     out = None
     if rank == 0:
         out = {
@@ -500,7 +506,7 @@ def run_b200(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic", "config": workload_config(),
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "mean_iou_vs_truth": mean_iou, "impl": "b200",
+            "cpu_baseline": cpu, "mean_iou_vs_truth": mean_iou, "impl": "b200", "sweep": sweep_rec,
         }
     if dist is not None:
         dist.barrier()
@@ -508,19 +514,38 @@ def run_b200(args, rank, world, local_rank):
     return out
 
 
-def run_sweep(args, rank, world):
-    """Second half of BASELINE.json's metric: the benchmark.py HYPERPARAMS x VIDEOS grid, whole
-    sequences sharded over the ranks (one process per GPU), ONE final gather of the scores."""
+def sweep_run(args, rank, world):
     import yaml
     from pcm import sweep
     with open(os.path.join(PKG, "config_benchmark.yaml")) as f:
         base = yaml.full_load(f)
     with open(os.path.join(PKG, "polygons.yaml")) as f:
         polygons = yaml.full_load(f)
-    summary, table = sweep.run(base, polygons, limit=args.sweep_limit or None, max_frames=args.sweep_max_frames or None,
-                               out_csv=os.path.join(ROOT, "gpurun_out", "benchmark_results.csv") if rank == 0 and
-                               os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None, log=log,
-                               seq_workers=args.sweep_workers or None)
+    return sweep.run(base, polygons, limit=args.sweep_limit or None, max_frames=args.sweep_max_frames or None,
+                     out_csv=os.path.join(ROOT, "gpurun_out", "benchmark_results.csv") if rank == 0 and
+                     os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None, log=log,
+                     seq_workers=args.sweep_workers or None)
+
+
+def sweep_record(args, rank, world):
+    """`sweep` sub-record of every bench line: the reference's benchmark.py grid (:26-89), 64 hyper-parameter
+    combinations x 4 SegTrack2 clips = 256 sequences, sharded over the ranks, ONE final gather."""
+    summary, table = sweep_run(args, rank, world)
+    if rank != 0:
+        return None
+    return {"metric": "grid-sweep sequences/sec", "sequences_per_s": summary["sequences_per_s"], "unit": "sequences/s",
+            "seconds": summary["seconds"], "n_sequences": summary["n_sequences"], "n_gpus": world, "scaling": "strong",
+            "mean_iou": float(np.nanmean(table["avg_benchmark"])) if table is not None else None,
+            "tracker_provider": summary.get("tracker_provider"), "host_cores": summary["host_cores"],
+            "per_rank_sequences": summary["per_rank_sequences"], "seq_workers": summary["seq_workers"],
+            "train_jobs": summary["train_jobs"], "per_stage_host_s": summary.get("per_stage_host_s_rank0"),
+            "data": "SegTrack2 clips shipped with the reference (soldier, frog, worm, bmx)"}
+
+
+def run_sweep(args, rank, world):
+    """Second half of BASELINE.json's metric: the benchmark.py HYPERPARAMS x VIDEOS grid, whole
+    sequences sharded over the ranks (one process per GPU), ONE final gather of the scores."""
+    summary, table = sweep_run(args, rank, world)
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         dist.barrier()
@@ -550,6 +575,7 @@ def main():
     ap.add_argument("--e2e-only", action="store_true", help="tuning aid: shorten the device-resident leg")
     ap.add_argument("--workload", default="1080p", choices=["1080p", "sweep"],
                     help="1080p: frames/s (default, the driver's metric); sweep: benchmark.py grid, sequences/s")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the grid-sweep sub-record of the default workload")
     ap.add_argument("--sweep-limit", type=int, default=0, help="only the first N sequences of the 256")
     ap.add_argument("--sweep-max-frames", type=int, default=0)
     ap.add_argument("--sweep-workers", type=int, default=0, help="sequence threads per rank (0: cores_per_rank / 3, at most 6)")

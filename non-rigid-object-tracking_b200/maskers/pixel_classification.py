@@ -21,7 +21,7 @@ from sklearn.decomposition import PCA
 from sklearn.ensemble import RandomForestClassifier
 from sklearn.metrics import f1_score
 
-from pcm import capi
+from pcm import capi, stages
 from pcm.providers import make_segment_provider
 from pcm.priors import SiftPrior
 from .masker import Masker
@@ -98,7 +98,8 @@ class PixelClassificationNonRigidMasker(Masker):
             Xn = self._rows(frame, tuple(int(v) for v in bbox_roni))
             return np.concatenate([X, Xn], axis=0), np.concatenate([labels, np.zeros(len(Xn), np.int64)])
 
-        X, labels = cached((self.cache_tag, n_frame, params["features"], "rows"), make_rows)
+        with stages.stage("train_rows"):
+            X, labels = cached((self.cache_tag, n_frame, params["features"], "rows"), make_rows)
 
         n_trees = int(params["n_estimators"])
         n_fit = max(n_trees, int(self.fit_estimators or 0))
@@ -110,7 +111,8 @@ class PixelClassificationNonRigidMasker(Masker):
                 print("F1 score classifier for frame {}= {}".format(n_frame, round(f1_score(labels, clf.predict(X)), 2)))
             return clf
 
-        clf = cached((self.cache_tag, n_frame, params["features"], n_fit, params["max_depth"], "forest"), make_forest)
+        with stages.stage("fit_forest"):
+            clf = cached((self.cache_tag, n_frame, params["features"], n_fit, params["max_depth"], "forest"), make_forest)
 
         if params["novelty_detection"]:
             def make_pca():
@@ -119,13 +121,15 @@ class PixelClassificationNonRigidMasker(Masker):
                     raise ValueError("the native novelty path supports n_components == 1 (config.yaml:27)")
                 residual = np.sum(np.sqrt(np.power(X - pca.inverse_transform(pca.transform(X)), 2)), axis=1)
                 return pca, np.percentile(residual, 90)
-            pca, threshold = cached((self.cache_tag, n_frame, params["features"], params["n_components"], "pca"), make_pca)
+            with stages.stage("fit_pca"):
+                pca, threshold = cached((self.cache_tag, n_frame, params["features"], params["n_components"], "pca"), make_pca)
         else:
             pca, threshold = None, 0.0
 
-        m = self.native.add_forest(n_frame, clf, n_trees)
-        if pca is not None:
-            self.native.set_novelty(m, pca.mean_, pca.components_[0])
+        with stages.stage("export_model"):
+            m = self.native.add_forest(n_frame, clf, n_trees)
+            if pca is not None:
+                self.native.set_novelty(m, pca.mean_, pca.components_[0])
         self.models.append({"n_frame": n_frame, "model": clf, "n_trees": n_trees})
         self.novelty_det.append({"n_frame": n_frame, "model": pca, "threshold": threshold})
         return bbox_roni
@@ -161,10 +165,12 @@ class PixelClassificationNonRigidMasker(Masker):
             if self._qs_noise_shape != (h, w):
                 noise = np.random.RandomState(42).normal(scale=0.00001, size=(h, w))
                 self._qs_noise_shape = (h, w)
-            segments, n_labels = self.native.quickshift(frame, (x, y, w, h), ratio=0.5, kernel_size=3, max_dist=6,
-                                                        noise=noise, want_labels=want_prior)
+            with stages.stage("gpu_quickshift_call"):
+                segments, n_labels = self.native.quickshift(frame, (x, y, w, h), ratio=0.5, kernel_size=3, max_dist=6,
+                                                            noise=noise, want_labels=want_prior)
             if want_prior:
-                priors = prior(segments, n_labels)
+                with stages.stage("sift_prior"):
+                    priors = prior(segments, n_labels)
             segments = None                    # update() continues from the device-resident map
         else:
             if self.native_felzenszwalb:
@@ -174,15 +180,17 @@ class PixelClassificationNonRigidMasker(Masker):
                 def segment():
                     return capi.felzenszwalb(frame, (x, y, w, h), scale=100, sigma=0.5, min_size=50)
                 cache = self.model_cache if self.cache_tag is not None else None
-                if cache is not None and hasattr(cache, "get_or_compute"):
-                    segments, n_labels = cache.get_or_compute((self.cache_tag, "felzenszwalb", self.index, (x, y, w, h)), segment)
-                else:
-                    segments, n_labels = segment()
+                with stages.stage("felzenszwalb"):
+                    if cache is not None and hasattr(cache, "get_or_compute"):
+                        segments, n_labels = cache.get_or_compute((self.cache_tag, "felzenszwalb", self.index, (x, y, w, h)), segment)
+                    else:
+                        segments, n_labels = segment()
             else:
                 segments = np.ascontiguousarray(self.segment_fn(crop), np.int32)
             if want_prior:
                 n_labels = int(segments.max()) + 1
-                priors = prior(segments, n_labels)
+                with stages.stage("sift_prior"):
+                    priors = prior(segments, n_labels)
 
         blend = bool(self.multi_selection) and len(self.models) > cur + 1
         w_cur, w_next = 1.0, 0.0
@@ -195,7 +203,8 @@ class PixelClassificationNonRigidMasker(Masker):
                                     dilation_kernel=params["dilation_kernel"],
                                     outlier_threshold=self.novelty_det[cur]["threshold"],
                                     prior_weight=params["prior_weight"])
-        self.native.update(frame, (x, y, w, h), segments, n_labels, priors, p, mask, channel=2)
+        with stages.stage("gpu_update_call"):
+            self.native.update(frame, (x, y, w, h), segments, n_labels, priors, p, mask, channel=2)
 
         self.index += 1
         self.prevFrame = crop

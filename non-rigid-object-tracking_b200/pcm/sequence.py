@@ -21,7 +21,7 @@ import numpy as np
 import yaml
 
 from maskers import getMaskerByName
-from . import providers
+from . import providers, stages
 
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -227,9 +227,12 @@ def run_sequence(config, device=0, out_path=None, segment_fn=None, prior_fn=None
                     tracker = factory(frame, [bboxes[t][status] for t in range(len(bboxes))], index + 1)
             if truth is not None:
                 # truth is the decoded BGR frame; pcm_iou applies the BGR2GRAY arithmetic of main.py:285
-                inter, union = native.iou_counts(masked[:, :, 2], truth)
+                with stages.stage("gpu_iou_call"):
+                    inter, union = native.iou_counts(masked[:, :, 2], truth)
                 ious.append(inter / union if union else float("nan"))
     seconds = time.time() - start
+    stages.add("frame_loop", seconds)
+    stages.add("decode", t_decode)
     mean_iou = float(np.mean(ious)) if ious else float("nan")
     if out_path is not None:
         with open(out_path, "w") as f:

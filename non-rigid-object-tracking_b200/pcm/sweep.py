@@ -16,6 +16,7 @@ import time
 import numpy as np
 
 from . import sequence as seq_mod
+from . import stages
 
 # benchmark.py:41-51
 VIDEOS = ["soldier", "frog", "worm", "bmx"]
@@ -246,6 +247,7 @@ def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, ou
         cv2.setNumThreads(max(1, cores // seq_workers))             # SIFT's internal parallel_for
     except Exception:
         pass
+    stages.reset()
     t0 = time.time()
     local = run_shard(shards[rank], base, polygons, device=local_rank, max_frames=max_frames, train_jobs=train_jobs,
                       seq_workers=seq_workers,
@@ -262,7 +264,8 @@ def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, ou
         t_all = float(t.item())
     summary = dict(n_sequences=len(items), seconds=t_all, sequences_per_s=len(items) / t_all if t_all > 0 else 0.0,
                    n_gpus=world, per_rank_sequences=[len(s) for s in shards], train_jobs=train_jobs,
-                   seq_workers=seq_workers, host_cores=os.cpu_count())
+                   seq_workers=seq_workers, host_cores=os.cpu_count(), tracker_provider=base.get("tracker_provider"),
+                   rank0_seconds=t_local, per_stage_host_s_rank0={k: round(v, 3) for k, v in sorted(stages.snapshot().items())})
     table = None
     if rank == 0:
         table = results_table(all_rows, videos, hyper)
