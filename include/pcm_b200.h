@@ -198,6 +198,29 @@ int pcm_felzenszwalb(const uint8_t* frame, int frame_h, int frame_w, int64_t fra
                      double scale, double sigma, int min_size, const double* kernel, int kernel_radius,
                      int32_t* labels_out, int* n_labels_out);
 
+/* ---- training (addModel :166-228), SURVEY.md §8 row f-3 ------------------- */
+
+/* Grow, on the GPU, the trees that scikit-learn 1.9's
+ *     RandomForestClassifier(random_state, n_estimators, max_depth).fit(X / 255, y)      (:199-200)
+ * grows -- node for node, threshold for threshold (tests compare the arrays with scikit-learn's tree_).
+ *   X            n_rows x n_features int16, row-major, raw feature values v in [-1, 255] as
+ *                pcm_gather_features returns them (the reference trains on X / 255, :196), or NULL to reuse the
+ *                rows that the previous call with the same non-zero rows_id left on the device
+ *   y            n_rows class labels 0 / 1 (both present)
+ *   counts       n_trees x n_rows bootstrap counts (np.bincount of RandomState(tree seed).randint(0, n, n),
+ *                sklearn/ensemble/_forest.py:148-153), each <= 127
+ *   rand_states  n_trees splitter seeds (RandomState(tree seed).randint(0, 2**31 - 1), tree/_splitter.pyx:155)
+ *   max_features features drawn per node: max(1, int(sqrt(n_features))) for the reference's default
+ *   node_capacity  stride of the per-tree outputs; 2^(max_depth+1) - 1 always suffices
+ * Outputs, tree t at [t * node_capacity, ...): node_count[t]; feature (-2 = leaf), threshold (-2.0 = leaf),
+ * left / right (-1 = leaf), value1 = class-1 fraction of the node, n_node_samples (may be NULL), nodes in
+ * scikit-learn's depth-first order.  The arrays feed pcm_add_model unchanged.  Synchronous.
+ * Limits: n_rows < 2^24, n_features <= 1176, max_depth <= 24. */
+int pcm_fit_forest(pcm_handle* h, const int16_t* X, const uint8_t* y, int n_rows, int n_features, long long rows_id,
+                   int n_trees, int max_depth, int max_features, const uint8_t* counts, const uint32_t* rand_states,
+                   int node_capacity, int32_t* node_count, int32_t* feature, double* threshold,
+                   int32_t* left, int32_t* right, double* value1, int32_t* n_node_samples);
+
 /* ---- parity taps (tests, smoke; not needed by the reference flow) -------- */
 
 /* cv.cvtColor(img, BGR2HSV / BGR2LAB) of an h x w x 3 host image with the same

@@ -6,6 +6,7 @@
 #include "../../include/pcm_b200.h"
 #include "pcm_kernels.cuh"
 #include "pcm_quickshift.cuh"
+#include "pcm_forest_fit.cuh"
 #include "pcm_host.h"
 
 #include <cudaTypedefs.h>
@@ -237,6 +238,11 @@ struct pcm_handle {
     bool qs_valid = false;
     const uint8_t* qs_frame_ptr = nullptr;     // host frame the resident crop was staged from
     int qs_rect[4] = {0, 0, 0, 0};
+
+    // forest training (pcm_fit_forest): feature-major rows resident between calls, scratch, outputs
+    DevBuf fit_x, fit_xt, fit_y, fit_counts, fit_rand, fit_samples, fit_tmp, fit_out;
+    long long fit_rows_id = 0;
+    int fit_n = 0, fit_F = 0;
 
     // description of the last update (for pcm_debug_last)
     int last_cw = 0, last_ch = 0, last_S = 0;
@@ -564,6 +570,8 @@ extern "C" void pcm_destroy(pcm_handle* h) {
     for (auto& m : h->models) free_model(m);
     for (DevBuf* b : {&h->frame, &h->labels, &h->priors, &h->planes, &h->sched, &h->p1, &h->sa, &h->seg, &h->rmin, &h->rmax, &h->decision,
                       &h->scores, &h->flagged, &h->mask, &h->pre, &h->counts})
+        b->release();
+    for (DevBuf* b : {&h->fit_x, &h->fit_xt, &h->fit_y, &h->fit_counts, &h->fit_rand, &h->fit_samples, &h->fit_tmp, &h->fit_out})
         b->release();
     for (DevBuf* b : {&h->qs_lab, &h->qs_dens, &h->qs_noise, &h->qs_parent, &h->qs_root, &h->qs_flag, &h->qs_rank, &h->qs_sums,
                       &h->qs_labels, &h->qs_lin, &h->qs_count})
@@ -1377,6 +1385,82 @@ extern "C" int pcm_felzenszwalb(const uint8_t* frame, int H, int W, int64_t stri
                                kernel_radius, labels_out);
     if (n < 0) return fail(PCM_E_INVALID, "pcm_felzenszwalb: bad arguments");
     if (n_labels_out) *n_labels_out = n;
+    return PCM_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// API: training: the forest of addModel, grown on the GPU
+// ---------------------------------------------------------------------------------
+extern "C" int pcm_fit_forest(pcm_handle* h, const int16_t* X, const uint8_t* y, int n_rows, int n_features,
+                              long long rows_id, int n_trees, int max_depth, int max_features, const uint8_t* counts,
+                              const uint32_t* rand_states, int node_capacity, int32_t* node_count, int32_t* feature,
+                              double* threshold, int32_t* left, int32_t* right, double* value1, int32_t* n_node_samples) {
+    if (!h || !y || !counts || !rand_states || !node_count || !feature || !threshold || !left || !right || !value1)
+        return fail(PCM_E_INVALID, "pcm_fit_forest: NULL argument");
+    if (n_rows < 1 || n_rows >= (1 << 24)) return fail(PCM_E_LIMIT, "pcm_fit_forest: n_rows %d outside [1, 2^24)", n_rows);
+    if (n_features < 1 || n_features > FIT_MAX_FEATURES)
+        return fail(PCM_E_LIMIT, "pcm_fit_forest: n_features %d outside [1, %d]", n_features, FIT_MAX_FEATURES);
+    if (n_trees < 1) return fail(PCM_E_INVALID, "pcm_fit_forest: n_trees %d", n_trees);
+    if (max_depth < 0 || max_depth > FIT_MAX_DEPTH)
+        return fail(PCM_E_LIMIT, "pcm_fit_forest: max_depth %d outside [0, %d]", max_depth, FIT_MAX_DEPTH);
+    if (max_features < 1 || max_features > n_features) return fail(PCM_E_INVALID, "pcm_fit_forest: max_features %d", max_features);
+    if (node_capacity < 1) return fail(PCM_E_INVALID, "pcm_fit_forest: node_capacity %d", node_capacity);
+    const bool resident = !X;
+    if (resident && (rows_id == 0 || rows_id != h->fit_rows_id || n_rows != h->fit_n || n_features != h->fit_F))
+        return fail(PCM_E_STATE, "pcm_fit_forest: X == NULL needs the rows of a previous call with the same rows_id");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    h->chain_tail = false;
+    const size_t n = (size_t)n_rows, T = (size_t)n_trees, cap = (size_t)node_capacity;
+    const long long n_pad = ((long long)n_rows + 63) / 64 * 64;
+    for (size_t i = 0; i < T * n; ++i)
+        if (counts[i] > 127) return fail(PCM_E_LIMIT, "pcm_fit_forest: bootstrap count %d > 127", (int)counts[i]);
+    if (!resident) {
+        h->fit_rows_id = 0;
+        CUDA_TRY(h->fit_x.reserve(n * n_features * sizeof(int16_t)));
+        CUDA_TRY(h->fit_xt.reserve((size_t)n_pad * n_features * sizeof(int16_t)));
+        CUDA_TRY(cudaMemcpyAsync(h->fit_x.p, X, n * n_features * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        fit_transpose_kernel<<<dim3((n_rows + 31) / 32, (n_features + 31) / 32), dim3(32, 8), 0, st>>>(
+            h->fit_x.as<int16_t>(), n_rows, n_features, h->fit_xt.as<int16_t>(), n_pad);
+        CHECK_LAUNCH(h, "fit_transpose_kernel");
+    }
+    CUDA_TRY(h->fit_y.reserve(n));
+    CUDA_TRY(h->fit_counts.reserve(T * n));
+    CUDA_TRY(h->fit_rand.reserve(T * sizeof(uint32_t)));
+    CUDA_TRY(h->fit_samples.reserve(T * n * sizeof(uint32_t)));
+    CUDA_TRY(h->fit_tmp.reserve(T * n * sizeof(uint32_t)));
+    // outputs: [feature i32 | left i32 | right i32 | n_node_samples i32 | node_count i32 (T)] [threshold f64 | value1 f64]
+    const size_t o_feat = 0, o_left = o_feat + 4 * T * cap, o_right = o_left + 4 * T * cap, o_nns = o_right + 4 * T * cap,
+                 o_cnt = o_nns + 4 * T * cap, o_thr = (o_cnt + 4 * T + 7) / 8 * 8, o_val = o_thr + 8 * T * cap,
+                 o_end = o_val + 8 * T * cap;
+    CUDA_TRY(h->fit_out.reserve(o_end));
+    CUDA_TRY(cudaMemcpyAsync(h->fit_y.p, y, n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->fit_counts.p, counts, T * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->fit_rand.p, rand_states, T * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    char* ob = h->fit_out.as<char>();
+    FitArgs a{};
+    a.Xt = h->fit_xt.as<int16_t>(); a.n_pad = n_pad;
+    a.y = h->fit_y.as<uint8_t>(); a.counts = h->fit_counts.as<uint8_t>(); a.rand_state = h->fit_rand.as<uint32_t>();
+    a.n = n_rows; a.F = n_features; a.max_depth = max_depth; a.max_features = max_features; a.cap = node_capacity;
+    a.samples = h->fit_samples.as<uint32_t>(); a.tmp = h->fit_tmp.as<uint32_t>();
+    a.feature = reinterpret_cast<int32_t*>(ob + o_feat); a.left = reinterpret_cast<int32_t*>(ob + o_left);
+    a.right = reinterpret_cast<int32_t*>(ob + o_right); a.n_node_samples = reinterpret_cast<int32_t*>(ob + o_nns);
+    a.node_count = reinterpret_cast<int32_t*>(ob + o_cnt);
+    a.threshold = reinterpret_cast<double*>(ob + o_thr); a.value1 = reinterpret_cast<double*>(ob + o_val);
+    forest_fit_kernel<<<n_trees, FIT_THREADS, 0, st>>>(a);
+    CHECK_LAUNCH(h, "forest_fit_kernel");
+    CUDA_TRY(cudaMemcpyAsync(feature, ob + o_feat, 4 * T * cap, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(left, ob + o_left, 4 * T * cap, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(right, ob + o_right, 4 * T * cap, cudaMemcpyDeviceToHost, st));
+    if (n_node_samples) CUDA_TRY(cudaMemcpyAsync(n_node_samples, ob + o_nns, 4 * T * cap, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(node_count, ob + o_cnt, 4 * T, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(threshold, ob + o_thr, 8 * T * cap, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(value1, ob + o_val, 8 * T * cap, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    h->fit_rows_id = rows_id;
+    h->fit_n = n_rows; h->fit_F = n_features;
+    for (int t = 0; t < n_trees; ++t)
+        if (node_count[t] < 0) return fail(PCM_E_LIMIT, "pcm_fit_forest: tree %d needs more than %d nodes", t, node_capacity);
     return PCM_OK;
 }
 

@@ -1,0 +1,82 @@
+"""Training side of addModel (reference maskers/pixel_classification.py:166-228) on the GPU.
+
+The reference fits `RandomForestClassifier(random_state=42, n_estimators, max_depth).fit(X, labels)` (:199-200).
+`fit_forest` grows the SAME trees with `pcm_fit_forest` (csrc/pcm_forest_fit.cuh): the per-tree seeds, bootstrap
+counts and splitter seeds are drawn here with numpy exactly as scikit-learn draws them
+(sklearn/ensemble/_base.py:77-84 `_set_random_states`, _forest.py:95-103,148-153 `_generate_sample_indices` +
+`np.bincount`, tree/_splitter.pyx:155 `rand_r_state`), the trees themselves are grown on the device.  The growing
+procedure restates scikit-learn 1.9's; it is used when the installed scikit-learn is of that series (the tests compare
+the result with scikit-learn's `tree_` arrays) and `RandomForestClassifier` itself is used otherwise.
+"""
+import ctypes as C
+
+import numpy as np
+
+VALIDATED_SKLEARN = ("1.9.",)          # series whose tree builder csrc/pcm_forest_fit.cuh restates
+MAX_INT32 = np.iinfo(np.int32).max
+RAND_R_MAX = 2147483647
+
+
+def gpu_fit_supported():
+    import sklearn
+    return sklearn.__version__.startswith(VALIDATED_SKLEARN)
+
+
+def tree_draws(n_samples, n_estimators, random_state=42):
+    """(counts uint8 [T, n], splitter seeds uint32 [T]) of the forest's trees."""
+    rs = np.random.RandomState(random_state)
+    counts = np.empty((n_estimators, n_samples), np.uint8)
+    seeds = np.empty(n_estimators, np.uint32)
+    for t in range(n_estimators):
+        seed = rs.randint(MAX_INT32)
+        c = np.bincount(np.random.RandomState(seed).randint(0, n_samples, n_samples), minlength=n_samples)
+        if c.max() > 127:
+            raise ValueError("bootstrap count above 127")
+        counts[t] = c
+        seeds[t] = np.random.RandomState(seed).randint(0, RAND_R_MAX)
+    return counts, seeds
+
+
+class GpuForest:
+    """Fitted forest as raw per-tree arrays [(feature, threshold, left, right, value1)] in scikit-learn's node
+    order; `classes_` / `n_estimators` / `n_features_in_` mirror the estimator attributes the masker reads."""
+
+    def __init__(self, trees, n_features, max_depth):
+        self.trees = trees
+        self.n_estimators = len(trees)
+        self.n_features_in_ = n_features
+        self.max_depth = max_depth
+        self.classes_ = np.array([0, 1])
+
+    def tree_arrays(self, n_trees=None):
+        return self.trees[:n_trees]
+
+
+def fit_forest(handle, X, y, n_estimators, max_depth, random_state=42, rows_id=0, rows_resident=False, draws=None):
+    """X: int16 [n, F] raw feature values (-1..255) as `Handle.gather_features` returns them; y: 0/1 labels.
+    rows_id / rows_resident: a non-zero id names the row set; with rows_resident=True the rows the handle still holds
+    from its previous fit with that id are reused instead of uploaded again.  Returns a GpuForest."""
+    X = np.ascontiguousarray(X, np.int16)
+    n, F = X.shape
+    y8 = np.ascontiguousarray(y, np.uint8)
+    if y8.min() != 0 or y8.max() != 1:
+        raise ValueError("binary {0,1} labels with both classes present are required (the reference indexes probs[:,1])")
+    counts, seeds = draws if draws is not None else tree_draws(n, n_estimators, random_state)
+    max_features = max(1, int(np.sqrt(F)))
+    cap = int(min(2 ** (max_depth + 1) - 1, 2 * n - 1)) if max_depth <= 24 else 2 * n - 1
+    T = n_estimators
+    node_count = np.empty(T, np.int32)
+    feature = np.empty((T, cap), np.int32)
+    left = np.empty((T, cap), np.int32)
+    right = np.empty((T, cap), np.int32)
+    thr = np.empty((T, cap), np.float64)
+    val = np.empty((T, cap), np.float64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    handle._check(handle.lib.pcm_fit_forest(handle._h, None if rows_resident else p(X), p(y8), n, F, int(rows_id), T,
+                                            int(max_depth), max_features, p(counts), p(seeds), cap, p(node_count),
+                                            p(feature), p(thr), p(left), p(right), p(val), None))
+    trees = []
+    for t in range(T):
+        k = int(node_count[t])
+        trees.append((feature[t, :k].copy(), thr[t, :k].copy(), left[t, :k].copy(), right[t, :k].copy(), val[t, :k].copy()))
+    return GpuForest(trees, F, max_depth)
