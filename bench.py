@@ -480,7 +480,7 @@ def run_b200(args, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         log("[cpu_baseline] timing the CPU port on a bounded sample ...")
-        clfs = [d["model"] for d in masker.models]
+        clfs = sklearn_models(seq)                     # the port scores with scikit-learn's predict_proba
         pm = cpu_port_setup(seq, clfs)
         cpu_port_step(pm, frames_h[0], truth_h[0], 64, 64, 0)          # numba JIT
         sw, sh = 640, 352

@@ -221,6 +221,19 @@ int pcm_fit_forest(pcm_handle* h, const int16_t* X, const uint8_t* y, int n_rows
                    int node_capacity, int32_t* node_count, int32_t* feature, double* threshold,
                    int32_t* left, int32_t* right, double* value1, int32_t* n_node_samples);
 
+/* Upload a training-row set (as for pcm_fit_forest) without fitting; it stays resident under rows_id != 0. */
+int pcm_fit_rows(pcm_handle* h, const int16_t* X, const uint8_t* y, int n_rows, int n_features, long long rows_id);
+
+/* Novelty detector of addModel (:203-213: PCA(n_components=1).fit(X[labels == 1]), then the L1 reconstruction
+ * error of every training row) on the RESIDENT rows `rows_id`:
+ *   pcm_pca_moments    gram[F*F] = sum over class-1 rows of v v^T, sums[F] = sum of v (raw integer feature values,
+ *                      exact), n_class1.  The caller forms sklearn's covariance (decomposition/_pca.py, solver
+ *                      covariance_eigh) and takes its leading eigenvector (pcm/train.py: numpy.linalg.eigh).
+ *   pcm_pca_residuals  err[n_rows] = sum_f |x_f - (t c_f + mean_f)|, t = x.c - mean.c, x = v / 255 (:208-211) for
+ *                      every row; the caller takes np.percentile(err, 90) as the outlier threshold (:212). */
+int pcm_pca_moments(pcm_handle* h, long long rows_id, double* gram, double* sums, int64_t* n_class1);
+int pcm_pca_residuals(pcm_handle* h, long long rows_id, const double* mean, const double* component, double* err);
+
 /* ---- parity taps (tests, smoke; not needed by the reference flow) -------- */
 
 /* cv.cvtColor(img, BGR2HSV / BGR2LAB) of an h x w x 3 host image with the same

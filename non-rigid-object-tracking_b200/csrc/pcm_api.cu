@@ -1391,15 +1391,49 @@ extern "C" int pcm_felzenszwalb(const uint8_t* frame, int H, int W, int64_t stri
 // ---------------------------------------------------------------------------------
 // API: training: the forest of addModel, grown on the GPU
 // ---------------------------------------------------------------------------------
+static int upload_fit_rows(pcm_handle* h, const int16_t* X, const uint8_t* y, int n_rows, int n_features, long long rows_id) {
+    cudaStream_t st = h->stream;
+    const size_t n = (size_t)n_rows;
+    const long long n_pad = ((long long)n_rows + 63) / 64 * 64;
+    h->fit_rows_id = 0;
+    CUDA_TRY(h->fit_x.reserve(n * n_features * sizeof(int16_t)));
+    CUDA_TRY(h->fit_xt.reserve((size_t)n_pad * n_features * sizeof(int16_t)));
+    CUDA_TRY(h->fit_y.reserve(n));
+    CUDA_TRY(cudaMemcpyAsync(h->fit_x.p, X, n * n_features * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->fit_y.p, y, n, cudaMemcpyHostToDevice, st));
+    fit_transpose_kernel<<<dim3((n_rows + 31) / 32, (n_features + 31) / 32), dim3(32, 8), 0, st>>>(
+        h->fit_x.as<int16_t>(), n_rows, n_features, h->fit_xt.as<int16_t>(), n_pad);
+    CHECK_LAUNCH(h, "fit_transpose_kernel");
+    h->fit_rows_id = rows_id;
+    h->fit_n = n_rows; h->fit_F = n_features;
+    return PCM_OK;
+}
+
+static int check_fit_rows(pcm_handle* h, const char* who, const uint8_t* y, int n_rows, int n_features) {
+    if (!h || !y) return fail(PCM_E_INVALID, "%s: NULL argument", who);
+    if (n_rows < 1 || n_rows >= (1 << 24)) return fail(PCM_E_LIMIT, "%s: n_rows %d outside [1, 2^24)", who, n_rows);
+    if (n_features < 1 || n_features > FIT_MAX_FEATURES)
+        return fail(PCM_E_LIMIT, "%s: n_features %d outside [1, %d]", who, n_features, FIT_MAX_FEATURES);
+    return PCM_OK;
+}
+
+extern "C" int pcm_fit_rows(pcm_handle* h, const int16_t* X, const uint8_t* y, int n_rows, int n_features, long long rows_id) {
+    int rc = check_fit_rows(h, "pcm_fit_rows", y, n_rows, n_features);
+    if (rc) return rc;
+    if (!X) return fail(PCM_E_INVALID, "pcm_fit_rows: NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->chain_tail = false;
+    return upload_fit_rows(h, X, y, n_rows, n_features, rows_id);
+}
+
 extern "C" int pcm_fit_forest(pcm_handle* h, const int16_t* X, const uint8_t* y, int n_rows, int n_features,
                               long long rows_id, int n_trees, int max_depth, int max_features, const uint8_t* counts,
                               const uint32_t* rand_states, int node_capacity, int32_t* node_count, int32_t* feature,
                               double* threshold, int32_t* left, int32_t* right, double* value1, int32_t* n_node_samples) {
-    if (!h || !y || !counts || !rand_states || !node_count || !feature || !threshold || !left || !right || !value1)
+    int rc = check_fit_rows(h, "pcm_fit_forest", y, n_rows, n_features);
+    if (rc) return rc;
+    if (!counts || !rand_states || !node_count || !feature || !threshold || !left || !right || !value1)
         return fail(PCM_E_INVALID, "pcm_fit_forest: NULL argument");
-    if (n_rows < 1 || n_rows >= (1 << 24)) return fail(PCM_E_LIMIT, "pcm_fit_forest: n_rows %d outside [1, 2^24)", n_rows);
-    if (n_features < 1 || n_features > FIT_MAX_FEATURES)
-        return fail(PCM_E_LIMIT, "pcm_fit_forest: n_features %d outside [1, %d]", n_features, FIT_MAX_FEATURES);
     if (n_trees < 1) return fail(PCM_E_INVALID, "pcm_fit_forest: n_trees %d", n_trees);
     if (max_depth < 0 || max_depth > FIT_MAX_DEPTH)
         return fail(PCM_E_LIMIT, "pcm_fit_forest: max_depth %d outside [0, %d]", max_depth, FIT_MAX_DEPTH);
@@ -1416,15 +1450,9 @@ extern "C" int pcm_fit_forest(pcm_handle* h, const int16_t* X, const uint8_t* y,
     for (size_t i = 0; i < T * n; ++i)
         if (counts[i] > 127) return fail(PCM_E_LIMIT, "pcm_fit_forest: bootstrap count %d > 127", (int)counts[i]);
     if (!resident) {
-        h->fit_rows_id = 0;
-        CUDA_TRY(h->fit_x.reserve(n * n_features * sizeof(int16_t)));
-        CUDA_TRY(h->fit_xt.reserve((size_t)n_pad * n_features * sizeof(int16_t)));
-        CUDA_TRY(cudaMemcpyAsync(h->fit_x.p, X, n * n_features * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-        fit_transpose_kernel<<<dim3((n_rows + 31) / 32, (n_features + 31) / 32), dim3(32, 8), 0, st>>>(
-            h->fit_x.as<int16_t>(), n_rows, n_features, h->fit_xt.as<int16_t>(), n_pad);
-        CHECK_LAUNCH(h, "fit_transpose_kernel");
+        rc = upload_fit_rows(h, X, y, n_rows, n_features, rows_id);
+        if (rc) return rc;
     }
-    CUDA_TRY(h->fit_y.reserve(n));
     CUDA_TRY(h->fit_counts.reserve(T * n));
     CUDA_TRY(h->fit_rand.reserve(T * sizeof(uint32_t)));
     CUDA_TRY(h->fit_samples.reserve(T * n * sizeof(uint32_t)));
@@ -1434,7 +1462,6 @@ extern "C" int pcm_fit_forest(pcm_handle* h, const int16_t* X, const uint8_t* y,
                  o_cnt = o_nns + 4 * T * cap, o_thr = (o_cnt + 4 * T + 7) / 8 * 8, o_val = o_thr + 8 * T * cap,
                  o_end = o_val + 8 * T * cap;
     CUDA_TRY(h->fit_out.reserve(o_end));
-    CUDA_TRY(cudaMemcpyAsync(h->fit_y.p, y, n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->fit_counts.p, counts, T * n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->fit_rand.p, rand_states, T * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     char* ob = h->fit_out.as<char>();
@@ -1457,10 +1484,52 @@ extern "C" int pcm_fit_forest(pcm_handle* h, const int16_t* X, const uint8_t* y,
     CUDA_TRY(cudaMemcpyAsync(threshold, ob + o_thr, 8 * T * cap, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(value1, ob + o_val, 8 * T * cap, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    h->fit_rows_id = rows_id;
-    h->fit_n = n_rows; h->fit_F = n_features;
     for (int t = 0; t < n_trees; ++t)
         if (node_count[t] < 0) return fail(PCM_E_LIMIT, "pcm_fit_forest: tree %d needs more than %d nodes", t, node_capacity);
+    return PCM_OK;
+}
+
+extern "C" int pcm_pca_moments(pcm_handle* h, long long rows_id, double* gram, double* sums, int64_t* n_class1) {
+    if (!h || !gram || !sums || !n_class1) return fail(PCM_E_INVALID, "pcm_pca_moments: NULL argument");
+    if (rows_id == 0 || rows_id != h->fit_rows_id) return fail(PCM_E_STATE, "pcm_pca_moments: rows %lld are not resident", rows_id);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    h->chain_tail = false;
+    const int F = h->fit_F, n = h->fit_n;
+    const long long n_pad = ((long long)n + 63) / 64 * 64;
+    const size_t gb = sizeof(double) * (size_t)F * F, sb = sizeof(double) * (size_t)F;
+    CUDA_TRY(h->fit_out.reserve(gb + sb + 8));
+    char* ob = h->fit_out.as<char>();
+    const int tiles = (F + 31) / 32;
+    pca_gram_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(h->fit_xt.as<int16_t>(), n_pad, h->fit_y.as<uint8_t>(), n, F,
+                                                       reinterpret_cast<double*>(ob), reinterpret_cast<double*>(ob + gb),
+                                                       reinterpret_cast<unsigned long long*>(ob + gb + sb));
+    CHECK_LAUNCH(h, "pca_gram_kernel");
+    CUDA_TRY(cudaMemcpyAsync(gram, ob, gb, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(sums, ob + gb, sb, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(n_class1, ob + gb + sb, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PCM_OK;
+}
+
+extern "C" int pcm_pca_residuals(pcm_handle* h, long long rows_id, const double* mean, const double* component, double* err) {
+    if (!h || !mean || !component || !err) return fail(PCM_E_INVALID, "pcm_pca_residuals: NULL argument");
+    if (rows_id == 0 || rows_id != h->fit_rows_id) return fail(PCM_E_STATE, "pcm_pca_residuals: rows %lld are not resident", rows_id);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    h->chain_tail = false;
+    const int F = h->fit_F, n = h->fit_n;
+    const long long n_pad = ((long long)n + 63) / 64 * 64;
+    const size_t fb = sizeof(double) * (size_t)F, eb = sizeof(double) * (size_t)n;
+    CUDA_TRY(h->fit_out.reserve(2 * fb + eb));
+    char* ob = h->fit_out.as<char>();
+    CUDA_TRY(cudaMemcpyAsync(ob, component, fb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ob + fb, mean, fb, cudaMemcpyHostToDevice, st));
+    pca_residual_kernel<<<(n + 255) / 256, 256, 2 * fb, st>>>(h->fit_xt.as<int16_t>(), n_pad, n, F, reinterpret_cast<double*>(ob + fb),
+                                                            reinterpret_cast<double*>(ob), reinterpret_cast<double*>(ob + 2 * fb));
+    CHECK_LAUNCH(h, "pca_residual_kernel");
+    CUDA_TRY(cudaMemcpyAsync(err, ob + 2 * fb, eb, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return PCM_OK;
 }
 

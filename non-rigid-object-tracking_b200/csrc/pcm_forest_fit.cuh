@@ -318,4 +318,77 @@ __global__ void __launch_bounds__(FIT_THREADS) forest_fit_kernel(const FitArgs a
     if (tid == 0) a.node_count[t] = node_count;
 }
 
+// ---- PCA novelty detector of addModel (:203-213) on the resident training rows -------------------------------
+// Gram matrix and column sums of the class-1 rows: G[i][j] = sum_r y_r v_ri v_rj, S[i] = sum_r y_r v_ri (raw integer
+// feature values v; exact: products < 2^16, every partial sum an integer far below 2^53).  The host turns them into
+// sklearn's covariance (decomposition/_pca.py `_fit_full`, solver covariance_eigh: C = X^T X - n mean mean^T,
+// C /= n - 1) and takes the leading eigenvector.  One block = a 32 x 32 tile of G, rows in chunks of 64.
+__global__ void __launch_bounds__(256) pca_gram_kernel(const int16_t* __restrict__ Xt, long long n_pad, const uint8_t* __restrict__ y,
+                                                       int n, int F, double* __restrict__ G, double* __restrict__ S,
+                                                       unsigned long long* __restrict__ n1) {
+    __shared__ int A[32][65], B[32][65];
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // 16 x 16 threads, 2 x 2 outputs each
+    long long acc[2][2] = {{0, 0}, {0, 0}};
+    long long colsum = 0, ones = 0;
+    for (int r0 = 0; r0 < n; r0 += 64) {
+        for (int k = threadIdx.x; k < 32 * 64; k += 256) {
+            const int f = k >> 6, r = r0 + (k & 63);
+            const int m = (r < n) ? (int)y[r] : 0;
+            A[f][k & 63] = (m && i0 + f < F) ? (int)Xt[(size_t)(i0 + f) * n_pad + r] : 0;
+            B[f][k & 63] = (m && j0 + f < F) ? (int)Xt[(size_t)(j0 + f) * n_pad + r] : 0;
+        }
+        __syncthreads();
+        int c[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll 16
+        for (int k = 0; k < 64; ++k) {
+            const int a0 = A[2 * ty][k], a1 = A[2 * ty + 1][k], b0 = B[2 * tx][k], b1 = B[2 * tx + 1][k];
+            c[0][0] += a0 * b0; c[0][1] += a0 * b1; c[1][0] += a1 * b0; c[1][1] += a1 * b1;
+        }
+        acc[0][0] += c[0][0]; acc[0][1] += c[0][1]; acc[1][0] += c[1][0]; acc[1][1] += c[1][1];
+        if (blockIdx.x == 0 && threadIdx.x < 32) {                    // column sums of the i-tile, class-1 count
+            int sm = 0;
+            for (int k = 0; k < 64; ++k) sm += A[threadIdx.x][k];
+            colsum += sm;
+            if (blockIdx.y == 0 && threadIdx.x == 0)
+                for (int k = 0; k < 64 && r0 + k < n; ++k) ones += y[r0 + k];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int i = i0 + 2 * ty + u, j = j0 + 2 * tx + v;
+            if (i < F && j < F) G[(size_t)i * F + j] = (double)acc[u][v];
+        }
+    if (blockIdx.x == 0 && threadIdx.x < 32 && i0 + (int)threadIdx.x < F) S[i0 + threadIdx.x] = (double)colsum;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *n1 = (unsigned long long)ones;
+}
+
+// L1 reconstruction error of EVERY training row under the rank-1 PCA (:208-211):
+//   t = x . c - mean . c ;  err = sum_f |x_f - (t c_f + mean_f)|,  x = v / 255.   One thread per row.
+__global__ void __launch_bounds__(256) pca_residual_kernel(const int16_t* __restrict__ Xt, long long n_pad, int n, int F,
+                                                           const double* __restrict__ mean, const double* __restrict__ comp,
+                                                           double* __restrict__ err) {
+    extern __shared__ double sh[];          // comp[F] | mean[F]
+    for (int f = threadIdx.x; f < F; f += blockDim.x) { sh[f] = comp[f]; sh[F + f] = mean[f]; }
+    __syncthreads();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double t = 0.0, mdc = 0.0;
+    for (int f = 0; f < F; ++f) {
+        const double x = (double)Xt[(size_t)f * n_pad + r] / 255.0;
+        t = fma(x, sh[f], t);
+        mdc = fma(sh[F + f], sh[f], mdc);
+    }
+    t -= mdc;
+    double e = 0.0;
+    for (int f = 0; f < F; ++f) {
+        const double x = (double)Xt[(size_t)f * n_pad + r] / 255.0;
+        e += fabs(x - fma(t, sh[f], sh[F + f]));
+    }
+    err[r] = e;
+}
+
 }  // namespace pcm

@@ -21,15 +21,17 @@ from sklearn.decomposition import PCA
 from sklearn.ensemble import RandomForestClassifier
 from sklearn.metrics import f1_score
 
-from pcm import capi, stages
+from pcm import capi, stages, train
 from pcm.providers import make_segment_provider
 from pcm.priors import SiftPrior
 from .masker import Masker
 
 
 class PixelClassificationNonRigidMasker(Masker):
+    _rows_ids = iter(range(1, 1 << 62))          # process-wide ids of training-row sets (device residency)
+
     def __init__(self, poly_roi=None, update_mask=None, segment_fn=None, prior_fn=None, device=0,
-                 model_cache=None, cache_tag=None, train_jobs=None, fit_estimators=None, **args):
+                 model_cache=None, cache_tag=None, train_jobs=None, fit_estimators=None, train_provider=None, **args):
         """Reference keywords: debug, frame, config, poly_roi, update_mask (main.py:138-144).
         Extra, all optional: `segment_fn(crop) -> int32 labels` and `prior_fn` (providers for the
         stages outside the hot path), `device` (CUDA ordinal), `model_cache` + `cache_tag` (a dict
@@ -38,8 +40,19 @@ class PixelClassificationNonRigidMasker(Masker):
         deterministic, random_state=42), `train_jobs` (sklearn n_jobs for the fit; the fitted
         forest does not depend on it), `fit_estimators` (a sweep's largest n_estimators: the forest
         is fitted once with that many trees and every smaller n_estimators uses its first trees --
-        with random_state=42 tree i is the same tree in both, tests/test_sweep_host.py)."""
+        with random_state=42 tree i is the same tree in both, tests/test_sweep_host.py),
+        `train_provider`: "gpu" grows the forest and fits the PCA on the device (pcm/train.py: the same trees
+        scikit-learn grows, tests/test_gpu_forest_fit.py), "sklearn" calls scikit-learn on the host as the
+        reference does; default: "gpu" when the installed scikit-learn is the series the GPU trainer restates."""
         Masker.__init__(self, **args)
+        import os
+        provider = train_provider or self.config.get("train_provider") or os.environ.get("PCM_TRAIN") or "auto"
+        if provider == "auto":
+            provider = "gpu" if train.gpu_fit_supported() else "sklearn"
+        if provider not in ("gpu", "sklearn"):
+            raise ValueError("train_provider must be auto, gpu or sklearn")
+        self.train_provider = provider
+        self._resident_rows = 0
         self.model_cache = model_cache
         self.cache_tag = cache_tag
         self.train_jobs = train_jobs
@@ -70,8 +83,8 @@ class PixelClassificationNonRigidMasker(Masker):
 
     # -- training (reference :166-228) -------------------------------------------
     def _rows(self, frame, rect):
-        """Feature rows of a rectangle as float64 X/255 (reference :54-55, :192-196)."""
-        return self.native.gather_features(frame, rect).astype(np.float64) / 255
+        """Raw feature rows of a rectangle, int16 in -1..255; the reference trains on these / 255 (:54-55, :192-196)."""
+        return self.native.gather_features(frame, rect)
 
     def addModel(self, frame, poly_roi, bbox, n_frame, bbox_roni=None, show_prob_map=False):
         if bbox_roni is None:
@@ -96,15 +109,27 @@ class PixelClassificationNonRigidMasker(Masker):
             X = self._rows(frame, (x, y, w, h))
             labels = (roi.reshape(-1) > 0).astype(np.int64)
             Xn = self._rows(frame, tuple(int(v) for v in bbox_roni))
-            return np.concatenate([X, Xn], axis=0), np.concatenate([labels, np.zeros(len(Xn), np.int64)])
+            return (np.concatenate([X, Xn], axis=0), np.concatenate([labels, np.zeros(len(Xn), np.int64)]),
+                    next(PixelClassificationNonRigidMasker._rows_ids))
 
         with stages.stage("train_rows"):
-            X, labels = cached((self.cache_tag, n_frame, params["features"], "rows"), make_rows)
+            Xi, labels, rows_id = cached((self.cache_tag, n_frame, params["features"], "rows"), make_rows)
+        gpu = self.train_provider == "gpu"
+
+        def resident():
+            """True when this handle already holds the row set; it does after the call."""
+            had = self._resident_rows == rows_id
+            self._resident_rows = rows_id
+            return had
 
         n_trees = int(params["n_estimators"])
         n_fit = max(n_trees, int(self.fit_estimators or 0))
 
         def make_forest():
+            if gpu:
+                return train.fit_forest(self.native, Xi, labels, n_fit, params["max_depth"], rows_id=rows_id,
+                                        rows_resident=resident())
+            X = Xi.astype(np.float64) / 255
             clf = RandomForestClassifier(random_state=42, n_estimators=n_fit, max_depth=params["max_depth"],
                                          n_jobs=self.train_jobs).fit(X, labels)
             if n_fit == n_trees:
@@ -116,6 +141,13 @@ class PixelClassificationNonRigidMasker(Masker):
 
         if params["novelty_detection"]:
             def make_pca():
+                if gpu:
+                    if params["n_components"] != 1:
+                        raise ValueError("the native novelty path supports n_components == 1 (config.yaml:27)")
+                    if not resident():
+                        train.upload_rows(self.native, Xi, labels, rows_id)
+                    return train.fit_pca(self.native, rows_id, len(labels), Xi.shape[1])
+                X = Xi.astype(np.float64) / 255
                 pca = PCA(n_components=params["n_components"]).fit(X[labels == 1])
                 if pca.components_.shape[0] != 1:
                     raise ValueError("the native novelty path supports n_components == 1 (config.yaml:27)")

@@ -65,7 +65,13 @@ def load_library():
         "pcm_quickshift": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
         "pcm_quickshift_device": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
         "pcm_felzenszwalb": (I, [P, I, I, L, P, D, D, I, P, I, P, C.POINTER(I)]),
+        "pcm_fit_rows": (I, [P, P, P, I, I, C.c_longlong]),
+        "pcm_pca_moments": (I, [P, C.c_longlong, P, P, P]),
+        "pcm_pca_residuals": (I, [P, C.c_longlong, P, P, P]),
         "pcm_fit_forest": (I, [P, P, P, I, I, C.c_longlong, I, I, I, P, P, I, P, P, P, P, P, P, P]),
+        "pcm_fit_rows": (I, [P, P, P, I, I, C.c_longlong]),
+        "pcm_pca_moments": (I, [P, C.c_longlong, P, P, P]),
+        "pcm_pca_residuals": (I, [P, C.c_longlong, P, P, P]),
         "pcm_fit_forest": (I, [P, P, P, I, I, C.c_longlong, I, I, I, P, P, I, P, P, P, P, P, P, P]),
         "pcm_convert": (I, [P, P, I, I, L, I, P, L]),
         "pcm_gather_features": (I, [P, P, I, I, L, P, P]),
@@ -92,7 +98,7 @@ EXPORTED_SYMBOLS = [
     "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_use_own_stream", "pcm_get_stream", "pcm_synchronize",
     "pcm_set_features", "pcm_num_features", "pcm_add_model", "pcm_set_novelty", "pcm_num_models", "pcm_crop_rect",
     "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device", "pcm_felzenszwalb",
-    "pcm_fit_forest", "pcm_convert", "pcm_gather_features",
+    "pcm_fit_forest", "pcm_fit_rows", "pcm_pca_moments", "pcm_pca_residuals", "pcm_convert", "pcm_gather_features",
     "pcm_set_debug", "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_transfer_bytes", "pcm_set_label_cache", "pcm_profile_enable", "pcm_profile_read",
 ]
 
@@ -245,6 +251,8 @@ class Handle:
         its first n_trees estimators (with a fixed random_state they ARE the smaller forest)."""
         if list(clf.classes_) != [0, 1]:
             raise ValueError("forest must be a binary {0,1} classifier (the reference indexes probs[:,1])")
+        if hasattr(clf, "tree_arrays"):            # pcm.train.GpuForest: already raw arrays in scikit-learn's layout
+            return self.add_model_arrays(n_frame, clf.tree_arrays(n_trees))
         arrays = []
         for est in clf.estimators_[:n_trees]:
             t = est.tree_

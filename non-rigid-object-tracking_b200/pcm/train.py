@@ -9,6 +9,7 @@ procedure restates scikit-learn 1.9's; it is used when the installed scikit-lear
 the result with scikit-learn's `tree_` arrays) and `RandomForestClassifier` itself is used otherwise.
 """
 import ctypes as C
+import functools
 
 import numpy as np
 
@@ -22,8 +23,10 @@ def gpu_fit_supported():
     return sklearn.__version__.startswith(VALIDATED_SKLEARN)
 
 
+@functools.lru_cache(maxsize=64)
 def tree_draws(n_samples, n_estimators, random_state=42):
-    """(counts uint8 [T, n], splitter seeds uint32 [T]) of the forest's trees."""
+    """(counts uint8 [T, n], splitter seeds uint32 [T]) of the forest's trees (they depend on the number of rows,
+    trees and the seed only: cached)."""
     rs = np.random.RandomState(random_state)
     counts = np.empty((n_estimators, n_samples), np.uint8)
     seeds = np.empty(n_estimators, np.uint32)
@@ -80,3 +83,48 @@ def fit_forest(handle, X, y, n_estimators, max_depth, random_state=42, rows_id=0
         k = int(node_count[t])
         trees.append((feature[t, :k].copy(), thr[t, :k].copy(), left[t, :k].copy(), right[t, :k].copy(), val[t, :k].copy()))
     return GpuForest(trees, F, max_depth)
+
+
+class GpuPCA:
+    """The two attributes of sklearn.decomposition.PCA(n_components=1) the masker reads."""
+
+    def __init__(self, mean, component):
+        self.mean_ = mean
+        self.components_ = component.reshape(1, -1)
+        self.n_components = 1
+
+
+def upload_rows(handle, X, y, rows_id):
+    X = np.ascontiguousarray(X, np.int16)
+    y8 = np.ascontiguousarray(y, np.uint8)
+    handle._check(handle.lib.pcm_fit_rows(handle._h, X.ctypes.data_as(C.c_void_p), y8.ctypes.data_as(C.c_void_p),
+                                          X.shape[0], X.shape[1], int(rows_id)))
+
+
+def fit_pca(handle, rows_id, n_rows, n_features):
+    """PCA(n_components=1).fit(X[labels == 1]) and the 90th percentile of the L1 reconstruction error of every
+    training row (reference :203-213) from the rows resident on `handle` under rows_id.
+    Mirrors sklearn/decomposition/_pca.py `_fit_full` with the covariance_eigh solver (the one scikit-learn 1.9
+    picks for these shapes): C = X^T X - n mean mean^T, C /= n - 1, leading eigenvector of C, sign chosen so that its
+    largest-magnitude entry is positive (svd_flip, u_based_decision=False).  The Gram matrix is accumulated on the
+    device over the raw integer feature values (exact) and scaled by 1/255^2 here.  Returns (GpuPCA, threshold)."""
+    F = n_features
+    G = np.empty((F, F), np.float64)
+    S = np.empty(F, np.float64)
+    n1 = np.zeros(1, np.int64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    handle._check(handle.lib.pcm_pca_moments(handle._h, int(rows_id), p(G), p(S), p(n1)))
+    m = int(n1[0])
+    if m < 2:
+        raise ValueError("PCA needs at least two foreground rows")
+    mean = S / 255.0 / m
+    Cov = G / (255.0 * 255.0)
+    Cov -= m * mean.reshape(-1, 1) * mean.reshape(1, -1)
+    Cov /= m - 1
+    _, vecs = np.linalg.eigh(Cov)
+    comp = np.ascontiguousarray(vecs[:, -1])
+    if comp[np.argmax(np.abs(comp))] < 0:
+        comp = -comp
+    err = np.empty(n_rows, np.float64)
+    handle._check(handle.lib.pcm_pca_residuals(handle._h, int(rows_id), p(mean), p(comp), p(err)))
+    return GpuPCA(mean, comp), float(np.percentile(err, 90))

@@ -121,20 +121,51 @@ def test_update_sequence_matches_reference(name):
         assert m.native.iou_counts(mask[:, :, 2], g.truth[i]) == (int(z["inter"][i]), int(z["union"][i]))
 
 
-def test_addmodel_trains_the_reference_forest():
-    """addModel with device-gathered feature rows + sklearn reproduces the reference's trees."""
+@pytest.mark.parametrize("provider", ["gpu", "sklearn"])
+def test_addmodel_trains_the_reference_forest(provider):
+    """addModel reproduces the trees the UNMODIFIED reference trained (golden): with the forest grown on the GPU
+    (pcm_fit_forest) and with scikit-learn on device-gathered rows."""
     g = GoldenSeq("soldier_default")
     from maskers import getMaskerByName
     poly = polygons()[g.meta["video"]]
     pts, ronis = poly["pts"][0], poly["bboxes_roni"][0]
-    m = getMaskerByName("PC", debug=False, frame=g.frames[0], config=g.config, poly_roi=pts[0], update_mask=False)
-    fn = g.model_frames()[0]
-    assert m.addModel(frame=g.frames[fn], poly_roi=pts[0], bbox=cv.boundingRect(np.array(pts[0])),
-                      bbox_roni=ronis[0], n_frame=fn) == ronis[0]
-    got = orc.sklearn_tree_arrays(m.models[0]["model"])
-    for a, b in zip(got, g.tree_arrays(0)):
-        for u, v in zip(a, b):
-            assert np.array_equal(u, v)
+    m = getMaskerByName("PC", debug=False, frame=g.frames[0], config=g.config, poly_roi=pts[0], update_mask=False,
+                        train_provider=provider)
+    for s in range(2):
+        fn = g.model_frames()[s]
+        assert m.addModel(frame=g.frames[fn], poly_roi=pts[s], bbox=cv.boundingRect(np.array(pts[s])),
+                          bbox_roni=ronis[s], n_frame=fn) == ronis[s]
+        model = m.models[s]["model"]
+        got = model.tree_arrays() if provider == "gpu" else orc.sklearn_tree_arrays(model)
+        assert len(got) == len(g.tree_arrays(s))
+        for a, b in zip(got, g.tree_arrays(s)):
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v)
+    m.close()
+
+
+@pytest.mark.parametrize("name", ["parachute_novelty", "frog_sweep"])
+def test_addmodel_gpu_pca_matches_the_reference(name):
+    """Novelty detector of addModel fitted on the device (Gram matrix + residuals) against the PCA and the outlier
+    threshold the unmodified reference computed (golden; sklearn PCA(n_components=1), :203-213), and the forests."""
+    g = GoldenSeq(name)
+    from maskers import getMaskerByName
+    poly = polygons()[g.meta["video"]]
+    pts, ronis = poly["pts"][0], poly["bboxes_roni"][0]
+    m = getMaskerByName("PC", debug=False, frame=g.frames[0], config=g.config, poly_roi=pts[0], update_mask=False,
+                        train_provider="gpu")
+    for s in range(g.n_models):
+        fn = g.model_frames()[s]
+        m.addModel(frame=g.frames[fn], poly_roi=pts[s], bbox=cv.boundingRect(np.array(pts[s])), bbox_roni=ronis[s], n_frame=fn)
+        for a, b in zip(m.models[s]["model"].tree_arrays(), g.tree_arrays(s)):
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v)
+        mean, comp = g.pca(s)
+        pca = m.novelty_det[s]["model"]
+        np.testing.assert_allclose(pca.mean_, mean, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(pca.components_, comp, rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(m.novelty_det[s]["threshold"], g.novelty_threshold(s), rtol=1e-8)
+    m.close()
 
 
 def _random_forest_arrays(rng, n_trees, depth, F):
