@@ -178,7 +178,6 @@ class PixelClassificationNonRigidMasker(Masker):
         ys, xs = slice(y, y + h), slice(x, x + w)
         crop = frame[ys, xs]
         params = self.config["params"]
-        cur = self.current_model
 
         want_prior = self.index != 0 and params["prior_weight"] != 0.0
 
@@ -224,6 +223,16 @@ class PixelClassificationNonRigidMasker(Masker):
                 with stages.stage("sift_prior"):
                     priors = prior(segments, n_labels)
 
+        p, blend = self._frame_params()
+        with stages.stage("gpu_update_call"):
+            self.native.update(frame, (x, y, w, h), segments, n_labels, priors, p, mask, channel=2)
+        return self._advance(blend, crop, mask[ys, xs, 2])
+
+    # -- state machine shared by update() and update_resident() (reference :81-87, :114-126) ----------
+    def _frame_params(self):
+        """(pcm_update_params of the frame about to be processed, blend flag)."""
+        params = self.config["params"]
+        cur = self.current_model
         blend = bool(self.multi_selection) and len(self.models) > cur + 1
         w_cur, w_next = 1.0, 0.0
         if blend:
@@ -235,14 +244,28 @@ class PixelClassificationNonRigidMasker(Masker):
                                     dilation_kernel=params["dilation_kernel"],
                                     outlier_threshold=self.novelty_det[cur]["threshold"],
                                     prior_weight=params["prior_weight"])
-        with stages.stage("gpu_update_call"):
-            self.native.update(frame, (x, y, w, h), segments, n_labels, priors, p, mask, channel=2)
+        return p, blend
 
+    def _advance(self, blend, crop, mask_crop, quiet=False):
+        cur = self.current_model
         self.index += 1
         self.prevFrame = crop
-        self.prevForegroundMask = mask[ys, xs, 2]
+        self.prevForegroundMask = mask_crop
         if blend and self.index >= self.models[cur + 1]["n_frame"]:
             self.current_model += 1
-            print("\n \n CHANGE OF MODEL \n \n")
+            if not quiet:
+                print("\n \n CHANGE OF MODEL \n \n")
             return self.current_model   # tells the caller to re-initialise the tracker
         return None
+
+    def update_resident(self, d_frame, frame_h, frame_w, frame_stride, rect, d_labels, n_labels, d_priors, d_mask,
+                        mask_stride):
+        """update() for a caller that keeps the frame, the label map of the crop `rect` (from pcm_crop_rect), the
+        optional priors and the mask plane ON THE DEVICE (integers = device addresses): the same state machine and
+        the same kernels as update(), enqueued on the handle's stream without waiting (pcm_update_device).  The
+        caller provides what update() derives on the host (over-segmentation labels, SIFT priors) and owns
+        prevFrame / prevForegroundMask bookkeeping.  Returns None or the new model index, like update()."""
+        p, blend = self._frame_params()
+        self.native.update_device(d_frame, frame_h, frame_w, frame_stride, rect, d_labels, n_labels, d_priors, p,
+                                  d_mask, mask_stride)
+        return self._advance(blend, None, None, quiet=True)

@@ -314,6 +314,17 @@ class Handle:
                                             C.byref(n)))
         return out, n.value
 
+    def quickshift_device(self, d_frame, frame_h, frame_w, stride, rect, ratio, kernel_size, max_dist, d_noise, d_labels_out):
+        """quickshift of the crop `rect` of a DEVICE frame into a device label map (integers = device addresses;
+        d_noise: float64 tie-breaking noise, h*w values, or 0).  Waits for the segment count, which it returns."""
+        r = (C.c_int * 4)(*[int(v) for v in rect])
+        n = C.c_int(0)
+        self._check(self.lib.pcm_quickshift_device(self._h, C.c_void_p(d_frame), int(frame_h), int(frame_w), int(stride), r,
+                                                   float(ratio), float(kernel_size), float(max_dist),
+                                                   C.c_void_p(d_noise) if d_noise else None,
+                                                   C.c_void_p(d_labels_out) if d_labels_out else None, C.byref(n)))
+        return n.value
+
     def update_device(self, d_frame, frame_h, frame_w, stride, rect, d_labels, n_labels, d_priors, params, d_mask,
                       mask_stride):
         """Device-pointer update (integers are raw device addresses); asynchronous."""

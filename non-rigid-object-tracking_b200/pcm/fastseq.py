@@ -1,0 +1,274 @@
+"""Clip-resident sequence driver: the flow of `pcm.sequence.run_sequence` (reference main.py:72-368) for callers
+that run MANY sequences over the same clip (the benchmark.py grid: 64 hyper-parameter sets per clip).
+
+What is shared by all sequences of a clip is computed once per rank and kept on the device (`ClipContext`):
+  * the decoded frames and the ground truth (gray, cv.cvtColor(BGR2GRAY) as main.py:285);
+  * the tracker boxes of every frame -- they depend on the frames and on the (known) frames at which the masker
+    switches models, never on the masks (main.py:287-339);
+  * the over-segmentation of every frame's crop: quickshift on the GPU (pcm_quickshift_device) or felzenszwalb in
+    the library's host code (pixel_classification.py:70-73) -- a function of frame and crop only;
+  * the SIFT keypoints / descriptors of every crop (pixel_classification.py:129-163), when a prior is asked for.
+A sequence is then ONE pass that enqueues, per frame, the masker kernels (`update_resident` -> pcm_update_device)
+and the IoU kernel (pcm_iou_device) on a stream and synchronises once at the end -- unless the SIFT prior is on,
+which needs the previous mask on the host every frame.
+
+Results are the ones `run_sequence` gives for the same config (tests/test_gpu_sequence.py).  PyTorch is used for
+device buffers and streams only.
+"""
+import threading
+import time
+
+import cv2 as cv
+import numpy as np
+
+from maskers import getMaskerByName
+from . import capi, providers, stages
+from . import sequence as seq_mod
+
+
+class _Once:
+    """dict whose values are computed once, by the first thread that asks (others wait)."""
+
+    def __init__(self):
+        self.values, self.locks, self.guard = {}, {}, threading.Lock()
+
+    def get(self, key, make):
+        with self.guard:
+            if key in self.values:
+                return self.values[key]
+            lock = self.locks.setdefault(key, threading.Lock())
+        with lock:
+            with self.guard:
+                if key in self.values:
+                    return self.values[key]
+            v = make()
+            with self.guard:
+                self.values[key] = v
+            return v
+
+
+class LabelArena:
+    """Per-frame label maps of one (clip, box schedule, over-segmentation) on the device, back to back."""
+
+    def __init__(self, d_labels, offsets, n_labels, host=None):
+        self.d_labels, self.offsets, self.n_labels, self.host = d_labels, offsets, n_labels, host
+
+    def ptr(self, k):
+        return self.d_labels.data_ptr() + 4 * self.offsets[k]
+
+
+class ClipContext:
+    def __init__(self, video_path, truth_path, resize_factor=1, device=0, max_frames=None):
+        import torch
+        self.torch = torch
+        self.device = device
+        self.dev = torch.device("cuda", device)
+        with stages.stage("decode"):
+            frames = seq_mod.read_clip(seq_mod.resolve_path(video_path), resize_factor)
+            truths = seq_mod.read_clip(seq_mod.resolve_path(truth_path), resize_factor) if truth_path is not None else None
+        if not frames:
+            raise IOError("Fatal error! no frames in %s" % video_path)
+        self.frames, self.truths = frames, truths
+        self.n = len(frames) if max_frames is None else min(len(frames), max_frames)
+        self.H, self.W = frames[0].shape[:2]
+        with stages.stage("clip_upload"):
+            self.d_frames = torch.from_numpy(np.stack(frames[:self.n])).to(self.dev)
+            self.n_truth = 0
+            self.d_truth = None
+            if truths is not None:
+                self.n_truth = min(len(truths), self.n)
+                gray = np.stack([cv.cvtColor(t, cv.COLOR_BGR2GRAY) for t in truths[:self.n_truth]])
+                self.d_truth = torch.from_numpy(gray).to(self.dev)
+            torch.cuda.synchronize(self.dev)
+        self.once = _Once()
+        self.handle = capi.Handle(device)            # clip-level GPU work (quickshift label maps)
+        self.handle_lock = threading.Lock()
+
+    def close(self):
+        self.handle.close()
+
+    # ---- tracker boxes ------------------------------------------------------------------------------------
+    def schedule(self, config, bboxes, switch_frames, tracker_provider=None):
+        """Per-frame integer boxes of every target [(x, y, w, h)], for a masker that switches to model s + 1 after
+        frame switch_frames[s] - 1 (pixel_classification.py:117-126); replays main.py:287-339 without the masks.
+        Returns (key, boxes[n][targets], rects[n][targets], tracker name)."""
+        provider = tracker_provider or config.get("tracker_provider") or "auto"
+        first = tuple(tuple(int(v) for v in b[0]) for b in bboxes)
+        key = (str(provider), config.get("tracker"), first, tuple(switch_frames),
+               tuple(tuple(tuple(int(v) for v in b) for b in tb) for tb in bboxes))
+
+        def make():
+            with stages.stage("tracker_boxes"):
+                factory, name = seq_mod.make_tracker(config, self.frames[0], [b[0] for b in bboxes], self.truths, provider)
+                tracker = factory(self.frames[0], [b[0] for b in bboxes])
+                out, rects = [], []
+                cur = 0
+                for index in range(self.n):
+                    ok, boxes = tracker.update(self.frames[index])
+                    ib = [seq_mod.int_box(b) for b in boxes]
+                    out.append(ib)
+                    rects.append([capi.crop_rect(b, self.H, self.W) for b in ib])
+                    if cur + 1 < len(switch_frames) and index + 1 >= switch_frames[cur + 1]:
+                        cur += 1
+                        tracker = factory(self.frames[index], [bboxes[t][cur] for t in range(len(bboxes))], index + 1)
+                return out, rects, name
+        boxes, rects, name = self.once.get(("boxes", key), make)
+        return key, boxes, rects, name
+
+    # ---- over-segmentation ----------------------------------------------------------------------------------
+    def labels(self, kind, box_key, rects, want_host=False):
+        """LabelArena of `kind` in {"quickshift", "felzenszwalb"} for the crops `rects` (entry k = frame k // T,
+        target k % T)."""
+        torch = self.torch
+
+        def make():
+            flat = [r for fr in rects for r in fr]
+            sizes = [r[2] * r[3] for r in flat]
+            offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+            d = torch.empty(int(offsets[-1]), dtype=torch.int32, device=self.dev)
+            n_labels = []
+            T = len(rects[0])
+            if kind == "quickshift":
+                with stages.stage("quickshift_maps"), self.handle_lock:
+                    # quickshift(crop, kernel_size=3, max_dist=6, ratio=0.5, random_seed=42) (:71): the tie-breaking
+                    # noise RandomState(42).normal(scale=1e-5, size=(h, w)) is the first h*w values of ONE stream
+                    noise = np.random.RandomState(42).normal(scale=0.00001, size=max(sizes))
+                    d_noise = torch.from_numpy(noise).to(self.dev)
+                    torch.cuda.synchronize(self.dev)
+                    fb = self.H * self.W * 3
+                    for k, r in enumerate(flat):
+                        n_labels.append(self.handle.quickshift_device(self.d_frames.data_ptr() + (k // T) * fb, self.H, self.W,
+                                                                      self.W * 3, r, 0.5, 3, 6, d_noise.data_ptr(),
+                                                                      d.data_ptr() + 4 * int(offsets[k])))
+                host = None
+            elif kind == "felzenszwalb":
+                with stages.stage("felzenszwalb_maps"):
+                    host = []
+                    for k, r in enumerate(flat):
+                        seg, n = capi.felzenszwalb(self.frames[k // T], r, scale=100, sigma=0.5, min_size=50)
+                        host.append(seg)
+                        n_labels.append(n)
+                    d.copy_(torch.from_numpy(np.concatenate([h.reshape(-1) for h in host])))
+                    torch.cuda.synchronize(self.dev)
+            else:
+                raise ValueError("no clip-resident over-segmentation for %r" % kind)
+            return LabelArena(d, [int(o) for o in offsets], n_labels, host)
+        arena = self.once.get(("labels", kind, box_key), make)
+        if want_host and arena.host is None:
+            def fetch():
+                flat = [r for fr in rects for r in fr]
+                h = arena.d_labels.cpu().numpy()
+                return [h[arena.offsets[k]:arena.offsets[k + 1]].reshape(flat[k][3], flat[k][2]) for k in range(len(flat))]
+            arena.host = self.once.get(("labels_host", kind, box_key), fetch)
+        return arena
+
+
+def _precomputable(config):
+    if config.get("masker") != "PC" or config.get("manual_roi_selection"):
+        return False
+    if config.get("masker") in (config.get("custom_trackers") or []):
+        return False
+    return config["params"]["over_segmentation"] in ("quickshift", "felzenszwalb")
+
+
+def run_sequence_fast(config, clip, device=0, model_cache=None, cache_tag=None, tracker_provider=None, stream=None,
+                      out_path=None):
+    """`run_sequence` over a ClipContext.  `stream`: a torch.cuda.Stream owned by the calling thread (created when
+    omitted); the maskers enqueue on it."""
+    torch = clip.torch
+    t_wall = time.time()
+    if not _precomputable(config):
+        raise ValueError("run_sequence_fast: this config needs pcm.sequence.run_sequence")
+    params = config["params"]
+    pts, frame_numbers, ronis = config.get("pts"), config.get("pts_frame_numbers"), config.get("bboxes_roni")
+    frames = clip.frames
+    stream = stream or torch.cuda.Stream(device=clip.dev)
+
+    t_train = time.time()
+    maskers, bboxes = [], []
+    for n_target, target_selection in enumerate(pts):
+        bboxes.append([])
+        m = getMaskerByName("PC", debug=False, frame=frames[0], config=config, poly_roi=pts[n_target][0],
+                            update_mask=config.get("update_mask"), device=device, model_cache=model_cache,
+                            cache_tag=(cache_tag, n_target) if cache_tag is not None else None,
+                            train_jobs=config.get("train_jobs"), fit_estimators=config.get("fit_estimators"))
+        maskers.append(m)
+        for n_selection, selection in enumerate(target_selection):
+            if not config.get("multi_selection") and n_selection > 0:
+                continue
+            bbox = cv.boundingRect(np.array(selection))
+            bboxes[-1].append(bbox)
+            n_frame = frame_numbers[n_selection]
+            if n_frame >= len(frames):
+                raise IOError("Fatal error! selection frame %d beyond the clip" % n_frame)
+            m.addModel(frame=frames[n_frame], poly_roi=pts[n_target][n_selection], bbox=bbox,
+                       bbox_roni=ronis[n_target][n_selection] if ronis is not None else None, n_frame=n_frame)
+    t_train = time.time() - t_train
+
+    switch_frames = [md["n_frame"] for md in maskers[0].models] if config.get("multi_selection") else [0]
+    box_key, boxes, rects, tracker_name = clip.schedule(config, bboxes, switch_frames, tracker_provider)
+    want_prior = params["prior_weight"] != 0.0
+    arena = clip.labels(params["over_segmentation"], box_key, rects, want_host=want_prior)
+    T = len(maskers)
+    n, H, W = clip.n, clip.H, clip.W
+    fb = H * W * 3
+
+    start = time.time()
+    with torch.cuda.stream(stream):
+        d_mask = torch.zeros((H, W), dtype=torch.uint8, device=clip.dev)
+        d_counts = torch.zeros((n * T, 2), dtype=torch.int64, device=clip.dev)
+        d_priors = None
+        for m in maskers:
+            m.native.set_stream(stream.cuda_stream)
+        prev_rects = [None] * T
+        prev_crops = [None] * T                         # the SAME array objects the prior saw one frame earlier (SiftPrior reuse)
+        for index in range(n):
+            prev_masks = None
+            if want_prior and index > 0:
+                with stages.stage("prior_mask_d2h"):
+                    hm = d_mask.cpu().numpy()           # waits for the previous frame; its crops are the prevForegroundMasks
+                prev_masks = [hm[r[1]:r[1] + r[3], r[0]:r[0] + r[2]] for r in prev_rects]
+            if index > 0:
+                d_mask.zero_()                          # main.py:286: a fresh mask per frame
+            for i in range(T):
+                rect = rects[index][i]
+                k = index * T + i
+                S = arena.n_labels[k]
+                pri_ptr = 0
+                m = maskers[i]
+                if want_prior:
+                    x, y, w, h = rect
+                    crop = frames[index][y:y + h, x:x + w]
+                if prev_masks is not None:
+                    with stages.stage("sift_prior"):
+                        pri = m.prior_fn(prev_crops[i], prev_masks[i], crop, arena.host[k], S,
+                                         cache=model_cache, key=(cache_tag, i, index, rect)) \
+                            if cache_tag is not None else \
+                            m.prior_fn(prev_crops[i], prev_masks[i], crop, arena.host[k], S)
+                    d_priors = torch.from_numpy(np.ascontiguousarray(pri, np.float32)).to(clip.dev)
+                    pri_ptr = d_priors.data_ptr()
+                m.update_resident(clip.d_frames.data_ptr() + index * fb, H, W, W * 3, rect, arena.ptr(k), S, pri_ptr,
+                                  d_mask.data_ptr(), W)
+                prev_rects[i] = rect
+                if want_prior:
+                    prev_crops[i] = crop
+                if index < clip.n_truth:
+                    m.native.iou_device(d_mask.data_ptr(), W, clip.d_truth.data_ptr() + index * H * W, W, 1, H, W,
+                                        d_counts.data_ptr() + 16 * k)
+        with stages.stage("gpu_wait"):
+            maskers[0].native.synchronize()
+            counts = d_counts.cpu().numpy()
+    seconds = time.time() - start
+    stages.add("frame_loop", seconds)
+    ious = []
+    for k in range(min(n, clip.n_truth) * T):
+        inter, union = int(counts[k, 0]), int(counts[k, 1])
+        ious.append(inter / union if union else float("nan"))
+    mean_iou = float(np.mean(ious)) if ious else float("nan")
+    if out_path is not None:
+        with open(out_path, "w") as f:
+            f.write("%s;%s" % (mean_iou, seconds))
+    for m in maskers:
+        m.close()
+    return dict(mean_iou=mean_iou, seconds=seconds, iou=ious, n_frames=n, n_updates=n * T, train_seconds=t_train,
+                tracker=tracker_name, decode_seconds=0.0, wall_seconds=time.time() - t_wall)

@@ -127,51 +127,73 @@ def sequence_config(base, polygons, video, params, videos_path, truth_path):
 
 
 def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Video", truth_path="Input/SegTrack2/Truth",
-              max_frames=None, train_jobs=None, progress=None, seq_workers=1):
+              max_frames=None, train_jobs=None, progress=None, seq_workers=1, resident=True):
     """Run this rank's sequences; returns float64 [n, 3] = (sequence id, mean IoU, seconds).
 
-    With seq_workers > 1 whole forest groups (the sequences that share their fitted forests) are
-    handed to a small thread pool: one group's scikit-learn fits and SIFT priors (host, GIL
-    released) overlap another group's masker updates (GPU).  Every masker owns its own native
-    context and stream; results do not depend on the schedule."""
+    resident=True (default): every clip of the shard is decoded and uploaded ONCE (`fastseq.ClipContext`); its tracker
+    boxes, over-segmentation maps and SIFT features are shared by all hyper-parameter sets, forests and PCAs are
+    fitted on the GPU and shared through a rank-wide `ModelCache`, and a sequence is one asynchronous pass over the
+    device-resident frames.  `seq_workers` threads run sequences concurrently, each on its own CUDA stream: the host
+    stages of one sequence (SIFT priors, Python) overlap the kernels of the others.  Every masker owns its own native
+    context; results do not depend on the schedule.
+    resident=False: the per-frame host-buffer path of `pcm.sequence.run_sequence` (what `main.py` runs)."""
     out = np.zeros((len(items), 3), np.float64)
-    groups = {}
-    for k, it in enumerate(items):
-        groups.setdefault(forest_key(it), []).append(k)
     done = [0]
     lock = threading.Lock()
-
-    cache = ModelCache()                            # rows / forests / PCAs, shared by the threads of this rank
+    cache = ModelCache()                            # rows / forests / PCAs / SIFT features, shared by the threads of this rank
     fit_estimators = max([int(it[3]["n_estimators"]) for it in items] or [0])
+    videos = sorted({it[2] for it in items})
+    from . import capi
+    if items:
+        capi.load_library()                                             # dlopen once, before the threads
+    clips = {}
+    if resident and items:
+        from . import fastseq
+        from concurrent.futures import ThreadPoolExecutor
 
-    def run_group(indices):
-        for k in indices:
-            sid, i, v, params = items[k]
-            cfg = sequence_config(base, polygons, v, params, videos_path, truth_path)
-            cfg["train_jobs"] = train_jobs
-            cfg["fit_estimators"] = fit_estimators
+        def open_clip(v):
+            cfg = sequence_config(base, polygons, v, items[0][3], videos_path, truth_path)
+            return fastseq.ClipContext(cfg["input_video"], cfg["input_truth"], cfg.get("resize_factor") or 1, device, max_frames)
+        with ThreadPoolExecutor(max_workers=max(1, min(len(videos), seq_workers))) as pool:
+            clips = dict(zip(videos, pool.map(open_clip, videos)))
+    local = threading.local()
+
+    def run_one(k):
+        sid, i, v, params = items[k]
+        cfg = sequence_config(base, polygons, v, params, videos_path, truth_path)
+        cfg["train_jobs"] = train_jobs
+        cfg["fit_estimators"] = fit_estimators
+        if resident:
+            from . import fastseq
+            if getattr(local, "stream", None) is None:
+                import torch
+                local.stream = torch.cuda.Stream(device=clips[v].dev)
+            r = fastseq.run_sequence_fast(cfg, clips[v], device=device, model_cache=cache, cache_tag=v, stream=local.stream)
+        else:
             r = seq_mod.run_sequence(cfg, device=device, model_cache=cache, cache_tag=v, max_frames=max_frames)
-            out[k] = (sid, r["mean_iou"], r["seconds"])
-            with lock:
-                done[0] += 1
-                if progress:
-                    progress(done[0], len(items), sid, r)
+        out[k] = (sid, r["mean_iou"], r["seconds"])
+        with lock:
+            done[0] += 1
+            if progress:
+                progress(done[0], len(items), sid, r)
 
-    order = sorted(groups.values(), key=lambda ix: -sum(item_cost(items[k]) for k in ix))
+    # longest sequences first; sequences that share fits next to each other
+    order = sorted(range(len(items)), key=lambda k: (-item_cost(items[k]), str(fit_key(items[k])), items[k][0]))
     if seq_workers <= 1 or len(order) <= 1:
-        for ix in order:
-            run_group(ix)
+        for k in order:
+            run_one(k)
     else:
         from concurrent.futures import ThreadPoolExecutor
-        from . import capi
-        capi.load_library()                                             # dlopen once, before the threads
-        for v in sorted({items[k][2] for k in range(len(items))}):      # decode every clip once, up front
-            cfg = sequence_config(base, polygons, v, items[0][3], videos_path, truth_path)
-            seq_mod.read_clip(seq_mod.resolve_path(cfg["input_video"]), cfg.get("resize_factor") or 1)
-            seq_mod.read_clip(seq_mod.resolve_path(cfg["input_truth"]), cfg.get("resize_factor") or 1)
+        if not resident:
+            for v in videos:                                            # decode every clip once, up front
+                cfg = sequence_config(base, polygons, v, items[0][3], videos_path, truth_path)
+                seq_mod.read_clip(seq_mod.resolve_path(cfg["input_video"]), cfg.get("resize_factor") or 1)
+                seq_mod.read_clip(seq_mod.resolve_path(cfg["input_truth"]), cfg.get("resize_factor") or 1)
         with ThreadPoolExecutor(max_workers=seq_workers) as pool:
-            for f in [pool.submit(run_group, ix) for ix in order]:
+            for f in [pool.submit(run_one, k) for k in order]:
                 f.result()
+    for c in clips.values():
+        c.close()
     return out
 
 
@@ -213,7 +235,7 @@ def results_table(all_rows, videos=None, hyper=None):
 
 
 def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, out_csv=None, backend=None,
-        train_jobs=None, log=None, seq_workers=None):
+        train_jobs=None, log=None, seq_workers=None, resident=True):
     """Entry point used by benchmark.py / bench.py --workload sweep.  Reads RANK / WORLD_SIZE /
     LOCAL_RANK; returns (summary dict, table or None) -- the table on rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -250,7 +272,7 @@ def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, ou
     stages.reset()
     t0 = time.time()
     local = run_shard(shards[rank], base, polygons, device=local_rank, max_frames=max_frames, train_jobs=train_jobs,
-                      seq_workers=seq_workers,
+                      seq_workers=seq_workers, resident=resident,
                       progress=(lambda k, n, sid, r: log("[rank %d] %d/%d seq %d iou %.3f %.2fs (train %.2fs, decode %.2fs, wall %.2fs)" %
                                                          (rank, k, n, sid, r["mean_iou"], r["seconds"], r["train_seconds"],
                                                           r["decode_seconds"], r["wall_seconds"])))

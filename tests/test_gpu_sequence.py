@@ -70,3 +70,47 @@ def test_sweep_single_rank_smoke(tmp_path):
     for v in sweep.VIDEOS:
         assert 0.0 <= table.loc[0, v + "_benchmark"] <= 1.0 and table.loc[0, v + "_time"] > 0
     assert "avg_benchmark" in table.columns and os.path.isfile(out)
+
+
+@pytest.mark.parametrize("video,over_seg,novelty,features", [("soldier", "quickshift", False, "8 hsv_lab"),
+                                                              ("bmx", "felzenszwalb", True, "6 lab"),
+                                                              ("worm", "quickshift", True, "6 lab")])
+def test_clip_resident_sequence_equals_the_per_frame_path(video, over_seg, novelty, features):
+    """pcm.fastseq (device-resident clip, precomputed boxes and label maps, asynchronous frames -- what the sweep
+    runs) gives the per-frame IoUs of pcm.sequence.run_sequence (the main.py flow through Masker.update)."""
+    from pcm import fastseq, sweep
+    with open(os.path.join(PKG, "config_benchmark.yaml")) as f:
+        base = yaml.full_load(f)
+    base["tracker_provider"] = "truth"
+    params = dict(n_estimators=20, max_depth=7, n_components=1, novelty_detection=novelty, over_segmentation=over_seg,
+                  features=features, dilation_kernel=7, prior_weight=0.0)
+    cfg = sweep.sequence_config(base, polygons(), video, params, "Input/SegTrack2/Video", "Input/SegTrack2/Truth")
+    n = 40
+    want = run_sequence(cfg, max_frames=n)
+    clip = fastseq.ClipContext(cfg["input_video"], cfg["input_truth"], 1, 0, max_frames=n)
+    got = fastseq.run_sequence_fast(cfg, clip)
+    again = fastseq.run_sequence_fast(cfg, clip, model_cache=sweep.ModelCache(), cache_tag=video)
+    clip.close()
+    assert got["n_frames"] == want["n_frames"] and got["tracker"] == want["tracker"] == "truth"
+    assert np.array_equal(np.asarray(got["iou"]), np.asarray(want["iou"]), equal_nan=True)
+    assert np.array_equal(np.asarray(again["iou"]), np.asarray(want["iou"]), equal_nan=True)
+    assert got["mean_iou"] == want["mean_iou"]
+
+
+def test_clip_resident_sequence_with_sift_prior():
+    """prior_weight = 0.1: the FLANN kd-tree matcher of the reference (:139-141) is randomised, so two runs of the SAME
+    path differ in a few matches; the two drivers must agree to within that noise."""
+    from pcm import fastseq, sweep
+    with open(os.path.join(PKG, "config_benchmark.yaml")) as f:
+        base = yaml.full_load(f)
+    base["tracker_provider"] = "truth"
+    params = dict(n_estimators=20, max_depth=7, n_components=1, novelty_detection=False, over_segmentation="quickshift",
+                  features="6 lab", dilation_kernel=7, prior_weight=0.1)
+    cfg = sweep.sequence_config(base, polygons(), "soldier", params, "Input/SegTrack2/Video", "Input/SegTrack2/Truth")
+    want = run_sequence(cfg)
+    clip = fastseq.ClipContext(cfg["input_video"], cfg["input_truth"], 1, 0)
+    got = fastseq.run_sequence_fast(cfg, clip)
+    clip.close()
+    assert len(got["iou"]) == len(want["iou"])
+    assert abs(got["mean_iou"] - want["mean_iou"]) < 0.02
+    assert got["iou"][0] == want["iou"][0]              # frame 0 has no prior
