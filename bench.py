@@ -293,6 +293,12 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cores_available": os.cpu_count(),
     }
+    if not args.no_sweep:
+        log("[reference] sampling the CPU port of the sweep ...")
+        try:
+            out["sweep"] = cpu_sweep_sample(cores)
+        except Exception as e:
+            out["sweep"] = {"error": "%s: %s" % (type(e).__name__, e)}
     return out
 
 
@@ -346,8 +352,10 @@ def run_b200(args, rank, world, local_rank):
     n_total = args.steps + args.warmup
     d_counts = torch.zeros((n_total, 2), dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream()
-    h.set_stream(stream.cuda_stream)
+    # the handle's PRIVATE stream: only there may the next frame's colour conversion start under the previous frame's
+    # last kernels (K0 "early" under programmatic dependent launch); events are recorded on it through an ExternalStream
+    h.use_own_stream()
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
     frame_bytes = HEIGHT * WIDTH * 3
 
     def device_step(s):
@@ -361,6 +369,7 @@ def run_b200(args, rank, world, local_rank):
                      d_counts.data_ptr() + 16 * s)
 
     def barrier():
+        h.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -493,6 +502,26 @@ def run_b200(args, rank, world, local_rank):
                          "frames/s by pixel count; the reference path is single-threaded" % (reps, sw, sh, tt),
                "host_cores_available": os.cpu_count()}
 
+    # ---- the other BASELINE.json configs, timed on rank 0 (extra keys of the line) ----------------------------
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        h.synchronize()
+        for name, fn in (("default_quickshift_1080p", lambda: extra_quickshift_1080p(h, d_frames, d_truth, d_mask, NF, args)),
+                         ("config4_4k", lambda: extra_config_4k(local_rank, args)),
+                         ("config0_soldier", lambda: extra_config0_soldier(local_rank))):
+            t0 = time.time()
+            try:
+                extras[name] = fn()
+            except Exception as e:            # an extra must never take the headline down with it
+                extras[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+            log("[extra] %s: %.1f s" % (name, time.time() - t0))
+    if cpu is not None and not args.no_sweep:
+        log("[cpu_baseline] sampling the CPU port of the sweep ...")
+        try:
+            cpu["sweep"] = cpu_sweep_sample(max(1, os.cpu_count() or 1))
+        except Exception as e:
+            cpu["sweep"] = {"error": "%s: %s" % (type(e).__name__, e)}
+
     # ---- second half of BASELINE.json's metric: the benchmark.py grid sweep, sharded over the ranks ----
     sweep_rec = None
     if not args.no_sweep:
@@ -508,10 +537,217 @@ def run_b200(args, rank, world, local_rank):
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "mean_iou_vs_truth": mean_iou, "impl": "b200", "sweep": sweep_rec,
         }
+        out.update(extras)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return out
+
+
+
+# ---------------------------------------------------------------------------------------
+# the other BASELINE.json configs (extra keys; the headline stays configs[1])
+# ---------------------------------------------------------------------------------------
+def extra_quickshift_1080p(h, d_frames, d_truth, d_mask, NF, args):
+    """configs[1] with the reference's DEFAULT over-segmentation (config.yaml:29 quickshift) instead of the cached
+    16x16 grid labels: per frame pcm_quickshift_device (12-13 k segments at 1080p) + the K-chain + IoU, device resident."""
+    import torch
+    from pcm import capi
+    dev = d_frames.device
+    rect = (0, 0, WIDTH, HEIGHT)
+    noise = torch.from_numpy(np.random.RandomState(42).normal(scale=0.00001, size=(HEIGHT, WIDTH))).to(dev)
+    d_labels = torch.empty((HEIGHT, WIDTH), dtype=torch.int32, device=dev)
+    n_steps = min(args.steps, 40)
+    d_counts = torch.zeros((n_steps + 3, 2), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    fb, S_seen = HEIGHT * WIDTH * 3, []
+
+    def step(s):
+        cur, nxt, w0, w1 = sequence_state(s % SEQ_FRAMES, MODEL_FRAMES)
+        p = capi.Handle.make_params(cur, nxt, w0, w1, novelty=False, dilation_kernel=7, outlier_threshold=0.0, prior_weight=0.0)
+        f = s % NF
+        S = h.quickshift_device(d_frames.data_ptr() + f * fb, HEIGHT, WIDTH, WIDTH * 3, rect, 0.5, 3, 6, noise.data_ptr(),
+                                d_labels.data_ptr())
+        S_seen.append(S)
+        h.update_device(d_frames.data_ptr() + f * fb, HEIGHT, WIDTH, WIDTH * 3, rect, d_labels.data_ptr(), S, 0, p,
+                        d_mask.data_ptr(), WIDTH)
+        h.iou_device(d_mask.data_ptr(), WIDTH, d_truth.data_ptr() + f * HEIGHT * WIDTH, WIDTH, 1, HEIGHT, WIDTH,
+                     d_counts.data_ptr() + 16 * s)
+    for s in range(3):
+        step(s)
+    h.synchronize()
+    t0 = time.perf_counter()
+    for s in range(3, 3 + n_steps):
+        step(s)
+    h.synchronize()
+    dt = time.perf_counter() - t0
+    c = d_counts.cpu().numpy()[3:]
+    return {"value": n_steps / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / n_steps, "steps": n_steps,
+            "segments_per_frame": int(np.mean(S_seen)), "mean_iou_vs_truth": float(np.mean(c[:, 0] / np.maximum(c[:, 1], 1))),
+            "note": "device-resident; quickshift(kernel_size=3, max_dist=6, ratio=0.5) on the GPU every frame (one host sync per "
+                    "frame for the segment count) + colour planes + forests + decision + dilation + IoU"}
+
+
+def extra_config_4k(device, args):
+    """BASELINE.json configs[4]: synthetic 3840x2160, FOUR targets (one masker each, 800x600 boxes -> 840x640 crops, shared
+    mask, main.py:130-164,286-343), 100 frames, default params, three blended models per target."""
+    import cv2 as cv
+    import torch
+    from maskers import getMaskerByName
+    from pcm import capi
+    from pcm.synthetic import SyntheticSequence
+    W4, H4, NT, NG, STEPS = 3840, 2160, 4, 8, 100
+    dev = torch.device("cuda", device)
+    seq = SyntheticSequence(W4, H4, NG, seed=1, n_targets=NT)
+    frames = [seq.frame(i) for i in range(NG)]
+    truths = [seq.truth(i) for i in range(NG)]
+    sel_frames, n_frames = [0, 3, 6], [0, 33, 66]
+    seg = CachedGrid(16)
+    maskers, boxes = [], []
+    for t in range(NT):
+        m = getMaskerByName("PC", debug=False, frame=frames[0], config=CONFIG, poly_roi=seq.polygon(t, 0), update_mask=False,
+                            segment_fn=seg, device=device)
+        for f, nf in zip(sel_frames, n_frames):
+            poly = seq.polygon(t, f)
+            m.addModel(frame=frames[f], poly_roi=poly, bbox=cv.boundingRect(np.array(poly, np.int32)), bbox_roni=seq.roni(), n_frame=nf)
+        maskers.append(m)
+        cx, cy = seq.centres[t][0]
+        boxes.append((int(min(max(cx - 400, 0), W4 - 800)), int(min(max(cy - 300, 0), H4 - 600)), 800, 600))
+    rects = [capi.crop_rect(b, H4, W4) for b in boxes]
+    labels = [seg(frames[0][r[1]:r[1] + r[3], r[0]:r[0] + r[2]]) for r in rects]
+    d_frames = torch.from_numpy(np.stack(frames)).to(dev)
+    d_truth = torch.from_numpy(np.stack(truths)).to(dev)
+    d_labels = [torch.from_numpy(l).to(dev) for l in labels]
+    d_mask = torch.zeros((H4, W4), dtype=torch.uint8, device=dev)
+    d_counts = torch.zeros((STEPS + 3, NT, 2), dtype=torch.int64, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    for m in maskers:
+        m.native.set_stream(stream.cuda_stream)
+    fb = H4 * W4 * 3
+
+    def dev_step(s):
+        f = s % NG
+        with torch.cuda.stream(stream):
+            d_mask.zero_()
+        for t, m in enumerate(maskers):
+            m.index = (s - 3) % STEPS if s >= 3 else 0
+            m.current_model = sequence_state(m.index, n_frames)[0]
+            m.update_resident(d_frames.data_ptr() + f * fb, H4, W4, W4 * 3, rects[t], d_labels[t].data_ptr(),
+                              int(labels[t].max()) + 1, 0, d_mask.data_ptr(), W4)
+            m.native.iou_device(d_mask.data_ptr(), W4, d_truth.data_ptr() + f * H4 * W4, W4, 1, H4, W4,
+                                d_counts.data_ptr() + 16 * (s * NT + t))
+    for s in range(3):
+        dev_step(s)
+    stream.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for s in range(3, 3 + STEPS):
+        dev_step(s)
+    e1.record(stream)
+    stream.synchronize()
+    ms = e0.elapsed_time(e1)
+    c = d_counts.cpu().numpy()[3:]
+    for m in maskers:
+        m.native.use_own_stream()
+    # end to end: Masker.update x 4 + IoU x 4 per frame with host buffers
+    mask_h = np.zeros_like(frames[0])
+    E2E = 12
+
+    def host_step(s):
+        f = s % NG
+        mask_h[:, :, 2] = 0
+        for t, m in enumerate(maskers):
+            m.index = s % STEPS
+            m.current_model = sequence_state(m.index, n_frames)[0]
+            m.update(bbox=boxes[t], frame=frames[f], mask=mask_h, color=(0, 0, 255))
+            m.native.iou_counts(mask_h[:, :, 2], truths[f])
+    host_step(0)
+    t0 = time.perf_counter()
+    for s in range(E2E):
+        host_step(s)
+    e2e_s = time.perf_counter() - t0
+    for m in maskers:
+        m.close()
+    px = sum(r[2] * r[3] for r in rects)
+    return {"value": STEPS / (ms / 1e3), "unit": "frames/s", "ms_per_step": ms / STEPS, "steps": STEPS,
+            "targets": NT, "crop_px_per_frame": px, "updates_per_s": NT * STEPS / (ms / 1e3),
+            "e2e": {"value": E2E / e2e_s, "unit": "frames/s", "steps": E2E},
+            "mean_iou_vs_truth": float(np.mean(c[..., 0] / np.maximum(c[..., 1], 1))),
+            "note": "device-resident value: per frame 4 x (K0..K3 on an 840x640 crop) + 4 x IoU over the whole 4K frame, one "
+                    "stream; %d distinct 4K frames (%.0f MB) cycled over 100 steps" % (NG, NG * fb / 1e6)}
+
+
+def extra_config0_soldier(device):
+    """BASELINE.json configs[0]: SegTrack2 soldier through the main.py flow with the default config.yaml (quickshift on the
+    GPU, 4 blended models, host buffers through Masker.update)."""
+    from pcm.sequence import load_config, run_sequence
+    out = {}
+    for provider in ("auto", "truth"):
+        cfg = load_config(os.path.join(PKG, "config.yaml"))
+        cfg["tracker_provider"] = provider
+        run_sequence(cfg, device=device)                      # warm-up (library load, first-touch allocations)
+        r = run_sequence(cfg, device=device)
+        out[provider] = {"frames_per_s": r["n_frames"] / r["seconds"], "seconds": r["seconds"], "n_frames": r["n_frames"],
+                         "mean_iou": r["mean_iou"], "tracker": r["tracker"], "train_seconds": r["train_seconds"]}
+    return {"value": out["truth"]["frames_per_s"], "unit": "frames/s", "by_tracker_provider": out,
+            "note": "main.py flow (pcm.sequence.run_sequence), 528x224 clip, 32 frames; `auto` = OpenCV tracker available in this "
+                    "image (the reference's cv.legacy CSRT is not), `truth` = boxes from the ground-truth clip (no tracker cost)"}
+
+
+def cpu_sweep_sample(cores):
+    """CPU arm of the grid sweep on a bounded sample.  The reference runs every (hyper-parameters, clip) as a
+    `python main.py cfg out` subprocess on a ThreadPool(cpu_count) (benchmark.py:16-24,63-84); here the CPU port
+    oracle/ref_sequence.py is launched the same way for TWO opposite corners of the hyper-parameter grid per clip (all six
+    binary factors low / all high: for a cost that is additive in the factors their mean is the grid mean), truncated to a few
+    frames; a sequence's full cost is extrapolated as (imports + JIT + training) + frames * seconds per frame, and the
+    sweep as the sum over the 256 sequences divided by the cores (perfect packing: optimistic for the CPU)."""
+    import tempfile
+    import yaml
+    from multiprocessing.pool import ThreadPool
+    from pcm import sweep
+    with open(os.path.join(PKG, "config_benchmark.yaml")) as f:
+        base = yaml.full_load(f)
+    with open(os.path.join(PKG, "polygons.yaml")) as f:
+        polygons = yaml.full_load(f)
+    lo = dict(n_estimators=20, max_depth=7, n_components=1, novelty_detection=False, over_segmentation="felzenszwalb",
+              features="6 lab", dilation_kernel=7, prior_weight=0.0)
+    hi = dict(n_estimators=30, max_depth=10, n_components=1, novelty_detection=True, over_segmentation="quickshift",
+              features="8 hsv_lab", dilation_kernel=7, prior_weight=0.1)
+    K = 4
+    tmp = tempfile.mkdtemp(prefix="pcm_cpu_sweep_")
+    jobs = []
+    for v in sweep.VIDEOS:
+        for tag, prm in (("lo", lo), ("hi", hi)):
+            cfg = sweep.sequence_config(base, polygons, v, prm, os.path.join(PKG, "Input/SegTrack2/Video"),
+                                        os.path.join(PKG, "Input/SegTrack2/Truth"))
+            cp, op = os.path.join(tmp, "config-%s-%s.yaml" % (tag, v)), os.path.join(tmp, "results-%s-%s.csv" % (tag, v))
+            with open(cp, "w") as f:
+                yaml.dump(cfg, f)
+            jobs.append((v, tag, cp, op))
+
+    def run(job):
+        v, tag, cp, op = job
+        subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_sequence.py"), cp, op, str(K)],
+                       capture_output=True, text=True, timeout=900)
+        l1, l2 = open(op).read().split("\n")[:2]
+        secs = float(l1.split(";")[1])
+        t_imp, t_train, n = l2.split(";")
+        return v, tag, float(t_imp) + float(t_train), secs / int(n)
+    t0 = time.time()
+    with ThreadPool(min(cores, len(jobs))) as pool:
+        res = pool.map(run, jobs)
+    wall = time.time() - t0
+    core_s, detail = 0.0, {}
+    for v, tag, fixed, per_frame in res:
+        full = fixed + sweep.CLIP_FRAMES[v] * per_frame
+        core_s += 32 * full
+        detail["%s_%s" % (v, tag)] = {"fixed_s": round(fixed, 2), "s_per_frame": round(per_frame, 3), "sequence_s": round(full, 1)}
+    return {"value": 256 / (core_s / cores), "unit": "sequences/s", "cores": cores, "kind": "port",
+            "core_seconds_256_sequences": core_s, "sample_wall_s": wall, "per_sequence": detail,
+            "sample": "8 sequences (4 clips x the all-low / all-high corners of the hyper-parameter grid), %d frames each, as "
+                      "concurrent `python oracle/ref_sequence.py cfg out` subprocesses (the reference's benchmark.py launches "
+                      "`python main.py cfg out` the same way); extrapolated to full clips and 256 sequences" % K}
 
 
 def sweep_run(args, rank, world):
@@ -575,6 +811,7 @@ def main():
     ap.add_argument("--e2e-only", action="store_true", help="tuning aid: shorten the device-resident leg")
     ap.add_argument("--workload", default="1080p", choices=["1080p", "sweep"],
                     help="1080p: frames/s (default, the driver's metric); sweep: benchmark.py grid, sequences/s")
+    ap.add_argument("--no-extras", action="store_true", help="skip the 4K / soldier / quickshift-1080p extra keys")
     ap.add_argument("--no-sweep", action="store_true", help="skip the grid-sweep sub-record of the default workload")
     ap.add_argument("--sweep-limit", type=int, default=0, help="only the first N sequences of the 256")
     ap.add_argument("--sweep-max-frames", type=int, default=0)

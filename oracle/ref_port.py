@@ -198,6 +198,32 @@ class RefPortMasker:
         return None
 
 
+class SiftFlannPrior:
+    """Port of computePriors (:129-163) for `prior_fn`: cv.SIFT on the previous crop (inside the previous mask) and on
+    the current crop, FLANN kd-tree 2-NN (algorithm 1, trees 5, checks 50, :40-43), Lowe ratio 0.7, matches farther
+    than the 90th percentile of the displacement dropped, +1 for the superpixel under every surviving keypoint."""
+
+    def __init__(self):
+        self.sift = cv.SIFT_create()
+        self.flann = cv.FlannBasedMatcher(dict(algorithm=1, trees=5), dict(checks=50))
+
+    def __call__(self, masker, crop, segments, labels):
+        priors = np.full(labels.shape, -1, np.float32)
+        kp1, des1 = self.sift.detectAndCompute(np.ascontiguousarray(masker.prevFrame), np.ascontiguousarray(masker.prevForegroundMask))
+        kp2, des2 = self.sift.detectAndCompute(np.ascontiguousarray(crop), None)
+        if len(kp1) == 0 or len(kp2) < 2:          # the reference unpacks (m, n) pairs and needs two neighbours
+            return priors
+        good = [pair[0] for pair in self.flann.knnMatch(des1, des2, k=2) if len(pair) == 2 and pair[0].distance < 0.7 * pair[1].distance]
+        if not good:
+            return priors
+        dist = np.array([((kp2[m.trainIdx].pt[0] - kp1[m.queryIdx].pt[0]) ** 2 +
+                          (kp2[m.trainIdx].pt[1] - kp1[m.queryIdx].pt[1]) ** 2) ** 0.5 for m in good])
+        thr = np.percentile(dist, 90)
+        for m in np.array(good)[dist <= thr]:
+            priors[segments[int(kp2[m.trainIdx].pt[1]), int(kp2[m.trainIdx].pt[0])]] = 1
+        return priors
+
+
 def compute_benchmark(mask, truth):
     """benchmark.py:8-14 (np.bool there; removed from numpy>=1.24 except as alias in 2.x)."""
     bm, bt = mask.astype(bool), truth.astype(bool)

@@ -59,17 +59,30 @@ SEQUENCES = {
         params=dict(n_estimators=20, max_depth=5, n_components=1, novelty_detection=False,
                     over_segmentation="quickshift", features="8 hsv_lab", dilation_kernel=7, prior_weight=0.0)),
     "parachute_novelty": dict(
-        video="parachute", multi_selection=True, segments="voronoi:120", n_frames=24, dump=[0, 5, 16, 20],
+        video="parachute", multi_selection=True, segments="voronoi:120", n_frames=50, dump=[0, 5, 16, 20, 44],
         params=dict(n_estimators=30, max_depth=10, n_components=1, novelty_detection=True,
                     over_segmentation="felzenszwalb", features="6 lab", dilation_kernel=7, prior_weight=0.0)),
+    # 200 frames: model 1 -> 2 blended over frames 0..92, 2 -> 3 over 93..185, the third model alone from 186 on
     "frog_sweep": dict(
-        video="frog", multi_selection=True, segments="voronoi:150", n_frames=14, dump=[0, 9],
+        video="frog", multi_selection=True, segments="voronoi:150", n_frames=200, dump=[0, 9, 120, 190],
         params=dict(n_estimators=30, max_depth=7, n_components=1, novelty_detection=True,
                     over_segmentation="felzenszwalb", features="8 hsv_lab", dilation_kernel=7, prior_weight=0.0)),
     "worm_rgb3": dict(
-        video="worm", multi_selection=False, segments="grid:5", n_frames=6, dump=[0, 3],
+        video="worm", multi_selection=False, segments="grid:5", n_frames=30, dump=[0, 3, 22],
         params=dict(n_estimators=8, max_depth=7, n_components=1, novelty_detection=False,
                     over_segmentation="SLIC", features="3 rgb", dilation_kernel=4, prior_weight=0.0)),
+    # the fifth clip of the reference's sweep (benchmark.py:41), whole clip, three blended models
+    "bmx_sweep": dict(
+        video="bmx", multi_selection=True, segments="voronoi:260", n_frames=36, dump=[0, 13, 30],
+        params=dict(n_estimators=20, max_depth=7, n_components=1, novelty_detection=True,
+                    over_segmentation="quickshift", features="6 lab", dilation_kernel=7, prior_weight=0.0)),
+    # the prior_weight = 0.1 half of the sweep (benchmark.py:50; computePriors :129-163).  The reference's FLANN
+    # kd-tree matcher is randomised (two runs give different matches), so the priors of THIS run are recorded for
+    # every frame and the parity tests inject them.
+    "soldier_prior": dict(
+        video="soldier", multi_selection=True, segments="grid:8", n_frames=32, dump=[1, 11, 25], record_priors=True,
+        params=dict(n_estimators=20, max_depth=7, n_components=1, novelty_detection=False,
+                    over_segmentation="quickshift", features="6 lab", dilation_kernel=7, prior_weight=0.1)),
 }
 
 
@@ -95,6 +108,14 @@ def run_sequence(name, spec, ref_maskers, ref_benchmark, polygons):
                         priors=np.asarray(kw["priors"]).copy(), thr=float(kw["outlier_threshold"]),
                         pre=kw["mask"][b[1]:b[1] + b[3], b[0]:b[0] + b[2], 2].copy())
     cls.compileSaliencyMap = staticmethod(spy)
+    orig_priors = cls.computePriors
+    recorded_priors = []
+
+    def spy_priors(self, crop_frame, segments, labels):
+        pr = orig_priors(self, crop_frame, segments, labels)
+        recorded_priors.append(np.asarray(pr, np.float32).copy())
+        return pr
+    cls.computePriors = spy_priors
     try:
         m = ref_maskers.getMaskerByName("PC", debug=False, frame=frames[0], config=config,
                                         poly_roi=pts[0], update_mask=False)
@@ -146,6 +167,11 @@ def run_sequence(name, spec, ref_maskers, ref_benchmark, polygons):
                 out["f%d_rect" % i] = np.array([x0, y0, x1 - x0, y1 - y0], np.int32)
                 out["f%d_thr" % i] = np.float64(captured["thr"])
                 assert captured["pre"].shape == (y1 - y0, x1 - x0)
+        if spec.get("record_priors"):
+            assert len(recorded_priors) == spec["n_frames"]
+            for i, pr in enumerate(recorded_priors):
+                out["pri%d" % i] = pr
+            out["priors_recorded"] = np.int64(1)
         out["bbox"] = np.array(per["bbox"], np.int32)
         out["ret"] = np.array(per["ret"], np.int32)
         out["fg"] = np.array(per["fg"], np.int64)
@@ -163,6 +189,7 @@ def run_sequence(name, spec, ref_maskers, ref_benchmark, polygons):
         print(name, "mean IoU %.4f" % np.nanmean(per["iou"]), "rets", [r for r in per["ret"] if r >= 0])
     finally:
         cls.compileSaliencyMap = staticmethod(orig)
+        cls.computePriors = orig_priors
     np.savez_compressed(os.path.join(HERE, "seq_%s.npz" % name), **out)
 
 

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "non-rigid-object-tracking_b200")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-SEQ_NAMES = ["soldier_default", "parachute_novelty", "worm_rgb3", "frog_sweep"]
+SEQ_NAMES = ["soldier_default", "parachute_novelty", "worm_rgb3", "frog_sweep", "bmx_sweep", "soldier_prior"]
 
 
 def sha1(a):
@@ -70,6 +70,26 @@ class GoldenSeq:
     def novelty_threshold(self, m):
         return float(self.z["m%d_threshold_novelty" % m])
 
+    def has_recorded_priors(self):
+        return "priors_recorded" in self.z
+
+    def recorded_priors(self, i):
+        """Priors the reference's computePriors returned at frame i (its FLANN matcher is randomised, so the golden
+        run's priors are injected wherever a sequence with prior_weight != 0 is replayed)."""
+        return self.z["pri%d" % i]
+
+    def sample_frames(self, budget=28):
+        """Frames for the (slow) CPU port: everything for short goldens, else the start, both sides of every model
+        switch, the dumped frames and an even sprinkling -- per-frame results depend on (index, current model) only."""
+        n = self.meta["n_frames"]
+        if n <= budget or self.has_recorded_priors():
+            return list(range(n))
+        keep = set(range(6)) | set(self.meta["dump"]) | {n - 1}
+        for f in self.model_frames()[1:]:
+            keep |= {f - 2, f - 1, f, f + 1}
+        keep |= set(np.linspace(0, n - 1, 8).astype(int).tolist())
+        return sorted(k for k in keep if 0 <= k < n)
+
     def model_frames(self):
         return self.meta["pts_frame_numbers"][:self.n_models]
 
@@ -96,6 +116,8 @@ def native_masker_from_golden(g, device=0, **kw):
     from pcm.providers import make_segment_provider
     m = getMaskerByName("PC", debug=False, frame=g.frames[0], config=g.config, poly_roi=None, update_mask=False,
                         segment_fn=make_segment_provider(g.meta["segments"]), device=device, **kw)
+    if g.has_recorded_priors():
+        m.prior_fn = lambda *a, **k: g.recorded_priors(m.index)
     m.native.set_debug(True)
     for s in range(g.n_models):
         idx = m.native.add_model_arrays(g.model_frames()[s], g.tree_arrays(s))

@@ -24,7 +24,7 @@ def test_sequence_state_follows_the_reference_schedule():
 
 def test_reference_arm_prints_one_json_line():
     env = dict(os.environ, PCM_REF_CORES="2")
-    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--no-sweep"],
                          capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.strip()]
@@ -46,3 +46,26 @@ def test_default_arm_has_no_cpu_fallback():
                          timeout=300, cwd=ROOT)
     assert res.returncode != 0 and "no CUDA device" in (res.stderr + res.stdout)
     assert not res.stdout.strip(), "nothing may be reported without a GPU"
+
+
+def test_cpu_sequence_port_runs_like_main_py(tmp_path):
+    """oracle/ref_sequence.py (the CPU arm of the sweep that bench.py samples): `script CONFIG RESULT [frames]` writes the
+    reference's "{mean IoU};{seconds}" result line (main.py:366-368) plus the timing detail bench.py extrapolates from."""
+    import yaml
+    from helpers import PKG, polygons
+    from pcm import sweep
+    base = yaml.full_load(open(os.path.join(PKG, "config_benchmark.yaml")))
+    prm = dict(n_estimators=20, max_depth=7, n_components=1, novelty_detection=False, over_segmentation="felzenszwalb",
+               features="6 lab", dilation_kernel=7, prior_weight=0.1)
+    cfg = sweep.sequence_config(base, polygons(), "soldier", prm, os.path.join(PKG, "Input/SegTrack2/Video"),
+                                os.path.join(PKG, "Input/SegTrack2/Truth"))
+    cp, op = tmp_path / "config-0-soldier.yaml", tmp_path / "results-0-soldier.csv"
+    yaml.dump(cfg, open(cp, "w"))
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_sequence.py"), str(cp), str(op), "2"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    l1, l2 = open(op).read().split("\n")
+    iou, secs = map(float, l1.split(";"))
+    assert 0.3 < iou <= 1.0 and secs > 0
+    t_imp, t_train, n = l2.split(";")
+    assert float(t_imp) > 0 and float(t_train) > 0 and int(n) == 2

@@ -99,7 +99,9 @@ def test_port_reproduces_reference_sequence(name):
     poly = polygons()[g.meta["video"]]
     pts, ronis = poly["pts"][0], poly["bboxes_roni"][0]
     m = RefPortMasker(debug=False, frame=g.frames[0], config=g.config, poly_roi=pts[0],
-                      segment_fn=make_segment_provider(g.meta["segments"]))
+                      segment_fn=make_segment_provider(g.meta["segments"]),
+                      prior_fn=(lambda self_, crop, segs, labels: g.recorded_priors(self_.index))
+                      if g.has_recorded_priors() else None)
     for s in range(g.n_models):
         fn = g.model_frames()[s]
         m.addModel(frame=g.frames[fn], poly_roi=pts[s], bbox=cv.boundingRect(np.array(pts[s])),
@@ -110,7 +112,8 @@ def test_port_reproduces_reference_sequence(name):
         for a, b in zip(got, want):
             for u, v in zip(a, b):
                 assert np.array_equal(u, v)
-    for i in range(g.meta["n_frames"]):
+    for i in g.sample_frames():
+        m.index, m.current_model = g.state_at(i)      # long goldens are sampled: the state is a function of the frame index
         mask = np.zeros_like(g.frames[i])
         ret = m.update(bbox=tuple(int(v) for v in g.z["bbox"][i]), frame=g.frames[i], mask=mask)
         assert (-1 if ret is None else ret) == int(g.z["ret"][i])
