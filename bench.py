@@ -796,6 +796,7 @@ def run_sweep(args, rank, world):
                                    "worm/bmx), sharded by forest group, one final all_gather" % summary["n_sequences"],
                        "per_rank_sequences": summary["per_rank_sequences"], "train_jobs": summary["train_jobs"], "seq_workers": summary["seq_workers"],
                        "max_frames": args.sweep_max_frames or None},
+            "per_stage_host_s": summary.get("per_stage_host_s_rank0"), "tracker_provider": summary.get("tracker_provider"),
             "mean_iou": float(np.nanmean(table["avg_benchmark"])) if table is not None else None, "impl": "b200"}
 
 

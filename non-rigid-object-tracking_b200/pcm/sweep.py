@@ -288,6 +288,9 @@ def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, ou
                    n_gpus=world, per_rank_sequences=[len(s) for s in shards], train_jobs=train_jobs,
                    seq_workers=seq_workers, host_cores=os.cpu_count(), tracker_provider=base.get("tracker_provider"),
                    rank0_seconds=t_local, per_stage_host_s_rank0={k: round(v, 3) for k, v in sorted(stages.snapshot().items())})
+    if log:
+        log("[rank %d] sweep %.2f s; host stage seconds (summed over %d sequence threads): %s" %
+            (rank, t_local, seq_workers, summary["per_stage_host_s_rank0"]))
     table = None
     if rank == 0:
         table = results_table(all_rows, videos, hyper)

@@ -30,8 +30,12 @@ def test_run_sequence_reproduces_reference_iou(name):
     if not g.frames_match():
         pytest.skip("video decoder output differs from the one the goldens were made with")
     n = g.meta["n_frames"]
+    prior_fn = None
+    if g.has_recorded_priors():            # the reference's FLANN matcher is randomised: replay the golden run's priors
+        calls = iter(range(1, n))
+        prior_fn = lambda *a, **k: g.recorded_priors(next(calls))
     r = run_sequence(_config(g), segment_fn=make_segment_provider(g.meta["segments"]), tracker_provider="truth",
-                     max_frames=n)
+                     max_frames=n, prior_fn=prior_fn)
     assert r["n_frames"] == n and r["n_updates"] == n and r["tracker"] == "truth"
     want = g.z["iou"]
     assert len(r["iou"]) == n
@@ -79,6 +83,7 @@ def test_clip_resident_sequence_equals_the_per_frame_path(video, over_seg, novel
     """pcm.fastseq (device-resident clip, precomputed boxes and label maps, asynchronous frames -- what the sweep
     runs) gives the per-frame IoUs of pcm.sequence.run_sequence (the main.py flow through Masker.update)."""
     from pcm import fastseq, sweep
+    from pcm.sequence import run_sequence
     with open(os.path.join(PKG, "config_benchmark.yaml")) as f:
         base = yaml.full_load(f)
     base["tracker_provider"] = "truth"
@@ -101,6 +106,7 @@ def test_clip_resident_sequence_with_sift_prior():
     """prior_weight = 0.1: the FLANN kd-tree matcher of the reference (:139-141) is randomised, so two runs of the SAME
     path differ in a few matches; the two drivers must agree to within that noise."""
     from pcm import fastseq, sweep
+    from pcm.sequence import run_sequence
     with open(os.path.join(PKG, "config_benchmark.yaml")) as f:
         base = yaml.full_load(f)
     base["tracker_provider"] = "truth"
