@@ -198,6 +198,24 @@ int pcm_felzenszwalb(const uint8_t* frame, int frame_h, int frame_w, int64_t fra
                      double scale, double sigma, int min_size, const double* kernel, int kernel_radius,
                      int32_t* labels_out, int* n_labels_out);
 
+/* ---- SIFT-match prior (computePriors :129-163), SURVEY.md §8 row f-2 -------- */
+
+/* Priors of one frame from the SIFT keypoints / descriptors the caller detected with OpenCV (host, once per clip
+ * frame) and uploaded: d_pts* = (x, y) float32 pairs in crop coordinates, d_des* = 128 uint8 per keypoint (OpenCV's
+ * float32 descriptors hold integers 0..255), 16-byte aligned.
+ *   previous crop: all keypoints of the UNMASKED detection; the mask filter of detectAndCompute(prev, prevMask) --
+ *                  keep mask[(int)(y + 0.5f)][(int)(x + 0.5f)] != 0 -- is applied here.  d_prev_mask points at the
+ *                  previous crop's top-left pixel inside the (device) mask plane, rows prev_mask_stride apart.
+ *   matching:      EXACT 2-nearest neighbours in squared L2 (ties to the smaller index) where the reference asks
+ *                  FLANN's randomised kd-trees for approximate ones; ratio test m.distance < 0.7 * n.distance on the
+ *                  float32 square roots (:147); displacement filter dist <= np.percentile(dist, 90) (:155-157)
+ *   output:        d_priors[n_labels] = -1, and +1 for labels[int(y)][int(x)] of every surviving current keypoint (:159-161)
+ * Fewer than one previous or two current keypoints: all -1, like the reference (:139).  Asynchronous. */
+int pcm_prior_device(pcm_handle* h, const float* d_pts_prev, const uint8_t* d_des_prev, int n_prev,
+                     const uint8_t* d_prev_mask, int64_t prev_mask_stride, int prev_w, int prev_h,
+                     const float* d_pts, const uint8_t* d_des, int n_cur, const int32_t* d_labels, int crop_w, int crop_h,
+                     int n_labels, float* d_priors);
+
 /* ---- training (addModel :166-228), SURVEY.md §8 row f-3 ------------------- */
 
 /* Grow, on the GPU, the trees that scikit-learn 1.9's

@@ -7,6 +7,7 @@
 #include "pcm_kernels.cuh"
 #include "pcm_quickshift.cuh"
 #include "pcm_forest_fit.cuh"
+#include "pcm_prior.cuh"
 #include "pcm_host.h"
 
 #include <cudaTypedefs.h>
@@ -241,6 +242,7 @@ struct pcm_handle {
 
     // forest training (pcm_fit_forest): feature-major rows resident between calls, scratch, outputs
     DevBuf fit_x, fit_xt, fit_y, fit_counts, fit_rand, fit_samples, fit_tmp, fit_out;
+    DevBuf prior_scratch;         // pcm_prior_device: per-keypoint match records
     long long fit_rows_id = 0;
     int fit_n = 0, fit_F = 0;
 
@@ -571,6 +573,7 @@ extern "C" void pcm_destroy(pcm_handle* h) {
     for (DevBuf* b : {&h->frame, &h->labels, &h->priors, &h->planes, &h->sched, &h->p1, &h->sa, &h->seg, &h->rmin, &h->rmax, &h->decision,
                       &h->scores, &h->flagged, &h->mask, &h->pre, &h->counts})
         b->release();
+    h->prior_scratch.release();
     for (DevBuf* b : {&h->fit_x, &h->fit_xt, &h->fit_y, &h->fit_counts, &h->fit_rand, &h->fit_samples, &h->fit_tmp, &h->fit_out})
         b->release();
     for (DevBuf* b : {&h->qs_lab, &h->qs_dens, &h->qs_noise, &h->qs_parent, &h->qs_root, &h->qs_flag, &h->qs_rank, &h->qs_sums,
@@ -1385,6 +1388,43 @@ extern "C" int pcm_felzenszwalb(const uint8_t* frame, int H, int W, int64_t stri
                                kernel_radius, labels_out);
     if (n < 0) return fail(PCM_E_INVALID, "pcm_felzenszwalb: bad arguments");
     if (n_labels_out) *n_labels_out = n;
+    return PCM_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// API: SIFT-match prior on the device
+// ---------------------------------------------------------------------------------
+extern "C" int pcm_prior_device(pcm_handle* h, const float* d_pts_prev, const uint8_t* d_des_prev, int n_prev,
+                                const uint8_t* d_prev_mask, int64_t prev_mask_stride, int prev_w, int prev_h,
+                                const float* d_pts, const uint8_t* d_des, int n_cur, const int32_t* d_labels, int crop_w,
+                                int crop_h, int n_labels, float* d_priors) {
+    if (!h || !d_labels || !d_priors) return fail(PCM_E_INVALID, "pcm_prior_device: NULL argument");
+    if (n_prev < 0 || n_cur < 0 || n_labels < 1 || crop_w < 1 || crop_h < 1 || prev_w < 1 || prev_h < 1)
+        return fail(PCM_E_INVALID, "pcm_prior_device: bad size");
+    if (n_prev > 0 && (!d_pts_prev || !d_des_prev || !d_prev_mask)) return fail(PCM_E_INVALID, "pcm_prior_device: NULL argument");
+    if (n_cur > 0 && (!d_pts || !d_des)) return fail(PCM_E_INVALID, "pcm_prior_device: NULL argument");
+    if (((uintptr_t)d_des_prev | (uintptr_t)d_des) & 15) return fail(PCM_E_INVALID, "pcm_prior_device: descriptors must be 16-byte aligned");
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->chain_tail = false;
+    cudaStream_t st = h->stream;
+    const size_t m1 = (size_t)std::max(n_prev, 1);
+    CUDA_TRY(h->prior_scratch.reserve(m1 * (2 * sizeof(double) + 2 * sizeof(int))));
+    char* sb = h->prior_scratch.as<char>();
+    PriorArgs a{};
+    a.pts1 = d_pts_prev; a.des1 = d_des_prev; a.m1 = n_prev;
+    a.prev_mask = d_prev_mask; a.prev_stride = prev_mask_stride; a.prev_w = prev_w; a.prev_h = prev_h;
+    a.pts2 = d_pts; a.des2 = d_des; a.m2 = n_cur;
+    a.labels = d_labels; a.cw = crop_w; a.ch = crop_h; a.n_labels = n_labels; a.priors = d_priors;
+    a.q_dist = reinterpret_cast<double*>(sb);
+    a.g_dist = a.q_dist + m1;
+    a.q_j = reinterpret_cast<int*>(a.g_dist + m1);
+    a.g_j = a.q_j + m1;
+    if (n_prev > 0) {
+        prior_match_kernel<<<(n_prev + 7) / 8, 256, 0, st>>>(a);
+        CHECK_LAUNCH(h, "prior_match_kernel");
+    }
+    prior_finish_kernel<<<1, 1024, 0, st>>>(a);
+    CHECK_LAUNCH(h, "prior_finish_kernel");
     return PCM_OK;
 }
 

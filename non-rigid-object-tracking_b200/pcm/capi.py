@@ -65,10 +65,12 @@ def load_library():
         "pcm_quickshift": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
         "pcm_quickshift_device": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
         "pcm_felzenszwalb": (I, [P, I, I, L, P, D, D, I, P, I, P, C.POINTER(I)]),
+        "pcm_prior_device": (I, [P, P, P, I, P, L, I, I, P, P, I, P, I, I, I, P]),
         "pcm_fit_rows": (I, [P, P, P, I, I, C.c_longlong]),
         "pcm_pca_moments": (I, [P, C.c_longlong, P, P, P]),
         "pcm_pca_residuals": (I, [P, C.c_longlong, P, P, P]),
         "pcm_fit_forest": (I, [P, P, P, I, I, C.c_longlong, I, I, I, P, P, I, P, P, P, P, P, P, P]),
+        "pcm_prior_device": (I, [P, P, P, I, P, L, I, I, P, P, I, P, I, I, I, P]),
         "pcm_fit_rows": (I, [P, P, P, I, I, C.c_longlong]),
         "pcm_pca_moments": (I, [P, C.c_longlong, P, P, P]),
         "pcm_pca_residuals": (I, [P, C.c_longlong, P, P, P]),
@@ -98,7 +100,7 @@ EXPORTED_SYMBOLS = [
     "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_use_own_stream", "pcm_get_stream", "pcm_synchronize",
     "pcm_set_features", "pcm_num_features", "pcm_add_model", "pcm_set_novelty", "pcm_num_models", "pcm_crop_rect",
     "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device", "pcm_felzenszwalb",
-    "pcm_fit_forest", "pcm_fit_rows", "pcm_pca_moments", "pcm_pca_residuals", "pcm_convert", "pcm_gather_features",
+    "pcm_prior_device", "pcm_fit_forest", "pcm_fit_rows", "pcm_pca_moments", "pcm_pca_residuals", "pcm_convert", "pcm_gather_features",
     "pcm_set_debug", "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_transfer_bytes", "pcm_set_label_cache", "pcm_profile_enable", "pcm_profile_read",
 ]
 
@@ -324,6 +326,14 @@ class Handle:
                                                    C.c_void_p(d_noise) if d_noise else None,
                                                    C.c_void_p(d_labels_out) if d_labels_out else None, C.byref(n)))
         return n.value
+
+    def prior_device(self, d_pts_prev, d_des_prev, n_prev, d_prev_mask, prev_stride, prev_w, prev_h, d_pts, d_des, n_cur,
+                     d_labels, crop_w, crop_h, n_labels, d_priors):
+        """SIFT-match priors of one frame on the device (pcm_prior_device; integers = device addresses); asynchronous."""
+        v = lambda x: C.c_void_p(x) if x else None
+        self._check(self.lib.pcm_prior_device(self._h, v(d_pts_prev), v(d_des_prev), int(n_prev), v(d_prev_mask), int(prev_stride),
+                                              int(prev_w), int(prev_h), v(d_pts), v(d_des), int(n_cur), v(d_labels),
+                                              int(crop_w), int(crop_h), int(n_labels), v(d_priors)))
 
     def update_device(self, d_frame, frame_h, frame_w, stride, rect, d_labels, n_labels, d_priors, params, d_mask,
                       mask_stride):

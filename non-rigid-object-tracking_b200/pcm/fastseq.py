@@ -163,6 +163,76 @@ class ClipContext:
         return arena
 
 
+class SiftStore:
+    """SIFT keypoints / descriptors of every crop of a box schedule: host arrays per entry and one device copy
+    (pts float32 [M, 2], descriptors uint8 [M, 128]) for pcm_prior_device."""
+
+    def __init__(self, pts, des, d_pts, d_des, offsets):
+        self.pts, self.des, self.d_pts, self.d_des, self.offsets = pts, des, d_pts, d_des, offsets
+
+    def count(self, k):
+        return self.offsets[k + 1] - self.offsets[k]
+
+    def pts_ptr(self, k):
+        return self.d_pts.data_ptr() + 8 * self.offsets[k]
+
+    def des_ptr(self, k):
+        return self.d_des.data_ptr() + 128 * self.offsets[k]
+
+
+_tls = threading.local()
+
+
+def _sift_detect(crop):
+    """cv.SIFT_create().detectAndCompute(crop, None) (:136) -> (pts float32 [m, 2], descriptors uint8 [m, 128])."""
+    if getattr(_tls, "sift", None) is None:
+        _tls.sift = cv.SIFT_create()
+    kps, des = _tls.sift.detectAndCompute(np.ascontiguousarray(crop), None)
+    pts = np.array([k.pt for k in kps], np.float32).reshape(-1, 2)
+    if des is None or len(kps) == 0:
+        return pts, np.zeros((0, 128), np.uint8)
+    d8 = des.astype(np.uint8)
+    if not np.array_equal(d8, des):
+        raise ValueError("SIFT descriptors are expected to hold integers 0..255")
+    return pts, d8
+
+
+def _clip_sift(self, box_key, rects, workers=4):
+    """SiftStore of the crops `rects` (computed once per clip and box schedule, frames in parallel)."""
+    torch = self.torch
+
+    def make():
+        from concurrent.futures import ThreadPoolExecutor
+        flat = [r for fr in rects for r in fr]
+        T = len(rects[0])
+        with stages.stage("sift_detect"):
+            def one(k):
+                x, y, w, h = flat[k]
+                t0 = time.perf_counter()
+                out = _sift_detect(self.frames[k // T][y:y + h, x:x + w])
+                stages.add("sift_detect_cpu", time.perf_counter() - t0)
+                return out
+            with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
+                res = list(pool.map(one, range(len(flat))))
+        offsets = [0]
+        for p, _ in res:
+            offsets.append(offsets[-1] + len(p))
+        M = max(offsets[-1], 1)
+        pts = np.zeros((M, 2), np.float32)
+        des = np.zeros((M, 128), np.uint8)
+        for k, (p, d) in enumerate(res):
+            pts[offsets[k]:offsets[k + 1]] = p
+            des[offsets[k]:offsets[k + 1]] = d
+        d_pts = torch.from_numpy(pts).to(self.dev)
+        d_des = torch.from_numpy(des).to(self.dev)
+        torch.cuda.synchronize(self.dev)
+        return SiftStore([r[0] for r in res], [r[1] for r in res], d_pts, d_des, offsets)
+    return self.once.get(("sift", box_key), make)
+
+
+ClipContext.sift = _clip_sift
+
+
 def _precomputable(config):
     if config.get("masker") != "PC" or config.get("manual_roi_selection"):
         return False
@@ -208,7 +278,12 @@ def run_sequence_fast(config, clip, device=0, model_cache=None, cache_tag=None, 
     switch_frames = [md["n_frame"] for md in maskers[0].models] if config.get("multi_selection") else [0]
     box_key, boxes, rects, tracker_name = clip.schedule(config, bboxes, switch_frames, tracker_provider)
     want_prior = params["prior_weight"] != 0.0
-    arena = clip.labels(params["over_segmentation"], box_key, rects, want_host=want_prior)
+    # prior_provider "gpu" (default): exact 2-NN matching and everything after it on the device (pcm_prior_device), SIFT
+    # detection once per clip frame on the host; "flann": the reference's own FLANN matcher on the host, per frame
+    gpu_prior = want_prior and (config.get("prior_provider") or "gpu") == "gpu"
+    host_prior = want_prior and not gpu_prior
+    arena = clip.labels(params["over_segmentation"], box_key, rects, want_host=host_prior)
+    sift = clip.sift(box_key, rects, workers=config.get("host_workers") or 4) if gpu_prior else None
     T = len(maskers)
     n, H, W = clip.n, clip.H, clip.W
     fb = H * W * 3
@@ -218,13 +293,25 @@ def run_sequence_fast(config, clip, device=0, model_cache=None, cache_tag=None, 
         d_mask = torch.zeros((H, W), dtype=torch.uint8, device=clip.dev)
         d_counts = torch.zeros((n * T, 2), dtype=torch.int64, device=clip.dev)
         d_priors = None
+        if gpu_prior:
+            d_pri = [torch.empty(max(arena.n_labels), dtype=torch.float32, device=clip.dev) for _ in range(T)]
         for m in maskers:
             m.native.set_stream(stream.cuda_stream)
         prev_rects = [None] * T
         prev_crops = [None] * T                         # the SAME array objects the prior saw one frame earlier (SiftPrior reuse)
         for index in range(n):
             prev_masks = None
-            if want_prior and index > 0:
+            if gpu_prior and index > 0:
+                # the priors of every target read the PREVIOUS frame's mask plane: queue them before it is cleared
+                for i in range(T):
+                    k, kp = index * T + i, (index - 1) * T + i
+                    x, y, w, h = rects[index][i]
+                    px, py, pw, ph = prev_rects[i]
+                    maskers[i].native.prior_device(sift.pts_ptr(kp), sift.des_ptr(kp), sift.count(kp),
+                                                   d_mask.data_ptr() + py * W + px, W, pw, ph,
+                                                   sift.pts_ptr(k), sift.des_ptr(k), sift.count(k),
+                                                   arena.ptr(k), w, h, arena.n_labels[k], d_pri[i].data_ptr())
+            if host_prior and index > 0:
                 with stages.stage("prior_mask_d2h"):
                     hm = d_mask.cpu().numpy()           # waits for the previous frame; its crops are the prevForegroundMasks
                 prev_masks = [hm[r[1]:r[1] + r[3], r[0]:r[0] + r[2]] for r in prev_rects]
@@ -234,9 +321,9 @@ def run_sequence_fast(config, clip, device=0, model_cache=None, cache_tag=None, 
                 rect = rects[index][i]
                 k = index * T + i
                 S = arena.n_labels[k]
-                pri_ptr = 0
+                pri_ptr = d_pri[i].data_ptr() if (gpu_prior and index > 0) else 0
                 m = maskers[i]
-                if want_prior:
+                if host_prior:
                     x, y, w, h = rect
                     crop = frames[index][y:y + h, x:x + w]
                 if prev_masks is not None:
@@ -250,7 +337,7 @@ def run_sequence_fast(config, clip, device=0, model_cache=None, cache_tag=None, 
                 m.update_resident(clip.d_frames.data_ptr() + index * fb, H, W, W * 3, rect, arena.ptr(k), S, pri_ptr,
                                   d_mask.data_ptr(), W)
                 prev_rects[i] = rect
-                if want_prior:
+                if host_prior:
                     prev_crops[i] = crop
                 if index < clip.n_truth:
                     m.native.iou_device(d_mask.data_ptr(), W, clip.d_truth.data_ptr() + index * H * W, W, 1, H, W,
