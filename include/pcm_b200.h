@@ -198,6 +198,34 @@ int pcm_felzenszwalb(const uint8_t* frame, int frame_h, int frame_w, int64_t fra
                      double scale, double sigma, int min_size, const double* kernel, int kernel_radius,
                      int32_t* labels_out, int* n_labels_out);
 
+/* ---- a whole sequence of frames in one call (main.py:280-343 for one target) ---- */
+
+/* One frame of a device-resident sequence: [priors from SIFT matches] -> [clear the mask plane] -> update -> [IoU].
+ * Every pointer is a device pointer; 0 / NULL switches the optional step off. */
+typedef struct pcm_frame_job {
+    const uint8_t* d_frame;        /* frame_h x frame_w x 3 BGR */
+    int32_t rect[4];               /* crop {x, y, w, h} from pcm_crop_rect */
+    const int32_t* d_labels;       /* over-segmentation of the crop */
+    int32_t n_labels;
+    int32_t clear_mask;            /* != 0: zero the whole mask plane before the update (main.py:286) */
+    pcm_update_params params;
+    /* pcm_prior_device before the update (skipped when d_priors_out is NULL): the previous frame's mask is read from
+     * the mask plane at prev_rect, BEFORE the plane is cleared */
+    const float* d_pts_prev; const uint8_t* d_des_prev; int32_t n_prev; int32_t prev_rect[4];
+    const float* d_pts; const uint8_t* d_des; int32_t n_cur; int32_t reserved;
+    float* d_priors_out;           /* n_labels float32: filled by the prior step and used by the update */
+    const float* d_priors;         /* priors for the update when there is no prior step (NULL: all -1) */
+    /* pcm_iou_device after the update (skipped when d_truth is NULL) */
+    const uint8_t* d_truth; int64_t truth_stride; int32_t truth_channels; int32_t reserved2;
+    int64_t* d_counts;             /* two int64, caller-zeroed */
+} pcm_frame_job;
+
+/* Enqueue n_jobs frames back to back on the handle's stream (no host synchronisation in between or at the end):
+ * the per-frame work of pcm_prior_device / pcm_update_device / pcm_iou_device, issued from native code so that a
+ * sequence costs one call.  d_mask: dense frame_h x frame_w plane shared by the frames. */
+int pcm_run_frames(pcm_handle* h, int frame_h, int frame_w, int64_t frame_stride, uint8_t* d_mask, int64_t mask_row_stride,
+                   const pcm_frame_job* jobs, int n_jobs);
+
 /* ---- SIFT-match prior (computePriors :129-163), SURVEY.md §8 row f-2 -------- */
 
 /* Priors of one frame from the SIFT keypoints / descriptors the caller detected with OpenCV (host, once per clip

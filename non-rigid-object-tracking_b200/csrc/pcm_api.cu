@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -182,13 +183,11 @@ struct PinBuf {
 struct Model {
     int n_frame = 0;
     DevForest forest{};
-    void* d_nodes = nullptr;
-    void* d_leaves = nullptr;
-    void* d_trees = nullptr;
+    DevBuf blob;                  // nodes | leaves | trees, one block (from the process-wide block cache)
     TopNodes top{};               // root + its children of the first MAX_TOP_TREES trees
     bool has_pca = false;
     DevPCA pca{};
-    void* d_pca = nullptr;        // comp | comp255 | mean, 3F doubles
+    DevBuf pca_buf;               // comp | comp255 | mean, 3F doubles
     int max_depth = 0;
 };
 
@@ -200,6 +199,7 @@ struct pcm_handle {
     cudaStream_t stream = nullptr;
     ColorTables* d_tables = nullptr;
     ColorTables h_tables;
+    DevBuf err_buf;
     int* d_err = nullptr;         // sticky "label out of range" word: set by K1, cleared by the host once reported
     // true while the last thing this handle queued on its PRIVATE stream is its own K3 / K5: only then may
     // the next K0 start before its predecessor has finished (PlanesArgs::early)
@@ -485,10 +485,8 @@ struct Encoder {
 };
 
 static void free_model(Model& m) {
-    if (m.d_nodes) cudaFree(m.d_nodes);
-    if (m.d_leaves) cudaFree(m.d_leaves);
-    if (m.d_trees) cudaFree(m.d_trees);
-    if (m.d_pca) cudaFree(m.d_pca);
+    m.blob.release();
+    m.pca_buf.release();
     m = Model{};
 }
 
@@ -522,6 +520,20 @@ static const ScoreVariant& pick_score_variant(bool smem, int depth, bool f16) {
     return score_variant(dyn);
 }
 
+// per-device state shared by every handle of the process
+struct DeviceShared {
+    std::mutex m;
+    bool ready = false;
+    int sm_count = 0, max_smem_optin = 0;
+    PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
+    ColorTables h_tables;
+    ColorTables* d_tables = nullptr;
+};
+static DeviceShared& device_shared(int device) {
+    static DeviceShared table[64];
+    return table[device & 63];
+}
+
 extern "C" int pcm_abi_version(void) { return PCM_ABI_VERSION; }
 extern "C" const char* pcm_last_error(void) { return g_last_error.c_str(); }
 
@@ -535,31 +547,42 @@ extern "C" int pcm_create(int device, pcm_handle** out) {
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     if (device < 0 || device >= count) return fail(PCM_E_INVALID, "pcm_create: device %d out of range [0,%d)", device, count);
     CUDA_TRY(cudaSetDevice(device));
+    // once per device and process: device attributes, the driver entry point, the colour tables and the kernels'
+    // shared-memory opt-in (a sweep creates one handle per sequence; none of this may cost per handle)
+    DeviceShared& ds = device_shared(device);
+    {
+        std::lock_guard<std::mutex> lk(ds.m);
+        if (!ds.ready) {
+            CUDA_TRY(cudaDeviceGetAttribute(&ds.sm_count, cudaDevAttrMultiProcessorCount, device));
+            CUDA_TRY(cudaDeviceGetAttribute(&ds.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            CUDA_TRY(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres));
+            if (qres != cudaDriverEntryPointSuccess || !fn)
+                return fail(PCM_E_CUDA, "pcm_create: driver does not provide cuTensorMapEncodeTiled");
+            ds.encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+            build_tables(ds.h_tables);
+            CUDA_TRY(cudaMalloc(&ds.d_tables, sizeof(ColorTables)));
+            CUDA_TRY(cudaMemcpy(ds.d_tables, &ds.h_tables, sizeof(ColorTables), cudaMemcpyHostToDevice));
+            for (int i = 0; i < N_SCORE_VARIANTS; ++i)
+                CUDA_TRY(cudaFuncSetAttribute(score_variant(i).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ds.max_smem_optin));
+            CUDA_TRY(cudaFuncSetAttribute(qs_window_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds.max_smem_optin));
+            CUDA_TRY(cudaFuncSetAttribute(qs_window_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds.max_smem_optin));
+            ds.ready = true;
+        }
+    }
     pcm_handle* h = new pcm_handle();
     h->device = device;
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    h->sm_count = prop.multiProcessorCount;
-    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    h->sm_count = ds.sm_count;
+    h->max_smem_optin = ds.max_smem_optin;
+    h->encode_tiled = ds.encode_tiled;
+    h->d_tables = ds.d_tables;          // shared, never freed
+    h->h_tables = ds.h_tables;
     CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
-    {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        CUDA_TRY(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres));
-        if (qres != cudaDriverEntryPointSuccess || !fn)
-            return fail(PCM_E_CUDA, "pcm_create: driver does not provide cuTensorMapEncodeTiled");
-        h->encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-    }
-    build_tables(h->h_tables);
-    CUDA_TRY(cudaMalloc(&h->d_tables, sizeof(ColorTables)));
-    CUDA_TRY(cudaMemcpy(h->d_tables, &h->h_tables, sizeof(ColorTables), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc(&h->d_err, sizeof(int)));
-    CUDA_TRY(cudaMemset(h->d_err, 0, sizeof(int)));
-    for (int i = 0; i < N_SCORE_VARIANTS; ++i)
-        CUDA_TRY(cudaFuncSetAttribute(score_variant(i).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-    CUDA_TRY(cudaFuncSetAttribute(qs_window_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-    CUDA_TRY(cudaFuncSetAttribute(qs_window_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+    CUDA_TRY(h->err_buf.reserve(sizeof(int)));
+    h->d_err = h->err_buf.as<int>();
+    CUDA_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
     *out = h;
     return PCM_OK;
 }
@@ -582,8 +605,7 @@ extern "C" void pcm_destroy(pcm_handle* h) {
     for (PinBuf* b : {&h->h_frame, &h->h_labels, &h->h_priors, &h->h_mask, &h->h_small, &h->h_noise}) b->release();
     for (auto& t : h->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : h->free_events) cudaEventDestroy(e);
-    if (h->d_tables) cudaFree(h->d_tables);
-    if (h->d_err) cudaFree(h->d_err);
+    h->err_buf.release();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -680,15 +702,19 @@ extern "C" int pcm_add_model(pcm_handle* h, int n_frame, int n_trees, const int6
     Model m;
     m.n_frame = n_frame;
     m.max_depth = max_depth;
-    CUDA_TRY(cudaMalloc(&m.d_nodes, nodes.size() * sizeof(NodeT)));
-    CUDA_TRY(cudaMalloc(&m.d_leaves, leaves.size() * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&m.d_trees, trees.size() * sizeof(int4)));
-    CUDA_TRY(cudaMemcpy(m.d_nodes, nodes.data(), nodes.size() * sizeof(NodeT), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(m.d_leaves, leaves.data(), leaves.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(m.d_trees, trees.data(), trees.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    m.forest.nodes = static_cast<const NodeT*>(m.d_nodes);
-    m.forest.leaves = static_cast<const double*>(m.d_leaves);
-    m.forest.trees = static_cast<const int4*>(m.d_trees);
+    // one block, one copy: [nodes | leaves | trees], every part 16-byte aligned
+    const size_t nb = (nodes.size() * sizeof(NodeT) + 15) / 16 * 16, lb = (leaves.size() * sizeof(double) + 15) / 16 * 16,
+                 tb = trees.size() * sizeof(int4);
+    std::vector<char> host(nb + lb + tb);
+    memcpy(host.data(), nodes.data(), nodes.size() * sizeof(NodeT));
+    memcpy(host.data() + nb, leaves.data(), leaves.size() * sizeof(double));
+    memcpy(host.data() + nb + lb, trees.data(), tb);
+    CUDA_TRY(m.blob.reserve(host.size()));
+    CUDA_TRY(cudaMemcpyAsync(m.blob.p, host.data(), host.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    m.forest.nodes = reinterpret_cast<const NodeT*>(m.blob.as<char>());
+    m.forest.leaves = reinterpret_cast<const double*>(m.blob.as<char>() + nb);
+    m.forest.trees = reinterpret_cast<const int4*>(m.blob.as<char>() + nb + lb);
     m.forest.n_trees = n_trees;
     m.forest.n_nodes = (int)nodes.size();
     m.forest.n_leaves = n_leaf;
@@ -721,9 +747,10 @@ extern "C" int pcm_set_novelty(pcm_handle* h, int model_index, const double* mea
         buf[2 * F + f] = mean[f];
         mdc += mean[f] * component[f];
     }
-    if (!m.d_pca) CUDA_TRY(cudaMalloc(&m.d_pca, buf.size() * sizeof(double)));
-    CUDA_TRY(cudaMemcpy(m.d_pca, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
-    m.pca.comp = static_cast<const double*>(m.d_pca);
+    CUDA_TRY(m.pca_buf.reserve(buf.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(m.pca_buf.p, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    m.pca.comp = m.pca_buf.as<double>();
     m.pca.comp255 = m.pca.comp + F;
     m.pca.mean = m.pca.comp + 2 * F;
     m.pca.mean_dot_comp = mdc;
@@ -1425,6 +1452,40 @@ extern "C" int pcm_prior_device(pcm_handle* h, const float* d_pts_prev, const ui
     }
     prior_finish_kernel<<<1, 1024, 0, st>>>(a);
     CHECK_LAUNCH(h, "prior_finish_kernel");
+    return PCM_OK;
+}
+
+static_assert(sizeof(pcm_frame_job) == 200 && offsetof(pcm_frame_job, d_pts) == 128 && offsetof(pcm_frame_job, d_counts) == 192,
+              "pcm_frame_job layout is part of the ABI (pcm/capi.py: FrameJob)");
+
+extern "C" int pcm_run_frames(pcm_handle* h, int frame_h, int frame_w, int64_t frame_stride, uint8_t* d_mask,
+                              int64_t mask_row_stride, const pcm_frame_job* jobs, int n_jobs) {
+    if (!h || !d_mask || (!jobs && n_jobs > 0)) return fail(PCM_E_INVALID, "pcm_run_frames: NULL argument");
+    if (n_jobs < 0 || frame_h <= 0 || frame_w <= 0 || mask_row_stride < frame_w) return fail(PCM_E_INVALID, "pcm_run_frames: bad size");
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (int k = 0; k < n_jobs; ++k) {
+        const pcm_frame_job& j = jobs[k];
+        int rc;
+        if (j.d_priors_out) {
+            rc = pcm_prior_device(h, j.d_pts_prev, j.d_des_prev, j.n_prev,
+                                  d_mask + (int64_t)j.prev_rect[1] * mask_row_stride + j.prev_rect[0], mask_row_stride,
+                                  j.prev_rect[2], j.prev_rect[3], j.d_pts, j.d_des, j.n_cur, j.d_labels, j.rect[2], j.rect[3],
+                                  j.n_labels, j.d_priors_out);
+            if (rc) return rc;
+        }
+        if (j.clear_mask) {
+            CUDA_TRY(cudaMemsetAsync(d_mask, 0, (size_t)mask_row_stride * frame_h, h->stream));
+            h->chain_tail = false;
+        }
+        const int rect[4] = {j.rect[0], j.rect[1], j.rect[2], j.rect[3]};
+        rc = pcm_update_device(h, j.d_frame, frame_h, frame_w, frame_stride, rect, j.d_labels, j.n_labels,
+                               j.d_priors_out ? j.d_priors_out : j.d_priors, &j.params, d_mask, mask_row_stride);
+        if (rc) return rc;
+        if (j.d_truth) {
+            rc = pcm_iou_device(h, d_mask, mask_row_stride, j.d_truth, j.truth_stride, j.truth_channels, frame_h, frame_w, j.d_counts);
+            if (rc) return rc;
+        }
+    }
     return PCM_OK;
 }
 

@@ -78,8 +78,18 @@ class PixelClassificationNonRigidMasker(Masker):
         self.segment_fn = segment_fn or (None if (self.native_quickshift or self.native_felzenszwalb)
                                          else make_segment_provider(params["over_segmentation"]))
         self._qs_noise_shape = None
-        self.prior_fn = prior_fn or SiftPrior()
+        self._prior_fn = prior_fn              # SiftPrior() on first use (SIFT + FLANN objects are not free to build)
         self.prevForegroundMask = None
+
+    @property
+    def prior_fn(self):
+        if self._prior_fn is None:
+            self._prior_fn = SiftPrior()
+        return self._prior_fn
+
+    @prior_fn.setter
+    def prior_fn(self, fn):
+        self._prior_fn = fn
 
     # -- training (reference :166-228) -------------------------------------------
     def _rows(self, frame, rect):

@@ -29,6 +29,17 @@ class UpdateParams(C.Structure):
                 ("outlier_threshold", C.c_double), ("prior_weight", C.c_double)]
 
 
+class FrameJob(C.Structure):
+    """pcm_frame_job (include/pcm_b200.h)."""
+    _fields_ = [("d_frame", C.c_void_p), ("rect", C.c_int32 * 4), ("d_labels", C.c_void_p), ("n_labels", C.c_int32),
+                ("clear_mask", C.c_int32), ("params", UpdateParams),
+                ("d_pts_prev", C.c_void_p), ("d_des_prev", C.c_void_p), ("n_prev", C.c_int32), ("prev_rect", C.c_int32 * 4),
+                ("d_pts", C.c_void_p), ("d_des", C.c_void_p), ("n_cur", C.c_int32), ("reserved", C.c_int32),
+                ("d_priors_out", C.c_void_p), ("d_priors", C.c_void_p),
+                ("d_truth", C.c_void_p), ("truth_stride", C.c_int64), ("truth_channels", C.c_int32), ("reserved2", C.c_int32),
+                ("d_counts", C.c_void_p)]
+
+
 def library_path():
     return _build.LIB
 
@@ -65,11 +76,13 @@ def load_library():
         "pcm_quickshift": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
         "pcm_quickshift_device": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
         "pcm_felzenszwalb": (I, [P, I, I, L, P, D, D, I, P, I, P, C.POINTER(I)]),
+        "pcm_run_frames": (I, [P, I, I, L, P, L, P, I]),
         "pcm_prior_device": (I, [P, P, P, I, P, L, I, I, P, P, I, P, I, I, I, P]),
         "pcm_fit_rows": (I, [P, P, P, I, I, C.c_longlong]),
         "pcm_pca_moments": (I, [P, C.c_longlong, P, P, P]),
         "pcm_pca_residuals": (I, [P, C.c_longlong, P, P, P]),
         "pcm_fit_forest": (I, [P, P, P, I, I, C.c_longlong, I, I, I, P, P, I, P, P, P, P, P, P, P]),
+        "pcm_run_frames": (I, [P, I, I, L, P, L, P, I]),
         "pcm_prior_device": (I, [P, P, P, I, P, L, I, I, P, P, I, P, I, I, I, P]),
         "pcm_fit_rows": (I, [P, P, P, I, I, C.c_longlong]),
         "pcm_pca_moments": (I, [P, C.c_longlong, P, P, P]),
@@ -100,7 +113,7 @@ EXPORTED_SYMBOLS = [
     "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_use_own_stream", "pcm_get_stream", "pcm_synchronize",
     "pcm_set_features", "pcm_num_features", "pcm_add_model", "pcm_set_novelty", "pcm_num_models", "pcm_crop_rect",
     "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device", "pcm_felzenszwalb",
-    "pcm_prior_device", "pcm_fit_forest", "pcm_fit_rows", "pcm_pca_moments", "pcm_pca_residuals", "pcm_convert", "pcm_gather_features",
+    "pcm_prior_device", "pcm_run_frames", "pcm_fit_forest", "pcm_fit_rows", "pcm_pca_moments", "pcm_pca_residuals", "pcm_convert", "pcm_gather_features",
     "pcm_set_debug", "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_transfer_bytes", "pcm_set_label_cache", "pcm_profile_enable", "pcm_profile_read",
 ]
 
@@ -334,6 +347,11 @@ class Handle:
         self._check(self.lib.pcm_prior_device(self._h, v(d_pts_prev), v(d_des_prev), int(n_prev), v(d_prev_mask), int(prev_stride),
                                               int(prev_w), int(prev_h), v(d_pts), v(d_des), int(n_cur), v(d_labels),
                                               int(crop_w), int(crop_h), int(n_labels), v(d_priors)))
+
+    def run_frames(self, frame_h, frame_w, frame_stride, d_mask, mask_stride, jobs, n_jobs):
+        """Enqueue `n_jobs` FrameJob records (a ctypes array) back to back; asynchronous (pcm_run_frames)."""
+        self._check(self.lib.pcm_run_frames(self._h, int(frame_h), int(frame_w), int(frame_stride), C.c_void_p(d_mask),
+                                            int(mask_stride), jobs, int(n_jobs)))
 
     def update_device(self, d_frame, frame_h, frame_w, stride, rect, d_labels, n_labels, d_priors, params, d_mask,
                       mask_stride):

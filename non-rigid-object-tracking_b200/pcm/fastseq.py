@@ -241,6 +241,61 @@ def _precomputable(config):
     return config["params"]["over_segmentation"] in ("quickshift", "felzenszwalb")
 
 
+def _frame_loop(clip, maskers, rects, arena, sift, d_mask, d_counts, d_pri, gpu_prior, host_prior, model_cache, cache_tag):
+    """Per-frame enqueue from Python: several targets share the mask plane (main.py:130-164,286-343), or the prior is
+    computed on the host (FLANN) and needs the previous mask there."""
+    torch = clip.torch
+    frames = clip.frames
+    T = len(maskers)
+    n, H, W = clip.n, clip.H, clip.W
+    fb = H * W * 3
+    prev_rects = [None] * T
+    prev_crops = [None] * T                         # the SAME array objects the prior saw one frame earlier (SiftPrior reuse)
+    for index in range(n):
+        prev_masks = None
+        if gpu_prior and index > 0:
+            # the priors of every target read the PREVIOUS frame's mask plane: queue them before it is cleared
+            for i in range(T):
+                k, kp = index * T + i, (index - 1) * T + i
+                x, y, w, h = rects[index][i]
+                px, py, pw, ph = prev_rects[i]
+                maskers[i].native.prior_device(sift.pts_ptr(kp), sift.des_ptr(kp), sift.count(kp),
+                                               d_mask.data_ptr() + py * W + px, W, pw, ph,
+                                               sift.pts_ptr(k), sift.des_ptr(k), sift.count(k),
+                                               arena.ptr(k), w, h, arena.n_labels[k], d_pri[i].data_ptr())
+        if host_prior and index > 0:
+            with stages.stage("prior_mask_d2h"):
+                hm = d_mask.cpu().numpy()           # waits for the previous frame; its crops are the prevForegroundMasks
+            prev_masks = [hm[r[1]:r[1] + r[3], r[0]:r[0] + r[2]] for r in prev_rects]
+        if index > 0:
+            d_mask.zero_()                          # main.py:286: a fresh mask per frame
+        for i in range(T):
+            rect = rects[index][i]
+            k = index * T + i
+            S = arena.n_labels[k]
+            pri_ptr = d_pri[i].data_ptr() if (gpu_prior and index > 0) else 0
+            m = maskers[i]
+            if host_prior:
+                x, y, w, h = rect
+                crop = frames[index][y:y + h, x:x + w]
+            if prev_masks is not None:
+                with stages.stage("sift_prior"):
+                    pri = m.prior_fn(prev_crops[i], prev_masks[i], crop, arena.host[k], S,
+                                     cache=model_cache, key=(cache_tag, i, index, rect)) \
+                        if cache_tag is not None else \
+                        m.prior_fn(prev_crops[i], prev_masks[i], crop, arena.host[k], S)
+                d_priors = torch.from_numpy(np.ascontiguousarray(pri, np.float32)).to(clip.dev)
+                pri_ptr = d_priors.data_ptr()
+            m.update_resident(clip.d_frames.data_ptr() + index * fb, H, W, W * 3, rect, arena.ptr(k), S, pri_ptr,
+                              d_mask.data_ptr(), W)
+            prev_rects[i] = rect
+            if host_prior:
+                prev_crops[i] = crop
+            if index < clip.n_truth:
+                m.native.iou_device(d_mask.data_ptr(), W, clip.d_truth.data_ptr() + index * H * W, W, 1, H, W,
+                                    d_counts.data_ptr() + 16 * k)
+
+
 def run_sequence_fast(config, clip, device=0, model_cache=None, cache_tag=None, tracker_provider=None, stream=None,
                       out_path=None):
     """`run_sequence` over a ClipContext.  `stream`: a torch.cuda.Stream owned by the calling thread (created when
@@ -297,51 +352,38 @@ def run_sequence_fast(config, clip, device=0, model_cache=None, cache_tag=None, 
             d_pri = [torch.empty(max(arena.n_labels), dtype=torch.float32, device=clip.dev) for _ in range(T)]
         for m in maskers:
             m.native.set_stream(stream.cuda_stream)
-        prev_rects = [None] * T
-        prev_crops = [None] * T                         # the SAME array objects the prior saw one frame earlier (SiftPrior reuse)
-        for index in range(n):
-            prev_masks = None
-            if gpu_prior and index > 0:
-                # the priors of every target read the PREVIOUS frame's mask plane: queue them before it is cleared
-                for i in range(T):
-                    k, kp = index * T + i, (index - 1) * T + i
-                    x, y, w, h = rects[index][i]
-                    px, py, pw, ph = prev_rects[i]
-                    maskers[i].native.prior_device(sift.pts_ptr(kp), sift.des_ptr(kp), sift.count(kp),
-                                                   d_mask.data_ptr() + py * W + px, W, pw, ph,
-                                                   sift.pts_ptr(k), sift.des_ptr(k), sift.count(k),
-                                                   arena.ptr(k), w, h, arena.n_labels[k], d_pri[i].data_ptr())
-            if host_prior and index > 0:
-                with stages.stage("prior_mask_d2h"):
-                    hm = d_mask.cpu().numpy()           # waits for the previous frame; its crops are the prevForegroundMasks
-                prev_masks = [hm[r[1]:r[1] + r[3], r[0]:r[0] + r[2]] for r in prev_rects]
-            if index > 0:
-                d_mask.zero_()                          # main.py:286: a fresh mask per frame
-            for i in range(T):
-                rect = rects[index][i]
-                k = index * T + i
-                S = arena.n_labels[k]
-                pri_ptr = d_pri[i].data_ptr() if (gpu_prior and index > 0) else 0
-                m = maskers[i]
-                if host_prior:
-                    x, y, w, h = rect
-                    crop = frames[index][y:y + h, x:x + w]
-                if prev_masks is not None:
-                    with stages.stage("sift_prior"):
-                        pri = m.prior_fn(prev_crops[i], prev_masks[i], crop, arena.host[k], S,
-                                         cache=model_cache, key=(cache_tag, i, index, rect)) \
-                            if cache_tag is not None else \
-                            m.prior_fn(prev_crops[i], prev_masks[i], crop, arena.host[k], S)
-                    d_priors = torch.from_numpy(np.ascontiguousarray(pri, np.float32)).to(clip.dev)
-                    pri_ptr = d_priors.data_ptr()
-                m.update_resident(clip.d_frames.data_ptr() + index * fb, H, W, W * 3, rect, arena.ptr(k), S, pri_ptr,
-                                  d_mask.data_ptr(), W)
-                prev_rects[i] = rect
-                if host_prior:
-                    prev_crops[i] = crop
+        if T == 1 and not host_prior:
+            # single target, everything device-side: the whole sequence is ONE native call (pcm_run_frames)
+            m = maskers[0]
+            jobs = (capi.FrameJob * n)()
+            frames_ptr, mask_ptr = clip.d_frames.data_ptr(), d_mask.data_ptr()
+            truth_ptr = clip.d_truth.data_ptr() if clip.d_truth is not None else 0
+            counts_ptr = d_counts.data_ptr()
+            pri_ptr = d_pri[0].data_ptr() if gpu_prior else 0
+            for index in range(n):
+                j = jobs[index]
+                rect = rects[index][0]
+                j.d_frame = frames_ptr + index * fb
+                j.rect[:] = rect
+                j.d_labels = arena.ptr(index)
+                j.n_labels = arena.n_labels[index]
+                j.clear_mask = 1 if index > 0 else 0
+                p, blend = m._frame_params()
+                j.params = p
+                if gpu_prior and index > 0:
+                    j.d_pts_prev, j.d_des_prev, j.n_prev = sift.pts_ptr(index - 1), sift.des_ptr(index - 1), sift.count(index - 1)
+                    j.prev_rect[:] = rects[index - 1][0]
+                    j.d_pts, j.d_des, j.n_cur = sift.pts_ptr(index), sift.des_ptr(index), sift.count(index)
+                    j.d_priors_out = pri_ptr
                 if index < clip.n_truth:
-                    m.native.iou_device(d_mask.data_ptr(), W, clip.d_truth.data_ptr() + index * H * W, W, 1, H, W,
-                                        d_counts.data_ptr() + 16 * k)
+                    j.d_truth, j.truth_stride, j.truth_channels = truth_ptr + index * H * W, W, 1
+                    j.d_counts = counts_ptr + 16 * index
+                m._advance(blend, None, None, quiet=True)
+            with stages.stage("enqueue"):
+                m.native.run_frames(H, W, W * 3, mask_ptr, W, jobs, n)
+        else:
+            _frame_loop(clip, maskers, rects, arena, sift, d_mask, d_counts, d_pri if gpu_prior else None, gpu_prior,
+                        host_prior, model_cache, cache_tag)
         with stages.stage("gpu_wait"):
             maskers[0].native.synchronize()
             counts = d_counts.cpu().numpy()
