@@ -58,14 +58,18 @@ class LabelArena:
 
 
 class ClipContext:
-    def __init__(self, video_path, truth_path, resize_factor=1, device=0, max_frames=None):
+    def __init__(self, video_path, truth_path, resize_factor=1, device=0, max_frames=None, host_workers=4):
         import torch
+        from concurrent.futures import ThreadPoolExecutor
         self.torch = torch
         self.device = device
         self.dev = torch.device("cuda", device)
+        self.host_workers = max(1, int(host_workers))
         with stages.stage("decode"):
-            frames = seq_mod.read_clip(seq_mod.resolve_path(video_path), resize_factor)
-            truths = seq_mod.read_clip(seq_mod.resolve_path(truth_path), resize_factor) if truth_path is not None else None
+            with ThreadPoolExecutor(max_workers=2) as pool:       # clip and ground truth decode side by side
+                ft = pool.submit(seq_mod.read_clip, seq_mod.resolve_path(truth_path), resize_factor) if truth_path is not None else None
+                frames = seq_mod.read_clip(seq_mod.resolve_path(video_path), resize_factor)
+                truths = ft.result() if ft is not None else None
         if not frames:
             raise IOError("Fatal error! no frames in %s" % video_path)
         self.frames, self.truths = frames, truths
@@ -143,11 +147,17 @@ class ClipContext:
                 host = None
             elif kind == "felzenszwalb":
                 with stages.stage("felzenszwalb_maps"):
-                    host = []
-                    for k, r in enumerate(flat):
-                        seg, n = capi.felzenszwalb(self.frames[k // T], r, scale=100, sigma=0.5, min_size=50)
-                        host.append(seg)
-                        n_labels.append(n)
+                    from concurrent.futures import ThreadPoolExecutor
+
+                    def one(k):          # felzenszwalb(crop, scale=100, sigma=0.5, min_size=50) (:73), frames in parallel
+                        t0 = time.perf_counter()
+                        out = capi.felzenszwalb(self.frames[k // T], flat[k], scale=100, sigma=0.5, min_size=50)
+                        stages.add("felzenszwalb_cpu", time.perf_counter() - t0)
+                        return out
+                    with ThreadPoolExecutor(max_workers=self.host_workers) as pool:
+                        res = list(pool.map(one, range(len(flat))))
+                    host = [r[0] for r in res]
+                    n_labels.extend(r[1] for r in res)
                     d.copy_(torch.from_numpy(np.concatenate([h.reshape(-1) for h in host])))
                     torch.cuda.synchronize(self.dev)
             else:
@@ -338,7 +348,7 @@ def run_sequence_fast(config, clip, device=0, model_cache=None, cache_tag=None, 
     gpu_prior = want_prior and (config.get("prior_provider") or "gpu") == "gpu"
     host_prior = want_prior and not gpu_prior
     arena = clip.labels(params["over_segmentation"], box_key, rects, want_host=host_prior)
-    sift = clip.sift(box_key, rects, workers=config.get("host_workers") or 4) if gpu_prior else None
+    sift = clip.sift(box_key, rects, workers=clip.host_workers) if gpu_prior else None
     T = len(maskers)
     n, H, W = clip.n, clip.H, clip.W
     fb = H * W * 3

