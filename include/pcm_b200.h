@@ -207,7 +207,9 @@ typedef struct pcm_frame_job {
     int32_t rect[4];               /* crop {x, y, w, h} from pcm_crop_rect */
     const int32_t* d_labels;       /* over-segmentation of the crop */
     int32_t n_labels;
-    int32_t clear_mask;            /* != 0: zero the whole mask plane before the update (main.py:286) */
+    int32_t clear_mask;            /* a fresh mask per frame (main.py:286): 1 = zero the whole plane before the update;
+                                    * 2 = leave the plane alone and let the IoU step read it as zero outside `rect`
+                                    * (same counts, no memset; the plane is then scratch outside the current crop) */
     pcm_update_params params;
     /* pcm_prior_device before the update (skipped when d_priors_out is NULL): the previous frame's mask is read from
      * the mask plane at prev_rect, BEFORE the plane is cleared */

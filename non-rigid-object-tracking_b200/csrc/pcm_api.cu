@@ -403,12 +403,14 @@ static Geom make_geom(int n, int n_spaces, const int* ids) {
 // Largest integer t in [-2, 255] with  float32(v / 255) <= thr  <=>  v <= t  for v in -1..255
 // (features are X/255 cast to float32 by sklearn).
 static int int_threshold(double thr) {
-    int cnt = 0;
-    for (int v = -1; v <= 255; ++v) {
-        float x = (float)((double)v / 255.0);
-        if ((double)x <= thr) ++cnt;
-    }
-    return cnt - 2;
+    // f32(v / 255) is increasing in v: start from the real-valued solution and correct by at most a few steps
+    auto le = [&](int v) { return (double)(float)((double)v / 255.0) <= thr; };
+    if (!(thr >= -1.0)) return le(-1) ? -1 : -2;            // also NaN: nothing passes
+    int t = thr >= 1.5 ? 255 : (int)floor(thr * 255.0);
+    t = std::min(std::max(t, -2), 255);
+    while (t < 255 && le(t + 1)) ++t;
+    while (t >= -1 && !le(t)) --t;
+    return t;
 }
 
 struct EncTree {
@@ -913,9 +915,22 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     if ((int)ls.total > h->max_smem_optin)
         return fail(PCM_E_LIMIT, "update: tile needs %u B of shared memory (> %d)", ls.total, h->max_smem_optin);
     const ScoreVariant& sv = pick_score_variant(forest_smem, a.depth, g.es == 2);
+    // CTAs per SM of this instantiation at this shared-memory size (queried once per distinct size: the runtime call
+    // costs more than launching a small crop's kernel)
     int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sv.fn, NTHREADS, ls.total));
-    occ = std::max(occ, 1);
+    {
+        static std::mutex occ_m;
+        static std::vector<std::pair<std::pair<const void*, unsigned>, int>> occ_cache;
+        std::lock_guard<std::mutex> lk(occ_m);
+        const std::pair<const void*, unsigned> key{reinterpret_cast<const void*>(sv.fn), ls.total};
+        for (auto& e : occ_cache)
+            if (e.first == key) { occ = e.second; break; }
+        if (!occ) {
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sv.fn, NTHREADS, ls.total));
+            occ = std::max(occ, 1);
+            if (occ_cache.size() < 4096) occ_cache.push_back({key, occ});
+        }
+    }
     const int n_tiles = a.tiles_x * a.tiles_y;
     const int grid = std::min(n_tiles, h->sm_count * occ);
     {
@@ -1148,8 +1163,17 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
     return finish_host_update(h, rect, mask, mask_row_stride, mask_pixel_stride);
 }
 
+static int enqueue_iou(pcm_handle* h, const uint8_t* d_mask, int64_t mask_row_stride, const uint8_t* d_truth,
+                       int64_t truth_row_stride, int truth_channels, int height, int width, int64_t* d_counts, const int* valid);
+
 extern "C" int pcm_iou_device(pcm_handle* h, const uint8_t* d_mask, int64_t mask_row_stride, const uint8_t* d_truth,
                               int64_t truth_row_stride, int truth_channels, int height, int width, int64_t* d_counts) {
+    return enqueue_iou(h, d_mask, mask_row_stride, d_truth, truth_row_stride, truth_channels, height, width, d_counts, nullptr);
+}
+
+// valid: {x, y, w, h} rectangle outside of which the mask plane reads as zero, or NULL
+static int enqueue_iou(pcm_handle* h, const uint8_t* d_mask, int64_t mask_row_stride, const uint8_t* d_truth,
+                       int64_t truth_row_stride, int truth_channels, int height, int width, int64_t* d_counts, const int* valid) {
     if (!h || !d_mask || !d_truth || !d_counts) return fail(PCM_E_INVALID, "pcm_iou_device: NULL argument");
     if (truth_channels != 1 && truth_channels != 3) return fail(PCM_E_INVALID, "pcm_iou_device: truth_channels %d", truth_channels);
     if (height <= 0 || width <= 0) return fail(PCM_E_INVALID, "pcm_iou_device: bad size");
@@ -1158,8 +1182,9 @@ extern "C" int pcm_iou_device(pcm_handle* h, const uint8_t* d_mask, int64_t mask
     const int blocks = (int)std::min<long long>((work + 255) / 256, (long long)h->sm_count * 8);
     {
         KernelTimer kt(h, 5);
+        const int4 vr = valid ? make_int4(valid[0], valid[1], valid[2], valid[3]) : make_int4(0, 0, -1, -1);
         CUDA_TRY(launch_chain(iou_kernel, dim3(std::max(blocks, 1)), dim3(256), 0, h->stream, d_mask, (long long)mask_row_stride,
-                              d_truth, (long long)truth_row_stride, truth_channels, height, width,
+                              d_truth, (long long)truth_row_stride, truth_channels, height, width, vr,
                               reinterpret_cast<unsigned long long*>(d_counts)));
     }
     CUDA_TRY(cudaGetLastError());
@@ -1473,7 +1498,7 @@ extern "C" int pcm_run_frames(pcm_handle* h, int frame_h, int frame_w, int64_t f
                                   j.n_labels, j.d_priors_out);
             if (rc) return rc;
         }
-        if (j.clear_mask) {
+        if (j.clear_mask == 1) {
             CUDA_TRY(cudaMemsetAsync(d_mask, 0, (size_t)mask_row_stride * frame_h, h->stream));
             h->chain_tail = false;
         }
@@ -1482,7 +1507,8 @@ extern "C" int pcm_run_frames(pcm_handle* h, int frame_h, int frame_w, int64_t f
                                j.d_priors_out ? j.d_priors_out : j.d_priors, &j.params, d_mask, mask_row_stride);
         if (rc) return rc;
         if (j.d_truth) {
-            rc = pcm_iou_device(h, d_mask, mask_row_stride, j.d_truth, j.truth_stride, j.truth_channels, frame_h, frame_w, j.d_counts);
+            rc = enqueue_iou(h, d_mask, mask_row_stride, j.d_truth, j.truth_stride, j.truth_channels, frame_h, frame_w, j.d_counts,
+                             j.clear_mask == 2 ? rect : nullptr);
             if (rc) return rc;
         }
     }

@@ -964,9 +964,11 @@ __global__ void __launch_bounds__(256) mask_dilate_kernel(const DilateArgs a) {
 // counts[0] += #(m != 0 && t != 0), counts[1] += #(m != 0 || t != 0) (benchmark.py:12-13);
 // truth either gray or BGR (converted like cv.cvtColor(BGR2GRAY), main.py:285).
 // Gray truth with 16-byte aligned rows is read 16 pixels per thread.
+// valid = {x, y, w, h}: the mask plane only counts inside this rectangle, everything outside reads as 0 (a sequence
+// that moves its crop from frame to frame does not have to clear the plane in between); valid.z < 0: whole plane.
 __global__ void __launch_bounds__(256) iou_kernel(const uint8_t* __restrict__ mask, long long mask_stride,
                                                   const uint8_t* __restrict__ truth, long long truth_stride,
-                                                  int truth_channels, int h, int w,
+                                                  int truth_channels, int h, int w, int4 valid,
                                                   unsigned long long* __restrict__ counts) {
     grid_launch_dependents();   // the next frame's K0 may start now: it touches nothing K3 or this kernel uses
     grid_dependency_wait();
@@ -978,7 +980,17 @@ __global__ void __launch_bounds__(256) iou_kernel(const uint8_t* __restrict__ ma
         const long long n = (long long)h * per_row;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
             const int r = (int)(i / per_row), c = (int)(i - (long long)r * per_row) * 16;
-            const uint4 m = __ldg(reinterpret_cast<const uint4*>(mask + (size_t)r * mask_stride + c));
+            uint4 m = make_uint4(0u, 0u, 0u, 0u);
+            const bool row_in = valid.z < 0 || (r >= valid.y && r < valid.y + valid.w);
+            if (row_in && (valid.z < 0 || (c + 16 > valid.x && c < valid.x + valid.z))) {
+                m = __ldg(reinterpret_cast<const uint4*>(mask + (size_t)r * mask_stride + c));
+                if (valid.z >= 0 && (c < valid.x || c + 16 > valid.x + valid.z)) {       // chunk straddles the rectangle's edge
+                    uint32_t* mw = reinterpret_cast<uint32_t*>(&m);
+#pragma unroll
+                    for (int b = 0; b < 16; ++b)
+                        if (c + b < valid.x || c + b >= valid.x + valid.z) mw[b >> 2] &= ~(0xffu << (8 * (b & 3)));
+                }
+            }
             const uint4 t = __ldg(reinterpret_cast<const uint4*>(truth + (size_t)r * truth_stride + c));
             const uint32_t mm[4] = {m.x, m.y, m.z, m.w}, tt[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
@@ -992,7 +1004,8 @@ __global__ void __launch_bounds__(256) iou_kernel(const uint8_t* __restrict__ ma
         const long long n = (long long)h * w;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
             const int r = (int)(i / w), c = (int)(i - (long long)r * w);
-            const bool m = mask[(size_t)r * mask_stride + c] != 0;
+            const bool in = valid.z < 0 || (r >= valid.y && r < valid.y + valid.w && c >= valid.x && c < valid.x + valid.z);
+            const bool m = in && mask[(size_t)r * mask_stride + c] != 0;
             const uint8_t* tp = truth + (size_t)r * truth_stride + (size_t)c * truth_channels;
             const bool t = (truth_channels == 3) ? (bgr2gray_px(tp[0], tp[1], tp[2]) != 0) : (tp[0] != 0);
             inter += m && t;

@@ -377,7 +377,7 @@ def run_sequence_fast(config, clip, device=0, model_cache=None, cache_tag=None, 
                 j.rect[:] = rect
                 j.d_labels = arena.ptr(index)
                 j.n_labels = arena.n_labels[index]
-                j.clear_mask = 1 if index > 0 else 0
+                j.clear_mask = 2 if index > 0 else 0
                 p, blend = m._frame_params()
                 j.params = p
                 if gpu_prior and index > 0:

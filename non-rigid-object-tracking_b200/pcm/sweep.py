@@ -182,6 +182,44 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
             if progress:
                 progress(done[0], len(items), sid, r)
 
+    def prefit_tasks():
+        """One task per (clip, features, max_depth, polygon selection) of the shard: training rows, forest and (with the
+        shallowest depth of a feature set, when any sequence asks for novelty detection) the PCA go into the rank-wide
+        cache before the sequences ask for them, all in parallel instead of one sequence thread fitting while the
+        others of its group wait."""
+        seen, tasks = set(), []
+        for it in items:
+            _, _, v, p = it
+            key = (v, p["features"], p["max_depth"])
+            if key in seen:
+                continue
+            seen.add(key)
+            novelty = any(q[2] == v and q[3]["features"] == p["features"] and q[3]["novelty_detection"] for q in items)
+            first_depth = min(q[3]["max_depth"] for q in items if q[2] == v and q[3]["features"] == p["features"])
+            cfg = sequence_config(base, polygons, v, dict(p, n_estimators=fit_estimators,
+                                                           novelty_detection=bool(novelty and p["max_depth"] == first_depth)),
+                                  videos_path, truth_path)
+            n_sel = len(cfg["pts"][0]) if cfg.get("multi_selection") else 1
+            for t in range(len(cfg["pts"])):
+                for sel in range(n_sel):
+                    tasks.append((v, cfg, t, sel))
+        return tasks
+
+    def prefit(task):
+        import cv2 as cv
+        from maskers import getMaskerByName
+        v, cfg, t, sel = task
+        frames = clips[v].frames
+        with stages.stage("prefit"):
+            m = getMaskerByName("PC", debug=False, frame=frames[0], config=cfg, poly_roi=cfg["pts"][t][0],
+                                update_mask=cfg.get("update_mask"), device=device, model_cache=cache, cache_tag=(v, t),
+                                fit_estimators=fit_estimators)
+            pts = cfg["pts"][t][sel]
+            n_frame = cfg["pts_frame_numbers"][sel]
+            m.addModel(frame=frames[n_frame], poly_roi=pts, bbox=cv.boundingRect(np.array(pts)),
+                       bbox_roni=cfg["bboxes_roni"][t][sel], n_frame=n_frame)
+            m.close()
+
     # longest sequences first; sequences that share fits next to each other
     order = sorted(range(len(items)), key=lambda k: (-item_cost(items[k]), str(fit_key(items[k])), items[k][0]))
     if seq_workers <= 1 or len(order) <= 1:
@@ -195,7 +233,9 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
                 seq_mod.read_clip(seq_mod.resolve_path(cfg["input_video"]), cfg.get("resize_factor") or 1)
                 seq_mod.read_clip(seq_mod.resolve_path(cfg["input_truth"]), cfg.get("resize_factor") or 1)
         with ThreadPoolExecutor(max_workers=seq_workers) as pool:
-            for f in [pool.submit(run_one, k) for k in order]:
+            futures = [pool.submit(prefit, t) for t in prefit_tasks()] if resident else []
+            futures += [pool.submit(run_one, k) for k in order]
+            for f in futures:
                 f.result()
     for c in clips.values():
         c.close()
