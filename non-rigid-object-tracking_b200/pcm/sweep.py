@@ -52,12 +52,13 @@ def build_items(videos=None, hyper=None):
 
 
 def item_cost(item):
-    """Relative cost of a sequence: per-frame host work (segmentation provider, SIFT prior) plus
-    a share of the fits it may trigger."""
+    """Relative cost of a sequence on the GPU path: frames x per-frame kernel time (two blended forests; the PCA novelty
+    pass costs about as much as the deepest forests; the device-side prior adds two small kernels)."""
     _, _, v, p = item
     frames = CLIP_FRAMES.get(v, 100)
-    per_frame = 1.0 + (3.0 if p.get("prior_weight") else 0.0) + (0.5 if p.get("novelty_detection") else 0.0)
-    return frames * per_frame + 30.0
+    per_frame = 1.0 + (2.5 if p.get("novelty_detection") else 0.0) + (0.6 if int(p.get("max_depth") or 0) >= 10 else 0.0) + \
+        (0.3 if int(p.get("n_estimators") or 0) >= 30 else 0.0) + (0.3 if p.get("prior_weight") else 0.0)
+    return frames * per_frame + 60.0          # + masker set-up, model export, job list (about 60 light frames)
 
 
 def forest_key(item):
@@ -95,28 +96,31 @@ class ModelCache:
 
 
 def partition(items, world):
-    """Longest-processing-time assignment of GROUPS of sequences that share their fits
-    (same video, features, max_depth) so that every fit happens on one rank only.
+    """Contiguous, cost-balanced split of the grid with CLIP LOCALITY: the sequences are ordered clip by clip (heaviest
+    clip first; inside a clip by features, max_depth, ... so that neighbours share their fitted models) and the ordered
+    list is cut into `world` runs of equal cost.  A rank therefore works on one or two clips -- what it has to decode,
+    over-segment and run SIFT on -- instead of on all of them; fits are cheap GPU work and may repeat on two ranks.
     Returns `world` lists of items; deterministic."""
-    groups = {}
+    clip_cost = {}
     for it in items:
-        groups.setdefault(fit_key(it), []).append(it)
-    order = sorted(groups.items(), key=lambda kv: (-sum(item_cost(i) for i in kv[1]), str(kv[0])))
-    # more ranks than groups: split the heaviest groups until every rank has work
-    while len(order) < world and any(len(g) > 1 for _, g in order):
-        k, g = max(order, key=lambda kv: (len(kv[1]) > 1, sum(item_cost(i) for i in kv[1])))
-        order.remove((k, g))
-        half = len(g) // 2
-        order += [((k, 0, id(g)), g[:half]), ((k, 1, id(g)), g[half:])]
-        order.sort(key=lambda kv: -sum(item_cost(i) for i in kv[1]))
-    load = [0.0] * world
+        clip_cost[it[2]] = clip_cost.get(it[2], 0.0) + item_cost(it)
+
+    def key(it):
+        p = it[3]
+        return (-clip_cost[it[2]], it[2], str(p.get("features")), p.get("max_depth") or 0, p.get("n_estimators") or 0, it[0])
+    ordered = sorted(items, key=key)
+    total = sum(item_cost(it) for it in ordered)
     shards = [[] for _ in range(world)]
-    for _, g in order:
-        r = min(range(world), key=lambda j: (load[j], j))
-        shards[r] += g
-        load[r] += sum(item_cost(i) for i in g)
-    for s in shards:
-        s.sort(key=lambda it: (forest_key(it)[0], forest_key(it)[1], forest_key(it)[2], forest_key(it)[3], it[0]))
+    if not ordered:
+        return shards
+    acc, r = 0.0, 0
+    for k, it in enumerate(ordered):
+        left = len(ordered) - k                      # items still to place, this one included
+        # move on when this rank has its share -- but never leave a later rank without an item
+        while r < world - 1 and shards[r] and (acc >= total * (r + 1) / world - 1e-9 or left <= world - 1 - r):
+            r += 1
+        shards[r].append(it)
+        acc += item_cost(it)
     return shards
 
 

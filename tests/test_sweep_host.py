@@ -33,12 +33,11 @@ def test_partition_is_a_balanced_exact_cover(world):
     assert all(len(s) > 0 for s in shards)
     loads = [sum(sweep.item_cost(it) for it in s) for s in shards]
     if world <= 8:
-        assert max(loads) <= 1.35 * (sum(loads) / world)
-        # sequences that share a forest (video, features, n_estimators, max_depth) stay on one rank
-        owner = {}
-        for r, s in enumerate(shards):
-            for it in s:
-                assert owner.setdefault(sweep.forest_key(it), r) == r
+        assert max(loads) <= 1.15 * (sum(loads) / world)
+        # clip locality: a rank decodes / over-segments / runs SIFT on the clips it touches -- at most two, and
+        # three at the end of the list where the two short clips sit
+        n_clips = [len({it[2] for it in s}) for s in shards]
+        assert world == 1 or (all(n <= 3 for n in n_clips) and (world < 4 or sorted(n_clips)[len(n_clips) // 2] <= 2))
     assert sweep.partition(items, world) == shards            # deterministic
 
 
@@ -155,7 +154,7 @@ def _run_worker(rank, world, port, q):
     sequence.run_sequence = fake_run_sequence
     hyper = dict(n_estimators=[20, 30], max_depth=[7, 10], features=["6 lab"], prior_weight=[0.0])
     summary, table = sweep.run({"masker": "PC"}, {"soldier": {}, "frog": {}}, videos=["soldier", "frog"], hyper=hyper,
-                               backend="gloo", seq_workers=2)
+                               backend="gloo", seq_workers=2, resident=False)
     q.put((rank, summary, None if table is None else table.to_dict()))
     import torch.distributed as dist
     dist.barrier()
