@@ -57,14 +57,32 @@ class LabelArena:
         return self.d_labels.data_ptr() + 4 * self.offsets[k]
 
 
+class Share:
+    """The ranks of a `torch.distributed` job that work on the same clip: per-frame host work of the clip (felzenszwalb
+    label maps, SIFT detection) is split between them -- member i of m takes entries i, i + m, ... -- and the pieces are
+    combined with an all-reduce (sum into zero-initialised buffers; NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, dist=None, group=None, index=0, size=1):
+        self.dist, self.group, self.index, self.size = dist, group, index, max(1, size)
+
+    def mine(self, n):
+        return range(self.index, n, self.size)
+
+    def combine(self, tensor):
+        if self.size > 1:
+            self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, group=self.group)
+        return tensor
+
+
 class ClipContext:
-    def __init__(self, video_path, truth_path, resize_factor=1, device=0, max_frames=None, host_workers=4):
+    def __init__(self, video_path, truth_path, resize_factor=1, device=0, max_frames=None, host_workers=4, share=None):
         import torch
         from concurrent.futures import ThreadPoolExecutor
         self.torch = torch
         self.device = device
         self.dev = torch.device("cuda", device)
         self.host_workers = max(1, int(host_workers))
+        self.share = share or Share()
         with stages.stage("decode"):
             with ThreadPoolExecutor(max_workers=2) as pool:       # clip and ground truth decode side by side
                 ft = pool.submit(seq_mod.read_clip, seq_mod.resolve_path(truth_path), resize_factor) if truth_path is not None else None
@@ -90,6 +108,33 @@ class ClipContext:
 
     def close(self):
         self.handle.close()
+
+    @staticmethod
+    def selections(config):
+        """(bboxes[target][selection], switch_frames) of a sequence config, as main.py:146-163 derives them."""
+        multi = config.get("multi_selection")
+        bboxes = [[cv.boundingRect(np.array(sel)) for k, sel in enumerate(target) if multi or k == 0] for target in config["pts"]]
+        switch = [config["pts_frame_numbers"][k] for k in range(len(bboxes[0]))] if multi else [0]
+        return bboxes, switch
+
+    def prepare(self, config, kinds, want_sift):
+        """Everything the sequences of this clip share, computed NOW by the calling thread: tracker boxes, the label
+        maps of the over-segmentations in `kinds`, SIFT features.  With a `share` of several ranks this is a collective:
+        every member must call it with the same arguments, in the same order relative to its other clips."""
+        bboxes, switch = self.selections(config)
+        box_key, _, rects, _ = self.schedule(config, bboxes, switch)
+        self._collective_ok = True
+        try:
+            for kind in sorted(kinds):
+                self.labels(kind, box_key, rects)
+            if want_sift:
+                self.sift(box_key, rects, workers=self.host_workers)
+        finally:
+            self._collective_ok = False
+
+    def _check_collective(self, what):
+        if self.share.size > 1 and not getattr(self, "_collective_ok", False):
+            raise RuntimeError("%s of a clip shared by %d ranks must be computed by ClipContext.prepare()" % (what, self.share.size))
 
     # ---- tracker boxes ------------------------------------------------------------------------------------
     def schedule(self, config, bboxes, switch_frames, tracker_provider=None):
@@ -146,6 +191,7 @@ class ClipContext:
                                                                       d.data_ptr() + 4 * int(offsets[k])))
                 host = None
             elif kind == "felzenszwalb":
+                self._check_collective("felzenszwalb label maps")
                 with stages.stage("felzenszwalb_maps"):
                     from concurrent.futures import ThreadPoolExecutor
 
@@ -154,12 +200,22 @@ class ClipContext:
                         out = capi.felzenszwalb(self.frames[k // T], flat[k], scale=100, sigma=0.5, min_size=50)
                         stages.add("felzenszwalb_cpu", time.perf_counter() - t0)
                         return out
+                    mine = list(self.share.mine(len(flat)))
                     with ThreadPoolExecutor(max_workers=self.host_workers) as pool:
-                        res = list(pool.map(one, range(len(flat))))
-                    host = [r[0] for r in res]
-                    n_labels.extend(r[1] for r in res)
-                    d.copy_(torch.from_numpy(np.concatenate([h.reshape(-1) for h in host])))
+                        res = dict(zip(mine, pool.map(one, mine)))
+                    flat_host = np.zeros(int(offsets[-1]), np.int32)
+                    counts = np.zeros(len(flat), np.int64)
+                    for k, (seg, n_seg) in res.items():
+                        flat_host[offsets[k]:offsets[k + 1]] = seg.reshape(-1)
+                        counts[k] = n_seg
+                    d.copy_(torch.from_numpy(flat_host))
+                    d_counts = torch.from_numpy(counts).to(self.dev)
+                    with stages.stage("share_allreduce"):
+                        self.share.combine(d)               # the other members' frames arrive here
+                        self.share.combine(d_counts)
+                        n_labels.extend(int(v) for v in d_counts.cpu().numpy())
                     torch.cuda.synchronize(self.dev)
+                    host = None
             else:
                 raise ValueError("no clip-resident over-segmentation for %r" % kind)
             return LabelArena(d, [int(o) for o in offsets], n_labels, host)
@@ -215,6 +271,7 @@ def _clip_sift(self, box_key, rects, workers=4):
         from concurrent.futures import ThreadPoolExecutor
         flat = [r for fr in rects for r in fr]
         T = len(rects[0])
+        self._check_collective("SIFT features")
         with stages.stage("sift_detect"):
             def one(k):
                 x, y, w, h = flat[k]
@@ -222,21 +279,33 @@ def _clip_sift(self, box_key, rects, workers=4):
                 out = _sift_detect(self.frames[k // T][y:y + h, x:x + w])
                 stages.add("sift_detect_cpu", time.perf_counter() - t0)
                 return out
+            mine = list(self.share.mine(len(flat)))
             with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
-                res = list(pool.map(one, range(len(flat))))
-        offsets = [0]
-        for p, _ in res:
-            offsets.append(offsets[-1] + len(p))
+                res = dict(zip(mine, pool.map(one, mine)))
+        counts = np.zeros(len(flat), np.int64)
+        for k, (p, _) in res.items():
+            counts[k] = len(p)
+        d_cnt = torch.from_numpy(counts).to(self.dev)
+        with stages.stage("share_allreduce"):
+            counts = self.share.combine(d_cnt).cpu().numpy()
+        offsets = [0] + [int(v) for v in np.cumsum(counts)]
         M = max(offsets[-1], 1)
         pts = np.zeros((M, 2), np.float32)
         des = np.zeros((M, 128), np.uint8)
-        for k, (p, d) in enumerate(res):
+        for k, (p, d) in res.items():
             pts[offsets[k]:offsets[k + 1]] = p
             des[offsets[k]:offsets[k + 1]] = d
         d_pts = torch.from_numpy(pts).to(self.dev)
         d_des = torch.from_numpy(des).to(self.dev)
+        with stages.stage("share_allreduce"):
+            self.share.combine(d_pts)                   # zero everywhere but on the member that detected the entry
+            self.share.combine(d_des)
         torch.cuda.synchronize(self.dev)
-        return SiftStore([r[0] for r in res], [r[1] for r in res], d_pts, d_des, offsets)
+        if self.share.size > 1:
+            pts, des = d_pts.cpu().numpy(), d_des.cpu().numpy()
+        host_pts = [pts[offsets[k]:offsets[k + 1]] for k in range(len(flat))]
+        host_des = [des[offsets[k]:offsets[k + 1]] for k in range(len(flat))]
+        return SiftStore(host_pts, host_des, d_pts, d_des, offsets)
     return self.once.get(("sift", box_key), make)
 
 

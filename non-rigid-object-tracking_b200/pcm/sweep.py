@@ -130,8 +130,26 @@ def sequence_config(base, polygons, video, params, videos_path, truth_path):
             "params": dict(params), **polygons[video]}
 
 
+def clip_needs(all_items):
+    """{clip: (over-segmentations, any SIFT prior)} over the WHOLE grid: what the ranks sharing a clip prepare together."""
+    needs = {}
+    for _, _, v, p in all_items:
+        kinds, sift = needs.setdefault(v, (set(), [False]))
+        kinds.add(p["over_segmentation"])
+        sift[0] = sift[0] or bool(p.get("prior_weight"))
+    return {v: (sorted(k), s[0]) for v, (k, s) in needs.items()}
+
+
+def clip_order(all_items):
+    """Clips, heaviest first: the order in which every rank opens and prepares the clips of its shard."""
+    cost = {}
+    for it in all_items:
+        cost[it[2]] = cost.get(it[2], 0.0) + item_cost(it)
+    return sorted(cost, key=lambda v: (-cost[v], v))
+
+
 def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Video", truth_path="Input/SegTrack2/Truth",
-              max_frames=None, train_jobs=None, progress=None, seq_workers=1, resident=True):
+              max_frames=None, train_jobs=None, progress=None, seq_workers=1, resident=True, shares=None, all_items=None):
     """Run this rank's sequences; returns float64 [n, 3] = (sequence id, mean IoU, seconds).
 
     resident=True (default): every clip of the shard is decoded and uploaded ONCE (`fastseq.ClipContext`); its tracker
@@ -150,7 +168,7 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
     from . import capi
     if items:
         capi.load_library()                                             # dlopen once, before the threads
-    clips = {}
+    clips, order_v = {}, []
     if resident and items:
         from . import fastseq
         from concurrent.futures import ThreadPoolExecutor
@@ -160,11 +178,23 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
         def open_clip(v):
             cfg = sequence_config(base, polygons, v, items[0][3], videos_path, truth_path)
             return fastseq.ClipContext(cfg["input_video"], cfg["input_truth"], cfg.get("resize_factor") or 1, device, max_frames,
-                                       host_workers=host_workers)
-        # longest clips first; every clip opens (decodes, uploads) on its own thread
-        by_len = sorted(videos, key=lambda v: -CLIP_FRAMES.get(v, 100))
+                                       host_workers=host_workers, share=(shares or {}).get(v))
+        # heaviest clips first; every clip opens (decodes, uploads) on its own thread
+        order_v = [v for v in clip_order(all_items or items) if v in videos]
         with ThreadPoolExecutor(max_workers=max(1, len(videos))) as pool:
-            clips = dict(zip(by_len, pool.map(open_clip, by_len)))
+            clips = dict(zip(order_v, pool.map(open_clip, order_v)))
+
+    def prepare_clips():
+        """What all sequences of a clip share (boxes, label maps, SIFT features), clip by clip in the same order on every
+        rank: the ranks that share a clip split the per-frame host work and all-reduce the pieces (main thread only)."""
+        if not clips:
+            return
+        needs = clip_needs(all_items or items)
+        for v in order_v:
+            cfg = sequence_config(base, polygons, v, items[0][3], videos_path, truth_path)
+            with stages.stage("prepare_clips"):
+                clips[v].prepare(cfg, needs[v][0], needs[v][1] and (cfg.get("prior_provider") or "gpu") == "gpu")
+
     local = threading.local()
 
     def run_one(k):
@@ -227,6 +257,8 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
     # longest sequences first; sequences that share fits next to each other
     order = sorted(range(len(items)), key=lambda k: (-item_cost(items[k]), str(fit_key(items[k])), items[k][0]))
     if seq_workers <= 1 or len(order) <= 1:
+        if resident:
+            prepare_clips()
         for k in order:
             run_one(k)
     else:
@@ -237,7 +269,9 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
                 seq_mod.read_clip(seq_mod.resolve_path(cfg["input_video"]), cfg.get("resize_factor") or 1)
                 seq_mod.read_clip(seq_mod.resolve_path(cfg["input_truth"]), cfg.get("resize_factor") or 1)
         with ThreadPoolExecutor(max_workers=seq_workers) as pool:
-            futures = [pool.submit(prefit, t) for t in prefit_tasks()] if resident else []
+            futures = [pool.submit(prefit, t) for t in prefit_tasks()] if resident else []     # GPU fits start at once ...
+            if resident:
+                prepare_clips()                                                                # ... while the host prepares the clips
             futures += [pool.submit(run_one, k) for k in order]
             for f in futures:
                 f.result()
@@ -327,10 +361,21 @@ def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, ou
         torch.cuda.synchronize()
         from . import capi
         capi.Handle(local_rank).close()
+    # ranks that work on the same clip form a group and split its per-frame host work (fastseq.Share)
+    shares = {}
+    if world > 1 and resident:
+        from .fastseq import Share
+        for v in clip_order(items):
+            members = [r for r in range(world) if any(it[2] == v for it in shards[r])]
+            if len(members) > 1:
+                group = dist.new_group(ranks=members)          # collective: every rank creates every group, same order
+                if rank in members:
+                    shares[v] = Share(dist, group, members.index(rank), len(members))
+        dist.barrier()
     stages.reset()
     t0 = time.time()
     local = run_shard(shards[rank], base, polygons, device=local_rank, max_frames=max_frames, train_jobs=train_jobs,
-                      seq_workers=seq_workers, resident=resident,
+                      seq_workers=seq_workers, resident=resident, shares=shares, all_items=items,
                       progress=(lambda k, n, sid, r: log("[rank %d] %d/%d seq %d iou %.3f %.2fs (train %.2fs, decode %.2fs, wall %.2fs)" %
                                                          (rank, k, n, sid, r["mean_iou"], r["seconds"], r["train_seconds"],
                                                           r["decode_seconds"], r["wall_seconds"])))

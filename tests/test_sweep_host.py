@@ -184,3 +184,46 @@ def test_sweep_run_world_size_2_gloo_end_to_end():
     assert t0["frog_benchmark"][3] == pytest.approx(0.5 + 0.03 + 0.10 + 0.05)
     assert t0["avg_benchmark"][0] == pytest.approx((0.59 + 0.64) / 2)
     assert all(v == 0.25 for v in t0["frog_time"].values())
+
+
+def _share_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from pcm.fastseq import Share
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    group = dist.new_group(ranks=list(range(world)))
+    share = Share(dist, group, rank, world)
+    n = 11
+    mine = list(share.mine(n))
+    flat = torch.zeros(n * 3, dtype=torch.int32)
+    desc = torch.zeros((n, 4), dtype=torch.uint8)
+    for k in mine:                                   # every member fills only its own entries ...
+        flat[3 * k:3 * k + 3] = torch.tensor([k, 10 * k, 100 + k], dtype=torch.int32)
+        desc[k] = torch.tensor([k, 255 - k, 7, 0], dtype=torch.uint8)
+    share.combine(flat)                              # ... and the all-reduce brings in the others'
+    share.combine(desc)
+    q.put((rank, mine, flat.numpy().copy(), desc.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_clip_share_splits_and_combines_world_size_2_gloo():
+    """fastseq.Share: the ranks working on one clip take interleaved entries of its per-frame host work and combine the
+    pieces with one all-reduce per buffer (NCCL on GPUs; gloo here)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_share_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in procs], key=lambda g: g[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][1] == [0, 2, 4, 6, 8, 10] and got[1][1] == [1, 3, 5, 7, 9]
+    want = np.array([[k, 10 * k, 100 + k] for k in range(11)], np.int32).reshape(-1)
+    for _, _, flat, desc in got:
+        assert np.array_equal(flat, want)
+        assert np.array_equal(desc[:, 0], np.arange(11)) and np.array_equal(desc[:, 1], 255 - np.arange(11))
