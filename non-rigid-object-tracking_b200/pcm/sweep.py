@@ -184,16 +184,28 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
         with ThreadPoolExecutor(max_workers=max(1, len(videos))) as pool:
             clips = dict(zip(order_v, pool.map(open_clip, order_v)))
 
-    def prepare_clips():
-        """What all sequences of a clip share (boxes, label maps, SIFT features), clip by clip in the same order on every
-        rank: the ranks that share a clip split the per-frame host work and all-reduce the pieces (main thread only)."""
-        if not clips:
-            return
+    gpu_prior = (base.get("prior_provider") or "gpu") == "gpu"
+    PREPARE_STEPS = ("quickshift", "felzenszwalb", "sift")
+
+    def prepare_clips(step):
+        """One kind of what all sequences of a clip share -- the label maps of an over-segmentation, or the SIFT features
+        -- for every clip of the shard, in the same (step, clip) order on every rank: the ranks that share a clip split
+        the per-frame host work and all-reduce the pieces (main thread only)."""
         needs = clip_needs(all_items or items)
         for v in order_v:
             cfg = sequence_config(base, polygons, v, items[0][3], videos_path, truth_path)
             with stages.stage("prepare_clips"):
-                clips[v].prepare(cfg, needs[v][0], needs[v][1] and (cfg.get("prior_provider") or "gpu") == "gpu")
+                if step == "sift":
+                    if needs[v][1] and gpu_prior:
+                        clips[v].prepare(cfg, [], True)
+                elif step in needs[v][0]:
+                    clips[v].prepare(cfg, [step], False)
+
+    def ready_after(step, k):
+        """Sequence k can start once `step` is prepared (its label maps, and the SIFT features if it uses the prior)."""
+        p = items[k][3]
+        need = "sift" if (p.get("prior_weight") and gpu_prior) else p["over_segmentation"]
+        return PREPARE_STEPS.index(need) <= PREPARE_STEPS.index(step) if need in PREPARE_STEPS else step == PREPARE_STEPS[-1]
 
     local = threading.local()
 
@@ -258,7 +270,8 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
     order = sorted(range(len(items)), key=lambda k: (-item_cost(items[k]), str(fit_key(items[k])), items[k][0]))
     if seq_workers <= 1 or len(order) <= 1:
         if resident:
-            prepare_clips()
+            for step in PREPARE_STEPS:
+                prepare_clips(step)
         for k in order:
             run_one(k)
     else:
@@ -270,9 +283,14 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
                 seq_mod.read_clip(seq_mod.resolve_path(cfg["input_truth"]), cfg.get("resize_factor") or 1)
         with ThreadPoolExecutor(max_workers=seq_workers) as pool:
             futures = [pool.submit(prefit, t) for t in prefit_tasks()] if resident else []     # GPU fits start at once ...
+            pending = list(order)
             if resident:
-                prepare_clips()                                                                # ... while the host prepares the clips
-            futures += [pool.submit(run_one, k) for k in order]
+                # ... while the host prepares the clips; sequences start as soon as what THEY need is there
+                for step in PREPARE_STEPS:
+                    prepare_clips(step)
+                    futures += [pool.submit(run_one, k) for k in pending if ready_after(step, k)]
+                    pending = [k for k in pending if not ready_after(step, k)]
+            futures += [pool.submit(run_one, k) for k in pending]
             for f in futures:
                 f.result()
     for c in clips.values():
