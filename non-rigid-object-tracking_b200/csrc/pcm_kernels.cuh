@@ -462,35 +462,45 @@ __device__ __forceinline__ void traverse_forest(const uint32_t nodes_s, const ui
 
 // L1 reconstruction error of a rank-1 PCA over the star features (:58-60):
 //   t = sum_f x_f c_f - mean.c ;  err = sum_f |x_f - (t c_f + mean_f)|,  x_f = v_f / 255, v_f = -1 off-crop
+// The feature loop runs tap by tap, plane by plane (it = k * NCH + p); comp / comp255 / mean and the tile byte offset
+// of every feature are staged in shared memory IN THAT ORDER by the kernel prologue, so the loop body is a broadcast
+// load of the three coefficients and, per pixel, one tile byte, one exact u8 -> f64 conversion and the FMAs.  A thread
+// whose pixels lie at least n away from every crop edge (`interior`) has no tap outside the crop and skips the
+// validity plane altogether.
+template <int NCH>
 __device__ __forceinline__ void novelty_error(const double* __restrict__ comp, const double* __restrict__ comp255,
-                                              const double* __restrict__ mean, const double mdc,
-                                              const int* __restrict__ sp, const Geom& g,
-                                              const uint32_t (&pix)[PIX_PER_THREAD],
-                                              double (&err)[PIX_PER_THREAD]) {
+                                              const double* __restrict__ mean, const uint32_t* __restrict__ noff,
+                                              const double mdc, const int* __restrict__ sp, const Geom& g, const bool interior,
+                                              const uint32_t (&pix)[PIX_PER_THREAD], double (&err)[PIX_PER_THREAD]) {
     // sp[k] and the plane offsets are BYTE offsets; the low byte of a 2-byte sample (0x6400 | v) is v
-    const int nch = 3 * g.n_spaces;
-    const int vplane = nch * g.PS * g.es;
+    const int vplane = NCH * g.PS * g.es;
     double t[PIX_PER_THREAD];
 #pragma unroll
     for (int i = 0; i < PIX_PER_THREAD; ++i) t[i] = 0.0;
+#pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
         for (int k = 0; k < g.K; ++k) {
-            const int so = sp[k];
-            unsigned ok = 0;
+            unsigned ok = (1u << PIX_PER_THREAD) - 1u;
+            if (!interior) {
+                const int so = sp[k];
+                ok = 0;
 #pragma unroll
-            for (int i = 0; i < PIX_PER_THREAD; ++i) ok |= (unsigned)(lds_u8(pix[i] + vplane + so) != 0) << i;
-            for (int p = 0; p < nch; ++p) {
-                const int f = (p / 3) * 3 * g.K + 3 * k + (p % 3);
-                const uint32_t off = (uint32_t)(p * g.PS * g.es + so);
+                for (int i = 0; i < PIX_PER_THREAD; ++i) ok |= (unsigned)(lds_u8(pix[i] + vplane + so) != 0) << i;
+            }
+#pragma unroll
+            for (int p = 0; p < NCH; ++p) {
+                const int it = k * NCH + p;
+                const uint32_t off = noff[it];
                 if (pass == 0) {
-                    const double c255 = comp255[f];
+                    const double c255 = comp255[it];
 #pragma unroll
                     for (int i = 0; i < PIX_PER_THREAD; ++i) {
                         const double v = ((ok >> i) & 1u) ? u8_to_double(lds_u8(pix[i] + off)) : -1.0;
                         t[i] = fma(v, c255, t[i]);
                     }
                 } else {
-                    const double c = comp[f], mu = mean[f];
+                    const double c = comp[it], mu = mean[it];
 #pragma unroll
                     for (int i = 0; i < PIX_PER_THREAD; ++i) {
                         const double v = ((ok >> i) & 1u) ? u8_to_double(lds_u8(pix[i] + off)) : -1.0;
@@ -520,7 +530,7 @@ __device__ __forceinline__ double blend2(double a, double b, double w0, double w
 __host__ __device__ constexpr int tile_buffers(int es) { return es == 2 ? 1 : PCM_U8_TILE_BUFS; }
 
 struct ScoreSmem {
-    uint32_t tiles, bars, sched, sp, f0_nodes, f0_leaves, f0_trees, f1_nodes, f1_leaves, f1_trees, pca0, pca1, total;
+    uint32_t tiles, bars, sched, sp, f0_nodes, f0_leaves, f0_trees, f1_nodes, f1_leaves, f1_trees, pca0, pca1, nov_off, total;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
@@ -547,10 +557,11 @@ __host__ __device__ inline ScoreSmem score_smem_layout(const Geom& g, const DevF
             s.f1_leaves = o; o = align_up(o + 8 * f1.n_nodes, 16);
         }
     }
-    s.pca0 = s.pca1 = 0;
+    s.pca0 = s.pca1 = s.nov_off = 0;
     if (novelty) {
         s.pca0 = o; o = align_up(o + 24 * g.F, 16);
         if (blend) { s.pca1 = o; o = align_up(o + 24 * g.F, 16); }
+        s.nov_off = o; o = align_up(o + 4 * g.F, 16);
     }
     s.total = o;
     return s;
@@ -620,20 +631,26 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
             copy_to_smem(reinterpret_cast<double*>(smem + L.f1_leaves), a.f1.leaves, a.f1.n_nodes);
         }
     }
+    // PCA vectors in the ORDER the novelty loop walks the features (tap by tap, plane by plane): entry it = k * nch + p
+    // holds feature f = (p / 3) * 3K + 3k + p % 3 (:272), next to the feature's byte offset inside the tile
     const double *p0c = nullptr, *p0c255 = nullptr, *p0m = nullptr, *p1c = nullptr, *p1c255 = nullptr, *p1m = nullptr;
+    const uint32_t* noff = reinterpret_cast<const uint32_t*>(smem + L.nov_off);
     if (a.novelty) {
+        const int nch = 3 * g.n_spaces;
         double* d0 = reinterpret_cast<double*>(smem + L.pca0);
-        copy_to_smem(d0, a.pca0.comp, g.F);
-        copy_to_smem(d0 + g.F, a.pca0.comp255, g.F);
-        copy_to_smem(d0 + 2 * g.F, a.pca0.mean, g.F);
-        p0c = d0; p0c255 = d0 + g.F; p0m = d0 + 2 * g.F;
-        if (a.blend) {
-            double* d1 = reinterpret_cast<double*>(smem + L.pca1);
-            copy_to_smem(d1, a.pca1.comp, g.F);
-            copy_to_smem(d1 + g.F, a.pca1.comp255, g.F);
-            copy_to_smem(d1 + 2 * g.F, a.pca1.mean, g.F);
-            p1c = d1; p1c255 = d1 + g.F; p1m = d1 + 2 * g.F;
+        double* d1 = reinterpret_cast<double*>(smem + L.pca1);
+        uint32_t* no = reinterpret_cast<uint32_t*>(smem + L.nov_off);
+        for (int it = tid; it < g.F; it += NTHREADS) {
+            const int k = it / nch, p = it - k * nch;
+            const int f = (p / 3) * 3 * g.K + 3 * k + (p % 3);
+            int dr, dc;
+            star_tap(k, dr, dc);
+            no[it] = (uint32_t)((p * g.PS + (dr + g.n) * g.RS + (dc + g.HX)) * ES);
+            d0[it] = a.pca0.comp[f]; d0[g.F + it] = a.pca0.comp255[f]; d0[2 * g.F + it] = a.pca0.mean[f];
+            if (a.blend) { d1[it] = a.pca1.comp[f]; d1[g.F + it] = a.pca1.comp255[f]; d1[2 * g.F + it] = a.pca1.mean[f]; }
         }
+        p0c = d0; p0c255 = d0 + g.F; p0m = d0 + 2 * g.F;
+        p1c = d1; p1c255 = d1 + g.F; p1m = d1 + 2 * g.F;
     }
     grid_dependency_wait();     // K0's planes, tile counter and per-label resets are complete and visible
     grid_launch_dependents();
@@ -702,12 +719,21 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
 #pragma unroll
         for (int i = 0; i < PIX_PER_THREAD; ++i) e[i] = 0.0;
         if (a.novelty) {
-            novelty_error(p0c, p0c255, p0m, a.pca0.mean_dot_comp, sp, g, pix, e);
+            // no tap of this thread's pixels can fall outside the crop: the validity plane need not be read
+            const bool interior = ox >= g.n && ox + g.n < a.cw && ty0 + row0 >= g.n && ty0 + row0 + PIX_PER_THREAD - 1 + g.n < a.ch;
+            auto run = [&](const double* c, const double* c255, const double* mu, double mdc, double (&out)[PIX_PER_THREAD]) {
+                switch (g.n_spaces) {
+                    case 1: novelty_error<3>(c, c255, mu, noff, mdc, sp, g, interior, pix, out); break;
+                    case 2: novelty_error<6>(c, c255, mu, noff, mdc, sp, g, interior, pix, out); break;
+                    default: novelty_error<9>(c, c255, mu, noff, mdc, sp, g, interior, pix, out); break;
+                }
+            };
+            run(p0c, p0c255, p0m, a.pca0.mean_dot_comp, e);
             if (a.blend) {
                 double e1[PIX_PER_THREAD];
 #pragma unroll
                 for (int i = 0; i < PIX_PER_THREAD; ++i) e1[i] = 0.0;
-                novelty_error(p1c, p1c255, p1m, a.pca1.mean_dot_comp, sp, g, pix, e1);
+                run(p1c, p1c255, p1m, a.pca1.mean_dot_comp, e1);
 #pragma unroll
                 for (int i = 0; i < PIX_PER_THREAD; ++i) e[i] = blend2(e[i], e1[i], a.w0, a.w1);
             }
