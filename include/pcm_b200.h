@@ -198,6 +198,14 @@ int pcm_felzenszwalb(const uint8_t* frame, int frame_h, int frame_w, int64_t fra
                      double scale, double sigma, int min_size, const double* kernel, int kernel_radius,
                      int32_t* labels_out, int* n_labels_out);
 
+/* Parity tap: the cost-ordered merge, union-find and min-size passes of pcm_felzenszwalb on a caller-provided
+ * edge list (n_edges edges a[i]-b[i] with non-negative cost[i]; `scale` is the k of k/|C|, already on the scale
+ * of the costs).  Same host code as pcm_felzenszwalb after its edge construction; checked against the
+ * Felzenszwalb-Huttenlocher code the reference vendors (prim/src/FelzenSegment/segment-graph.h:48-81,
+ * segment_image_index.h:85-91) in tests/test_felzenszwalb_ref.py.  labels_out: n_vertices int32. */
+int pcm_felzenszwalb_graph(int n_vertices, int n_edges, const int32_t* a, const int32_t* b, const double* cost,
+                           double scale, int min_size, int32_t* labels_out, int* n_labels_out);
+
 /* ---- a whole sequence of frames in one call (main.py:280-343 for one target) ---- */
 
 /* One frame of a device-resident sequence: [priors from SIFT matches] -> [clear the mask plane] -> update -> [IoU].

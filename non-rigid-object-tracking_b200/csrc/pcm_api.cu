@@ -32,6 +32,8 @@ void scatter_strided(const uint8_t* src, uint8_t* dst, int64_t stride, int n);
 // pcm_felzenszwalb.cpp
 int felzenszwalb(const uint8_t* frame, int64_t stride, int cx, int cy, int w, int h, double scale, double sigma,
                  int min_size, const double* kernel, int radius, int32_t* labels_out);
+int felzenszwalb_graph(int n_vertices, int n_edges, const int32_t* a, const int32_t* b, const double* cost, double scale,
+                       int min_size, int32_t* labels_out);
 }
 
 // ---------------------------------------------------------------------------------
@@ -1439,6 +1441,16 @@ extern "C" int pcm_felzenszwalb(const uint8_t* frame, int H, int W, int64_t stri
     const int n = felzenszwalb(frame, stride, rect[0], rect[1], rect[2], rect[3], scale, sigma, min_size, kernel,
                                kernel_radius, labels_out);
     if (n < 0) return fail(PCM_E_INVALID, "pcm_felzenszwalb: bad arguments");
+    if (n_labels_out) *n_labels_out = n;
+    return PCM_OK;
+}
+
+extern "C" int pcm_felzenszwalb_graph(int n_vertices, int n_edges, const int32_t* a, const int32_t* b, const double* cost,
+                                      double scale, int min_size, int32_t* labels_out, int* n_labels_out) {
+    if (!a || !b || !cost || !labels_out) return fail(PCM_E_INVALID, "pcm_felzenszwalb_graph: NULL argument");
+    if (n_vertices <= 0 || n_vertices > (1 << 28) || n_edges < 0) return fail(PCM_E_INVALID, "pcm_felzenszwalb_graph: bad sizes");
+    const int n = felzenszwalb_graph(n_vertices, n_edges, a, b, cost, scale, min_size, labels_out);
+    if (n < 0) return fail(PCM_E_INVALID, "pcm_felzenszwalb_graph: vertex index out of range or negative / NaN cost");
     if (n_labels_out) *n_labels_out = n;
     return PCM_OK;
 }

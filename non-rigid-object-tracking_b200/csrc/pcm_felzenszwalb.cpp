@@ -85,6 +85,40 @@ static void sort_edges(std::vector<Edge>& e) {
     }
 }
 
+// Stable cost sort, greedy merge (cost < min over both components of Int + scale / |C|), min-size pass,
+// labels = rank of the root index.  Returns the number of segments.
+static int merge_sorted_edges(std::vector<Edge>& edges, size_t n, double sc, int min_size, int32_t* labels_out) {
+    sort_edges(edges);
+
+    std::vector<int> parent(n), size(n, 1);
+    std::vector<double> cint(n, 0.0);
+    std::iota(parent.begin(), parent.end(), 0);
+    for (const Edge& e : edges) {
+        const int s0 = find_root(parent, e.a), s1 = find_root(parent, e.b);
+        if (s0 == s1) continue;
+        if (e.cost < std::min(cint[s0] + sc / size[s0], cint[s1] + sc / size[s1])) {
+            const int total = size[s0] + size[s1];
+            const int r = join(parent, s0, s1);
+            size[r] = total;
+            cint[r] = e.cost;
+        }
+    }
+    for (const Edge& e : edges) {
+        const int s0 = find_root(parent, e.a), s1 = find_root(parent, e.b);
+        if (s0 == s1) continue;
+        if (size[s0] < min_size || size[s1] < min_size) {
+            const int total = size[s0] + size[s1];
+            size[join(parent, s0, s1)] = total;
+        }
+    }
+    // np.unique(root, return_inverse=True)[1]: rank of the root index
+    std::vector<int> rank(n, 0);
+    int count = 0;
+    for (size_t i = 0; i < n; ++i) rank[i] = (find_root(parent, (int)i) == (int)i) ? count++ : -1;
+    for (size_t i = 0; i < n; ++i) labels_out[i] = rank[find_root(parent, (int)i)];
+    return count;
+}
+
 // labels_out[h*w]; returns the number of segments, or -1 on bad arguments
 int felzenszwalb(const uint8_t* frame, int64_t stride, int cx, int cy, int w, int h, double scale, double sigma,
                  int min_size, const double* kernel, int radius, int32_t* labels_out) {
@@ -123,35 +157,19 @@ int felzenszwalb(const uint8_t* frame, int64_t stride, int cx, int cy, int w, in
     for (int r = 1; r < h; ++r) for (int c = 0; c < w; ++c) edges.push_back({cost(r, c, r - 1, c), r * w + c, (r - 1) * w + c});
     for (int r = 1; r < h; ++r) for (int c = 1; c < w; ++c) edges.push_back({cost(r, c, r - 1, c - 1), r * w + c, (r - 1) * w + c - 1});
     for (int r = 1; r < h; ++r) for (int c = 1; c < w; ++c) edges.push_back({cost(r, c - 1, r - 1, c), (r - 1) * w + c, r * w + c - 1});
-    sort_edges(edges);
+    return merge_sorted_edges(edges, n, sc, min_size, labels_out);
+}
 
-    std::vector<int> parent(n), size(n, 1);
-    std::vector<double> cint(n, 0.0);
-    std::iota(parent.begin(), parent.end(), 0);
-    for (const Edge& e : edges) {
-        const int s0 = find_root(parent, e.a), s1 = find_root(parent, e.b);
-        if (s0 == s1) continue;
-        if (e.cost < std::min(cint[s0] + sc / size[s0], cint[s1] + sc / size[s1])) {
-            const int total = size[s0] + size[s1];
-            const int r = join(parent, s0, s1);
-            size[r] = total;
-            cint[r] = e.cost;
-        }
+// Parity tap (pcm_felzenszwalb_graph): the passes above on a caller-provided edge list.
+int felzenszwalb_graph(int n_vertices, int n_edges, const int32_t* a, const int32_t* b, const double* cost, double scale,
+                       int min_size, int32_t* labels_out) {
+    if (n_vertices <= 0 || n_edges < 0) return -1;
+    std::vector<Edge> edges((size_t)n_edges);
+    for (int i = 0; i < n_edges; ++i) {
+        if (a[i] < 0 || a[i] >= n_vertices || b[i] < 0 || b[i] >= n_vertices || !(cost[i] >= 0.0)) return -1;
+        edges[i] = {cost[i], a[i], b[i]};
     }
-    for (const Edge& e : edges) {
-        const int s0 = find_root(parent, e.a), s1 = find_root(parent, e.b);
-        if (s0 == s1) continue;
-        if (size[s0] < min_size || size[s1] < min_size) {
-            const int total = size[s0] + size[s1];
-            size[join(parent, s0, s1)] = total;
-        }
-    }
-    // np.unique(root, return_inverse=True)[1]: rank of the root index
-    std::vector<int> rank(n, 0);
-    int count = 0;
-    for (size_t i = 0; i < n; ++i) rank[i] = (find_root(parent, (int)i) == (int)i) ? count++ : -1;
-    for (size_t i = 0; i < n; ++i) labels_out[i] = rank[find_root(parent, (int)i)];
-    return count;
+    return merge_sorted_edges(edges, (size_t)n_vertices, scale, min_size, labels_out);
 }
 
 }  // namespace pcm

@@ -9,7 +9,7 @@ PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.environ.get("PCM_LIB_PATH") or os.path.join(PKG, "libpcm_b200.so")
 SOURCES = ["pcm_api.cu", "pcm_host_simd.cpp", "pcm_felzenszwalb.cpp"]
-DEPS = ["pcm_api.cu", "pcm_kernels.cuh", "pcm_device.cuh", "pcm_host.h", "pcm_host_simd.cpp", "pcm_felzenszwalb.cpp", "pcm_quickshift.cuh", os.path.join("..", "..", "include", "pcm_b200.h")]
+DEPS = ["pcm_api.cu", "pcm_kernels.cuh", "pcm_device.cuh", "pcm_host.h", "pcm_host_simd.cpp", "pcm_felzenszwalb.cpp", "pcm_quickshift.cuh", "pcm_forest_fit.cuh", "pcm_prior.cuh", os.path.join("..", "..", "include", "pcm_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

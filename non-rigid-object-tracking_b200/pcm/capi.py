@@ -76,6 +76,7 @@ def load_library():
         "pcm_quickshift": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
         "pcm_quickshift_device": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
         "pcm_felzenszwalb": (I, [P, I, I, L, P, D, D, I, P, I, P, C.POINTER(I)]),
+        "pcm_felzenszwalb_graph": (I, [I, I, P, P, P, D, I, P, C.POINTER(I)]),
         "pcm_run_frames": (I, [P, I, I, L, P, L, P, I]),
         "pcm_prior_device": (I, [P, P, P, I, P, L, I, I, P, P, I, P, I, I, I, P]),
         "pcm_fit_rows": (I, [P, P, P, I, I, C.c_longlong]),
@@ -112,7 +113,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_use_own_stream", "pcm_get_stream", "pcm_synchronize",
     "pcm_set_features", "pcm_num_features", "pcm_add_model", "pcm_set_novelty", "pcm_num_models", "pcm_crop_rect",
-    "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device", "pcm_felzenszwalb",
+    "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device", "pcm_felzenszwalb", "pcm_felzenszwalb_graph",
     "pcm_prior_device", "pcm_run_frames", "pcm_fit_forest", "pcm_fit_rows", "pcm_pca_moments", "pcm_pca_residuals", "pcm_convert", "pcm_gather_features",
     "pcm_set_debug", "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_transfer_bytes", "pcm_set_label_cache", "pcm_profile_enable", "pcm_profile_read",
 ]
@@ -168,6 +169,23 @@ def felzenszwalb(frame, rect, scale=100, sigma=0.5, min_size=50):
     n = C.c_int(0)
     rc = lib.pcm_felzenszwalb(_ptr(frame), frame.shape[0], frame.shape[1], frame.strides[0], r, float(scale), float(sigma),
                               int(min_size), _ptr(kernel), radius, _ptr(out), C.byref(n))
+    if rc:
+        raise PcmError(rc, lib.pcm_last_error().decode())
+    return out, n.value
+
+
+def felzenszwalb_graph(n_vertices, a, b, cost, scale, min_size):
+    """Parity tap: the merge / union-find / min-size passes of `felzenszwalb` on an explicit edge list.
+    Returns (labels int32[n_vertices], n_labels)."""
+    lib = load_library()
+    a = np.ascontiguousarray(a, np.int32)
+    b = np.ascontiguousarray(b, np.int32)
+    cost = np.ascontiguousarray(cost, np.float64)
+    assert a.shape == b.shape == cost.shape and a.ndim == 1
+    out = np.empty(int(n_vertices), np.int32)
+    n = C.c_int(0)
+    rc = lib.pcm_felzenszwalb_graph(int(n_vertices), a.size, _ptr(a), _ptr(b), _ptr(cost), float(scale), int(min_size), _ptr(out),
+                                    C.byref(n))
     if rc:
         raise PcmError(rc, lib.pcm_last_error().decode())
     return out, n.value
