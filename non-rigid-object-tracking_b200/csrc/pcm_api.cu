@@ -5,6 +5,7 @@
 // every entry point either runs the CUDA kernels or fails.
 #include "../../include/pcm_b200.h"
 #include "pcm_kernels.cuh"
+#include "pcm_score_variants.h"
 #include "pcm_quickshift.cuh"
 #include "pcm_forest_fit.cuh"
 #include "pcm_prior.cuh"
@@ -378,24 +379,9 @@ static Geom make_geom(int n, int n_spaces, const int* ids) {
     g.K = 1 + 8 * n;
     g.F = 3 * g.K * n_spaces;
     g.n_planes = 3 * n_spaces + 1;
-    g.PH = TILE_H + 2 * n;
-    // 2-byte samples (one half-precision compare per node, no threshold unpacking: 5 instead of 6
-    // instructions per node visit, 2 instead of 4 on the ALU pipe) are built and tested but OFF by
-    // default: measured on B200 the kernel is bound by shared-memory instruction issue (1 LDS per
-    // clock per SM), which this does not change, and the larger planes cost K0 2 us
-    // (score 105.9 vs 106.8 us, planes 17.0 vs 14.9 us).  PCM_TILE_F16=1 turns them on when every
-    // tap offset fits the 16-bit field of a node.
-    auto layout = [&](int es) {
-        g.es = es;
-        g.HX = (es == 2 && n <= 8) ? 8 : 16;
-        g.RS = TILE_W + 2 * g.HX;
-        g.PS = g.RS * g.PH;
-    };
-    layout(2);
-    bool f16 = (long long)g.es * g.n_planes * g.PS < (1 << 16);
-    const char* e = getenv("PCM_TILE_F16");
-    f16 = f16 && e && e[0] == '1';
-    if (!f16) layout(1);
+    g.HX = 16;
+    g.RS = TILE_W + 2 * g.HX;
+    g.PS = (g.RS * (MAX_TILE_H + 2 * n) + 127) / 128 * 128;     // every plane slot starts on a 128-byte boundary (TMA)
     return g;
 }
 
@@ -461,7 +447,7 @@ struct Encoder {
             if (++visited > (size_t)n + 1) { err = "tree is not a tree"; return false; }
             const int i = it.node;
             if (left[i] == -1) {
-                out.nodes[it.entry] = make_node(0u, g.es == 2 ? 0x7c00u /* +inf */ : LEAF_THR, (unsigned)it.entry);
+                out.nodes[it.entry] = make_node(0u, LEAF_THR, (unsigned)it.entry);
                 out.values[it.entry] = value1[i];
                 out.n_leaf++;
                 out.depth = std::max(out.depth, it.depth);
@@ -474,9 +460,8 @@ struct Encoder {
             int plane = 3 * q + ch;
             int thr = tint[i];
             if (thr == -1) { plane = vplane; thr = 0; }   // "tap is outside the crop"
-            const unsigned off = (unsigned)g.es * (unsigned)(plane * g.PS + (dr + g.n) * g.RS + (dc + g.HX));
+            const unsigned off = (unsigned)(plane * g.PS + (dr + g.n) * g.RS + (dc + g.HX));
             if (off >= (1u << 16)) { err = "tap offset overflow"; return false; }
-            if (g.es == 2) thr |= 0x6400;                     // half-precision 1024 + thr
             const int child = (int)out.nodes.size();
             out.nodes.resize(child + 2, make_node(0, 0, 0));
             out.values.resize(child + 2, 0.0);
@@ -497,27 +482,20 @@ static void free_model(Model& m) {
 // ---------------------------------------------------------------------------------
 // API: lifetime
 // ---------------------------------------------------------------------------------
-// K1 instantiations: forest in shared memory or behind L1, walk depth fixed at compile time
-// for the depths the reference's configs use (config.yaml:26 -> 5; benchmark.py:44 -> 7, 10)
-// or taken from the arguments (DEPTH = 0).
-typedef void (*ScoreFn)(const CUtensorMap, const ScoreArgs);
-struct ScoreVariant { bool smem; int depth; bool f16; ScoreFn fn; const char* name; };
-constexpr int N_SCORE_VARIANTS = 16;
-#define PCM_SV(S, D, F) {S, D, F, score_kernel<S, D, F>, "score_kernel<" #S "," #D "," #F ">"}
+// K1 instantiations (pcm_score_variants.h): forest in shared memory or behind L1, walk depth fixed at compile
+// time for the depths the reference's configs use (config.yaml:26 -> 5; benchmark.py:44 -> 7, 10) or taken
+// from the arguments (DEPTH = 0), tile height 24 / 28 / 32 rows.
+constexpr int N_SCORE_VARIANTS = 3 * N_SCORE_VARIANTS_PER_PPT;
 static const ScoreVariant& score_variant(int i) {
-    static const ScoreVariant v[N_SCORE_VARIANTS] = {
-        PCM_SV(true, 5, false),  PCM_SV(true, 7, false),  PCM_SV(true, 10, false),  PCM_SV(true, 0, false),
-        PCM_SV(false, 5, false), PCM_SV(false, 7, false), PCM_SV(false, 10, false), PCM_SV(false, 0, false),
-        PCM_SV(true, 5, true),   PCM_SV(true, 7, true),   PCM_SV(true, 10, true),   PCM_SV(true, 0, true),
-        PCM_SV(false, 5, true),  PCM_SV(false, 7, true),  PCM_SV(false, 10, true),  PCM_SV(false, 0, true),
-    };
-    return v[i];
+    const ScoreVariant* t = i < N_SCORE_VARIANTS_PER_PPT ? score_variants_ppt6()
+                          : i < 2 * N_SCORE_VARIANTS_PER_PPT ? score_variants_ppt7() : score_variants_ppt8();
+    return t[i % N_SCORE_VARIANTS_PER_PPT];
 }
-static const ScoreVariant& pick_score_variant(bool smem, int depth, bool f16) {
+static const ScoreVariant& pick_score_variant(bool smem, int depth, int ppt) {
     int dyn = -1;
     for (int i = 0; i < N_SCORE_VARIANTS; ++i) {
         const ScoreVariant& v = score_variant(i);
-        if (v.smem != smem || v.f16 != f16) continue;
+        if (v.smem != smem || v.ppt != ppt) continue;
         if (v.depth == depth) return v;
         if (v.depth == 0) dyn = i;
     }
@@ -827,8 +805,8 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
 
     // ---- K0: BGR crop -> planar colour planes (+ validity plane) ------------------------
     const Geom& g = h->geom;
-    const long long pitch = ((long long)cw + 127) / 128 * 128;        // samples
-    const long long plane_stride = pitch * ch * g.es;                  // bytes
+    const long long pitch = ((long long)cw + 127) / 128 * 128;        // bytes
+    const long long plane_stride = pitch * ch;                         // bytes
     CUDA_TRY(h->planes.reserve((size_t)plane_stride * g.n_planes));
     CUDA_TRY(h->sched.reserve(64));
     PlanesArgs pa{};
@@ -860,30 +838,15 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
         const int mode = (g.n_spaces == 2 && g.space_id[0] == PCM_SPACE_HSV && g.space_id[1] == PCM_SPACE_LAB) ? 1
                          : (g.n_spaces == 1 && g.space_id[0] == PCM_SPACE_LAB) ? 2 : 0;
         typedef void (*PlanesFn)(const PlanesArgs);
-        static const PlanesFn table[3][2] = {{planes_kernel<0, false>, planes_kernel<0, true>},
-                                             {planes_kernel<1, false>, planes_kernel<1, true>},
-                                             {planes_kernel<2, false>, planes_kernel<2, true>}};
-        CUDA_TRY(launch_chain(table[mode][g.es == 2], dim3(std::max(blocks, 1)), dim3(256), 0, st, pa));
+        static const PlanesFn table[3] = {planes_kernel<0>, planes_kernel<1>, planes_kernel<2>};
+        CUDA_TRY(launch_chain(table[mode], dim3(std::max(blocks, 1)), dim3(256), 0, st, pa));
     }
     CHECK_LAUNCH(h, "planes_kernel");
 
     // ---- K1: TMA-tiled star features + forest(s) [+ novelty] -> P(fg) ------------------------
-    CUtensorMap tmap;
-    {
-        const cuuint64_t gdim[3] = {(cuuint64_t)cw, (cuuint64_t)ch, (cuuint64_t)g.n_planes};
-        const cuuint64_t gstr[2] = {(cuuint64_t)(pitch * g.es), (cuuint64_t)plane_stride};   // bytes
-        const cuuint32_t box[3] = {(cuuint32_t)g.RS, (cuuint32_t)g.PH, (cuuint32_t)g.n_planes};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = h->encode_tiled(&tmap, g.es == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
-                                     h->planes.p, gdim, gstr, box, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(PCM_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d crop", (int)r, cw, ch);
-    }
     ScoreArgs a{};
     a.cw = cw; a.ch = ch;
     a.tiles_x = (cw + TILE_W - 1) / TILE_W;
-    a.tiles_y = (ch + TILE_H - 1) / TILE_H;
     a.g = g;
     a.tile_counter = h->sched.as<unsigned>();
     const Model& m0 = h->models[p->model_cur];
@@ -916,22 +879,52 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     if (!forest_smem) ls = score_smem_layout(a.g, a.f0, a.f1, a.blend, a.novelty, false);
     if ((int)ls.total > h->max_smem_optin)
         return fail(PCM_E_LIMIT, "update: tile needs %u B of shared memory (> %d)", ls.total, h->max_smem_optin);
-    const ScoreVariant& sv = pick_score_variant(forest_smem, a.depth, g.es == 2);
-    // CTAs per SM of this instantiation at this shared-memory size (queried once per distinct size: the runtime call
+    // CTAs per SM of an instantiation at this shared-memory size (queried once per distinct size: the runtime call
     // costs more than launching a small crop's kernel)
-    int occ = 0;
-    {
+    auto occupancy = [&](const ScoreVariant& v, int& occ) -> cudaError_t {
         static std::mutex occ_m;
         static std::vector<std::pair<std::pair<const void*, unsigned>, int>> occ_cache;
         std::lock_guard<std::mutex> lk(occ_m);
-        const std::pair<const void*, unsigned> key{reinterpret_cast<const void*>(sv.fn), ls.total};
+        const std::pair<const void*, unsigned> key{reinterpret_cast<const void*>(v.fn), ls.total};
         for (auto& e : occ_cache)
-            if (e.first == key) { occ = e.second; break; }
-        if (!occ) {
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sv.fn, NTHREADS, ls.total));
-            occ = std::max(occ, 1);
-            if (occ_cache.size() < 4096) occ_cache.push_back({key, occ});
+            if (e.first == key) { occ = e.second; return cudaSuccess; }
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, NTHREADS, ls.total);
+        if (e != cudaSuccess) return e;
+        occ = std::max(occ, 1);
+        if (occ_cache.size() < 4096) occ_cache.push_back({key, occ});
+        return cudaSuccess;
+    };
+    // Tile height: every CTA slot (SMs x CTAs per SM) works through ceil(tiles / slots) tiles of 4 * ppt rows, and the
+    // kernel ends with the slowest slot, so the makespan is ~ ceil(tiles / slots) * ppt row-steps.  Take the ppt that
+    // minimises it (ties: the taller tile -- fewer halo rows, fewer scheduler round trips).  PCM_PPT forces one.
+    int ppt = MAX_PPT, occ = 0;
+    {
+        static const int forced = [] { const char* e = getenv("PCM_PPT"); return e ? atoi(e) : 0; }();
+        CUDA_TRY(occupancy(pick_score_variant(forest_smem, a.depth, MAX_PPT), occ));
+        const long long slots = (long long)h->sm_count * occ;
+        long long best = -1;
+        for (int c = MAX_PPT; c >= MIN_PPT; --c) {
+            const long long tiles = (long long)a.tiles_x * ((ch + ROW_GROUPS * c - 1) / (ROW_GROUPS * c));
+            const long long cost = (tiles + slots - 1) / slots * c;
+            if (best < 0 || cost < best) { best = cost; ppt = c; }
         }
+        if (forced >= MIN_PPT && forced <= MAX_PPT) ppt = forced;
+    }
+    const int tile_h = ROW_GROUPS * ppt;
+    a.tiles_y = (ch + tile_h - 1) / tile_h;
+    const ScoreVariant& sv = pick_score_variant(forest_smem, a.depth, ppt);
+    CUDA_TRY(occupancy(sv, occ));
+    CUtensorMap tmap;
+    {
+        // planar u8 crop tensor {x, y, plane}; a box is ONE plane of a tile with its halo, zero fill outside the crop
+        const cuuint64_t gdim[3] = {(cuuint64_t)cw, (cuuint64_t)ch, (cuuint64_t)g.n_planes};
+        const cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)plane_stride};   // bytes
+        const cuuint32_t box[3] = {(cuuint32_t)g.RS, (cuuint32_t)(tile_h + 2 * g.n), 1u};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = h->encode_tiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->planes.p, gdim, gstr, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(PCM_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d crop", (int)r, cw, ch);
     }
     const int n_tiles = a.tiles_x * a.tiles_y;
     const int grid = std::min(n_tiles, h->sm_count * occ);

@@ -11,11 +11,12 @@
 namespace pcm {
 
 // ---- tile geometry of the fused score kernel ---------------------------------
+// A tile is TILE_W columns x 4 * PPT rows: 8 warps = 4 row groups x 2 column halves, a thread walks PPT
+// vertically adjacent pixels of one column.  PPT is a compile-time parameter of the kernel (6, 7 or 8);
+// the host picks, per launch, the value with the shortest makespan: ceil(tiles / CTA slots) * PPT
+// (a 1080p crop on 296 slots: 32-row tiles = 1020 tiles = 3.45 rounds -> 4 x 8 row-steps, 28-row tiles =
+// 1170 tiles = 3.95 rounds -> 4 x 7).
 constexpr int TILE_W = 64;            // output pixels per tile row
-#ifndef PCM_TILE_H
-#define PCM_TILE_H 32
-#endif
-constexpr int TILE_H = PCM_TILE_H;    // output rows per tile
 #ifndef PCM_NTHREADS
 #define PCM_NTHREADS 256
 #endif
@@ -23,14 +24,15 @@ constexpr int TILE_H = PCM_TILE_H;    // output rows per tile
 #define PCM_MIN_CTAS 2
 #endif
 constexpr int NTHREADS = PCM_NTHREADS;   // warp = (row group, 32-column half of the tile)
-constexpr int PIX_PER_THREAD = TILE_H / (NTHREADS / 64);   // rows of one column handled by a thread
+constexpr int ROW_GROUPS = NTHREADS / 64;
+constexpr int MIN_PPT = 6, MAX_PPT = 8;
+constexpr int MAX_TILE_H = ROW_GROUPS * MAX_PPT;
 constexpr int MAX_NEIGHBORS = 16;
 constexpr int MAX_SPACES = 3;
 constexpr int LAB_CBRT_SIZE = 2041;
 constexpr int LAB_CBRT_PAD = 2048;
 
-static_assert(TILE_W == 64 && (NTHREADS / 64) * PIX_PER_THREAD == TILE_H && NTHREADS % 64 == 0,
-              "thread mapping: NTHREADS/64 row groups x 2 column halves, PIX_PER_THREAD rows each");
+static_assert(TILE_W == 64 && NTHREADS % 64 == 0, "thread mapping: NTHREADS/64 row groups x 2 column halves");
 
 // Lookup tables built on the host at pcm_create (pcm_api.cu: build_tables).
 struct ColorTables {
@@ -48,15 +50,12 @@ struct Geom {
     int K;            // 1 + 8 n taps
     int F;            // 3 K Q features
     int n_planes;     // 3 Q + 1 (last plane = in-crop validity)
-    int es;           // bytes per tile sample: 1 = u8 value v; 2 = the half-precision number
-                      // 1024 + v stored as 0x6400 | v (thresholds are stored the same way, so a node
-                      // test is one half-precision compare with no unpacking; 0 outside the crop)
     int HX;           // horizontal halo of the smem tile in samples: the TMA box must start on a
-                      // 16-byte boundary of the row (measured: any other x faults on sm_100a), so 16
-                      // samples for u8 and 8 (n <= 8) or 16 for 2-byte samples
-    int PH;           // tile rows incl. vertical halo: TILE_H + 2 n
-    int RS;           // plane row stride in the smem tile (samples) = TMA box width = TILE_W + 2 HX
-    int PS;           // plane stride in the smem tile (samples)
+                      // 16-byte boundary of the row (measured: any other x faults on sm_100a) -> 16
+    int RS;           // plane row stride in the smem tile (bytes) = TMA box width = TILE_W + 2 HX
+    int PS;           // plane stride in the smem tile (bytes): RS * (MAX_TILE_H + 2 n) rounded up to 128 -- the
+                      // SAME for every tile height, so that the tap offsets packed into the forests do not
+                      // depend on the tile height chosen per launch (each plane of a tile is its own TMA box)
 };
 
 __host__ __device__ inline void star_tap(int k, int& dr, int& dc) {

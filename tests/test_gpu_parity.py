@@ -506,15 +506,16 @@ def test_device_pointer_path_equals_host_path():
     h.close()
 
 
-def test_two_byte_tile_variant_in_a_subprocess():
-    """PCM_TILE_F16=1 (2-byte tile samples, half-precision node tests, single-buffered tiles) is an
-    opt-in K1/K0 variant: the forest-shape, random-forest and golden-sequence parity cases must
-    hold for it as well."""
+@pytest.mark.parametrize("ppt", [6, 7, 8])
+def test_every_tile_height_in_a_subprocess(ppt):
+    """K1 is instantiated for tiles of 24, 28 and 32 rows (6 / 7 / 8 pixels per thread) and the library picks the height with
+    the shortest makespan per launch; PCM_PPT forces one.  The forest-shape, random-forest, golden-sequence, full-HD,
+    prior and fuzz parity cases must hold for each of them."""
     import subprocess
     import sys
-    env = dict(os.environ, PCM_TILE_F16="1")
+    env = dict(os.environ, PCM_PPT=str(ppt))
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
-                          "forest_shapes or random_forests or update_sequence or full_hd or priors"],
+                          "forest_shapes or random_forests or update_sequence or full_hd or priors or fuzz or guard_band"],
                          env=env, capture_output=True, text=True, timeout=1200,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
