@@ -24,6 +24,7 @@
 #ifndef PCM_B200_H
 #define PCM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -140,6 +141,16 @@ int pcm_update(pcm_handle* h, const uint8_t* frame, int frame_h, int frame_w, in
  * only the 1 MiB chunks whose bytes changed.  on = 0 switches that off: every call uploads the
  * whole map (default: on). */
 int pcm_set_label_cache(pcm_handle* h, int on);
+
+/* labels == NULL with no pcm_quickshift pending: the label map the previous pcm_update left on the device is used
+ * again (same crop size required; n_labels is ignored).  The caller vouches that the map has not changed -- the
+ * plugin does this when its over-segmentation provider hands back the very same read-only array. */
+
+/* Page-lock a long-lived caller buffer (cudaHostRegister, portable) so that pcm_update / pcm_iou copy a frame or truth
+ * image that lies inside it straight from the caller's memory instead of staging it through the handle's pinned
+ * buffers.  The range must stay allocated until pcm_host_unregister(p) (same start address). */
+int pcm_host_register(void* p, size_t bytes);
+int pcm_host_unregister(void* p);
 
 /* Same work on DEVICE buffers, asynchronous on the handle's stream.
  * d_mask is a dense plane (pixel stride 1) of frame_h x frame_w, rows

@@ -181,6 +181,37 @@ struct PinBuf {
 };
 
 // ---------------------------------------------------------------------------------
+// caller-registered (page-locked) host ranges: pcm_host_register / pcm_host_unregister.
+// A frame / truth image that lies inside one is copied to the device straight from the caller's
+// memory; everything else is staged through the handle's pinned buffers.
+// ---------------------------------------------------------------------------------
+class HostRegistry {
+public:
+    static HostRegistry& instance() { static HostRegistry r; return r; }
+    bool contains(const void* p, size_t bytes) {
+        const uintptr_t lo = reinterpret_cast<uintptr_t>(p), hi = lo + bytes;
+        std::lock_guard<std::mutex> lk(m_);
+        for (const R& r : v_)
+            if (lo >= r.lo && hi <= r.hi) return true;
+        return false;
+    }
+    void add(const void* p, size_t bytes) {
+        std::lock_guard<std::mutex> lk(m_);
+        v_.push_back({reinterpret_cast<uintptr_t>(p), reinterpret_cast<uintptr_t>(p) + bytes});
+    }
+    bool remove(const void* p) {
+        std::lock_guard<std::mutex> lk(m_);
+        for (size_t i = 0; i < v_.size(); ++i)
+            if (v_[i].lo == reinterpret_cast<uintptr_t>(p)) { v_.erase(v_.begin() + i); return true; }
+        return false;
+    }
+private:
+    struct R { uintptr_t lo, hi; };
+    std::mutex m_;
+    std::vector<R> v_;
+};
+
+// ---------------------------------------------------------------------------------
 // models
 // ---------------------------------------------------------------------------------
 struct Model {
@@ -248,6 +279,16 @@ struct pcm_handle {
     DevBuf prior_scratch;         // pcm_prior_device: per-keypoint match records
     long long fit_rows_id = 0;
     int fit_n = 0, fit_F = 0;
+
+    // host-path mask mirror: `mask` (device) and `h_mask` (pinned) are dense mir_H x mir_W planes that follow the
+    // caller's mask image.  pcm_update writes its crop into both; pcm_iou compares the caller's bytes with the pinned
+    // copy band by band (mir_band_rows rows each) and uploads only the bands that differ (or were never synchronised:
+    // mir_ok[b] == 0), so the mask pcm_update has just produced is not sent back to the device.
+    int mir_H = 0, mir_W = 0, mir_band_rows = 0;
+    std::vector<uint8_t> mir_ok;
+    cudaEvent_t band_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int resident_labels = 0;      // n_labels of the label map the last host pcm_update left on the device (0: none)
+    int resident_cw = 0, resident_ch = 0;
 
     // description of the last update (for pcm_debug_last)
     int last_cw = 0, last_ch = 0, last_S = 0;
@@ -586,6 +627,7 @@ extern "C" void pcm_destroy(pcm_handle* h) {
         b->release();
     for (PinBuf* b : {&h->h_frame, &h->h_labels, &h->h_priors, &h->h_mask, &h->h_small, &h->h_noise}) b->release();
     for (auto& t : h->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (cudaEvent_t e : h->band_events) if (e) cudaEventDestroy(e);
     for (auto e : h->free_events) cudaEventDestroy(e);
     h->err_buf.release();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -894,19 +936,22 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
         if (occ_cache.size() < 4096) occ_cache.push_back({key, occ});
         return cudaSuccess;
     };
-    // Tile height: every CTA slot (SMs x CTAs per SM) works through ceil(tiles / slots) tiles of 4 * ppt rows, and the
-    // kernel ends with the slowest slot, so the makespan is ~ ceil(tiles / slots) * ppt row-steps.  Take the ppt that
-    // minimises it (ties: the taller tile -- fewer halo rows, fewer scheduler round trips).  PCM_PPT forces one.
+    // Tile height.  Measured on B200 (profiles/README.md, round 2): the kernel is throughput-bound on pipes the co-resident
+    // CTAs of an SM share, so a partially filled last round of tiles does NOT cost a whole round (an SM with one CTA left
+    // runs it nearly twice as fast) -- the time follows the fluid model  max(1, tiles / slots) * t_tile(ppt)  with
+    // t_tile ~ 0.4 + 0.075 * ppt (per-tile and per-tree overheads do not shrink with the rows): at 1080p 32-row tiles win
+    // (108.4 us vs 116.8 / 115.5 us for 28 / 24 rows), and shorter tiles pay only for crops with fewer tiles than CTA slots,
+    // where every CTA has a single tile and a shorter tile simply ends sooner.  PCM_PPT forces a height.
     int ppt = MAX_PPT, occ = 0;
     {
         static const int forced = [] { const char* e = getenv("PCM_PPT"); return e ? atoi(e) : 0; }();
         CUDA_TRY(occupancy(pick_score_variant(forest_smem, a.depth, MAX_PPT), occ));
-        const long long slots = (long long)h->sm_count * occ;
-        long long best = -1;
+        const double slots = (double)h->sm_count * occ;
+        double best = -1.0;
         for (int c = MAX_PPT; c >= MIN_PPT; --c) {
-            const long long tiles = (long long)a.tiles_x * ((ch + ROW_GROUPS * c - 1) / (ROW_GROUPS * c));
-            const long long cost = (tiles + slots - 1) / slots * c;
-            if (best < 0 || cost < best) { best = cost; ppt = c; }
+            const double tiles = (double)a.tiles_x * ((ch + ROW_GROUPS * c - 1) / (ROW_GROUPS * c));
+            const double cost = std::max(1.0, tiles / slots) * (0.4 + 0.075 * c);
+            if (best < 0 || cost < best - 1e-9) { best = cost; ppt = c; }
         }
         if (forced >= MIN_PPT && forced <= MAX_PPT) ppt = forced;
     }
@@ -982,25 +1027,54 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     return PCM_OK;
 }
 
-// D2H of the dense crop mask, wait, scatter into the caller's (possibly interleaved) mask
+// (re)size the mask mirror for an H x W mask image; a new size forgets what was synchronised
+static int ensure_mirror(pcm_handle* h, int H, int W) {
+    if (h->mir_H == H && h->mir_W == W && h->mask.p && h->h_mask.p) return PCM_OK;
+    const size_t n = (size_t)H * W;
+    CUDA_TRY(h->h_mask.reserve(n));
+    CUDA_TRY(h->mask.reserve(n));
+    h->mir_H = H; h->mir_W = W;
+    h->mir_band_rows = std::max(1, (int)((1u << 18) / (size_t)W));          // ~256 KiB bands
+    h->mir_ok.assign((size_t)(H + h->mir_band_rows - 1) / h->mir_band_rows, 0);
+    return PCM_OK;
+}
+
+// D2H of the crop region of the mask mirror in a few row bands; every band is scattered into the caller's (possibly
+// interleaved) mask as soon as it has arrived, while the next one is still on the bus
 static int finish_host_update(pcm_handle* h, const int rect[4], uint8_t* mask, int64_t mask_row_stride, int64_t mask_pixel_stride) {
-    const int cx = rect[0], cy = rect[1], cw = rect[2], ch = rect[3];
+    const int cx = rect[0], cy = rect[1], cw = rect[2], ch = rect[3], W = h->mir_W;
     const size_t npx = (size_t)cw * ch;
     cudaStream_t st = h->stream;
-    CUDA_TRY(cudaMemcpyAsync(h->h_mask.p, h->mask.p, npx, cudaMemcpyDeviceToHost, st));
+    uint8_t* hm = h->h_mask.as<uint8_t>();
+    const uint8_t* dm = h->mask.as<uint8_t>();
+    const int n_bands = (int)std::min<size_t>(4, std::max<size_t>(1, npx >> 19));    // >= 512 Ki px per band
+    for (int b = 0; b < n_bands; ++b) {
+        const int r0 = (int)((long long)ch * b / n_bands), r1 = (int)((long long)ch * (b + 1) / n_bands);
+        const size_t o = (size_t)(cy + r0) * W + cx;
+        CUDA_TRY(cudaMemcpy2DAsync(hm + o, (size_t)W, dm + o, (size_t)W, (size_t)cw, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, st));
+        if (b + 1 < n_bands) {
+            if (!h->band_events[b]) CUDA_TRY(cudaEventCreateWithFlags(&h->band_events[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(h->band_events[b], st));
+        }
+    }
     h->bytes_d2h += (int64_t)npx + (int64_t)sizeof(int);
-    int rc = check_label_error(h);
-    if (rc) return rc;
-    h->trace.lap(HostTrace::UPD_WAIT);
-    const uint8_t* hm = h->h_mask.as<uint8_t>();
     HostPool& pool = HostPool::instance();
-    const int parts = std::min(pool.size(), std::max(1, (int)(npx >> 16)));
-    pool.parallel_for(parts, [&](int part) {
-        const int a0 = (int)((long long)ch * part / parts), a1 = (int)((long long)ch * (part + 1) / parts);
-        for (int r = a0; r < a1; ++r)
-            scatter_strided(hm + (size_t)r * cw, mask + (size_t)(cy + r) * mask_row_stride + (size_t)cx * mask_pixel_stride,
-                            mask_pixel_stride, cw);
-    });
+    for (int b = 0; b < n_bands; ++b) {
+        if (b + 1 < n_bands) CUDA_TRY(cudaEventSynchronize(h->band_events[b]));
+        else {
+            int rc = check_label_error(h);                // last band: waits for the stream
+            if (rc) return rc;
+        }
+        if (b == 0) h->trace.lap(HostTrace::UPD_WAIT);
+        const int r0 = (int)((long long)ch * b / n_bands), r1 = (int)((long long)ch * (b + 1) / n_bands);
+        const int parts = std::min(pool.size(), std::max(1, (int)(((size_t)(r1 - r0) * cw) >> 16)));
+        pool.parallel_for(parts, [&](int part) {
+            const int a0 = r0 + (int)((long long)(r1 - r0) * part / parts), a1 = r0 + (int)((long long)(r1 - r0) * (part + 1) / parts);
+            for (int r = a0; r < a1; ++r)
+                scatter_strided(hm + (size_t)(cy + r) * W + cx, mask + (size_t)(cy + r) * mask_row_stride + (size_t)cx * mask_pixel_stride,
+                                mask_pixel_stride, cw);
+        });
+    }
     h->trace.lap(HostTrace::UPD_SCATTER);
     return PCM_OK;
 }
@@ -1018,10 +1092,9 @@ static int update_from_quickshift(pcm_handle* h, const uint8_t* frame, int H, in
     CUDA_TRY(cudaSetDevice(h->device));
     h->trace.start();
     const int cw = rect[2], ch = rect[3];
-    const size_t npx = (size_t)cw * ch;
     cudaStream_t st = h->stream;
-    CUDA_TRY(h->h_mask.reserve(npx));
-    CUDA_TRY(h->mask.reserve(npx));
+    rc = ensure_mirror(h, H, W);
+    if (rc) return rc;
     CUDA_TRY(h->h_small.reserve(64));
     const float* d_priors = nullptr;
     if (priors) {
@@ -1036,7 +1109,7 @@ static int update_from_quickshift(pcm_handle* h, const uint8_t* frame, int H, in
     h->trace.lap(HostTrace::UPD_STAGE);
     const int crop_rect[4] = {0, 0, cw, ch};
     rc = enqueue_update(h, h->frame.as<uint8_t>(), ch, cw, (int64_t)cw * 3, crop_rect, h->qs_labels.as<int32_t>(),
-                        h->qs_n_labels, d_priors, params, h->mask.as<uint8_t>(), cw, 0, 0, h->keep_pre);
+                        h->qs_n_labels, d_priors, params, h->mask.as<uint8_t>(), W, rect[0], rect[1], h->keep_pre);
     if (rc) return rc;
     h->trace.lap(HostTrace::UPD_ENQUEUE);
     return finish_host_update(h, rect, mask, mask_row_stride, mask_pixel_stride);
@@ -1058,7 +1131,16 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
                           const int32_t* labels, int n_labels, const float* priors, const pcm_update_params* params,
                           uint8_t* mask, int64_t mask_row_stride, int64_t mask_pixel_stride) {
     if (!h || !frame || !mask) return fail(PCM_E_INVALID, "pcm_update: NULL argument");
-    if (!labels) return update_from_quickshift(h, frame, H, W, stride, rect, priors, params, mask, mask_row_stride, mask_pixel_stride);
+    if (!labels && h->qs_valid) return update_from_quickshift(h, frame, H, W, stride, rect, priors, params, mask, mask_row_stride, mask_pixel_stride);
+    // labels == NULL without a pending quickshift: the label map of the previous pcm_update (same crop size) is still on
+    // the device and the caller vouches that it has not changed
+    const bool reuse_labels = !labels;
+    if (reuse_labels) {
+        if (!rect || h->resident_labels <= 0 || rect[2] != h->resident_cw || rect[3] != h->resident_ch)
+            return fail(PCM_E_STATE, "pcm_update: labels == NULL needs a preceding pcm_quickshift of the same frame and rect, or a "
+                                     "preceding pcm_update with a label map for a crop of the same size");
+        n_labels = h->resident_labels;
+    }
     h->qs_valid = false;                               // the resident crop is about to be replaced
     h->chain_tail = false;
     const bool auto_labels = n_labels <= 0;            // n_labels = max(label) + 1, found while staging
@@ -1071,76 +1153,102 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
     const size_t npx = (size_t)cw * ch, row_bytes = (size_t)cw * 3;
     cudaStream_t st = h->stream;
     h->trace.start();
-    // host -> pinned -> device: only the crop travels
+    // host -> device: only the crop travels.  A crop inside a caller-registered (page-locked) range is copied
+    // straight from the caller's memory, anything else goes through the handle's pinned staging buffer.
+    const uint8_t* crop0 = frame + (size_t)cy * stride + (size_t)cx * 3;
+    const bool direct = HostRegistry::instance().contains(crop0, (size_t)(ch - 1) * stride + row_bytes);
     const void* old_hl = h->h_labels.p;
     const void* old_dl = h->labels.p;
-    CUDA_TRY(h->h_frame.reserve(npx * 3));
+    if (!direct) CUDA_TRY(h->h_frame.reserve(npx * 3));
     CUDA_TRY(h->frame.reserve(npx * 3));
-    CUDA_TRY(h->h_labels.reserve(npx * sizeof(int32_t)));
+    if (!reuse_labels) CUDA_TRY(h->h_labels.reserve(npx * sizeof(int32_t)));
     CUDA_TRY(h->labels.reserve(npx * sizeof(int32_t)));
-    CUDA_TRY(h->h_mask.reserve(npx));
-    CUDA_TRY(h->mask.reserve(npx));
+    rc = ensure_mirror(h, H, W);
+    if (rc) return rc;
     CUDA_TRY(h->h_small.reserve(64));
+    if (reuse_labels && old_dl != h->labels.p) return fail(PCM_E_STATE, "pcm_update: the resident label map was lost");
     CUDA_TRY(cudaStreamSynchronize(st));   // staging buffers are reused between calls
     h->trace.lap(HostTrace::UPD_SYNC);
+    h->resident_labels = 0;
 
-    // One dispatch of the host pool stages everything: an item is a ~1 MiB chunk of crop rows or
+    uint8_t* df = h->frame.as<uint8_t>();
+    if (direct) {
+        CUDA_TRY(cudaMemcpy2DAsync(df, row_bytes, crop0, (size_t)stride, row_bytes, (size_t)ch, cudaMemcpyHostToDevice, st));
+        h->bytes_h2d += (int64_t)(npx * 3);
+    }
+    // One dispatch of the host pool stages everything else: an item is a ~1 MiB chunk of crop rows or
     // of the label map; the worker copies it into pinned memory and queues its H2D copy itself,
     // so the DMA of finished chunks overlaps the staging of the others.  A label chunk whose
     // bytes equal the previous call's (kept in the pinned buffer) is neither copied nor re-sent.
     constexpr size_t CHUNK = 1u << 20;
     const int rows_per_chunk = std::max(1, (int)(CHUNK / std::max<size_t>(row_bytes, 1)));
-    const int n_frame_items = (ch + rows_per_chunk - 1) / rows_per_chunk;
+    const int n_frame_items = direct ? 0 : (ch + rows_per_chunk - 1) / rows_per_chunk;
     const size_t label_bytes = npx * sizeof(int32_t);
-    const int n_label_items = (int)((label_bytes + CHUNK - 1) / CHUNK);
-    const bool cache_ok = h->label_cache_on && h->label_cache_px == npx && old_hl == h->h_labels.p && old_dl == h->labels.p &&
-                          (int)h->label_chunk_max.size() == n_label_items;
-    if (!cache_ok) h->label_chunk_max.assign(n_label_items, -1);
-    h->label_cache_px = 0;                 // invalid until every chunk is staged
-    uint8_t* hf = h->h_frame.as<uint8_t>();
-    uint8_t* hl = h->h_labels.as<uint8_t>();
-    uint8_t* df = h->frame.as<uint8_t>();
-    uint8_t* dl = h->labels.as<uint8_t>();
-    const uint8_t* lsrc = reinterpret_cast<const uint8_t*>(labels);
-    int* chunk_max = h->label_chunk_max.data();
-    std::atomic<int> cuda_err{0};
-    const int device = h->device;
-    HostPool& pool = HostPool::instance();
-    pool.parallel_for(n_frame_items + n_label_items, [&](int item) {
-        cudaSetDevice(device);
-        cudaError_t e = cudaSuccess;
-        if (item < n_frame_items) {
+    const int n_label_items = reuse_labels ? 0 : (int)((label_bytes + CHUNK - 1) / CHUNK);
+    if (!reuse_labels) {
+        const bool cache_ok = h->label_cache_on && h->label_cache_px == npx && old_hl == h->h_labels.p && old_dl == h->labels.p &&
+                              (int)h->label_chunk_max.size() == n_label_items;
+        if (!cache_ok) h->label_chunk_max.assign(n_label_items, -1);
+        h->label_cache_px = 0;                 // invalid until every chunk is staged
+        uint8_t* hf = h->h_frame.as<uint8_t>();
+        uint8_t* hl = h->h_labels.as<uint8_t>();
+        uint8_t* dl = h->labels.as<uint8_t>();
+        const uint8_t* lsrc = reinterpret_cast<const uint8_t*>(labels);
+        int* chunk_max = h->label_chunk_max.data();
+        std::atomic<int> cuda_err{0};
+        const int device = h->device;
+        HostPool& pool = HostPool::instance();
+        pool.parallel_for(n_frame_items + n_label_items, [&](int item) {
+            cudaSetDevice(device);
+            cudaError_t e = cudaSuccess;
+            if (item < n_frame_items) {
+                const int r0 = item * rows_per_chunk, r1 = std::min(ch, r0 + rows_per_chunk);
+                for (int r = r0; r < r1; ++r)
+                    memcpy(hf + (size_t)r * row_bytes, frame + (size_t)(cy + r) * stride + (size_t)cx * 3, row_bytes);
+                e = cudaMemcpyAsync(df + (size_t)r0 * row_bytes, hf + (size_t)r0 * row_bytes, (size_t)(r1 - r0) * row_bytes,
+                                    cudaMemcpyHostToDevice, st);
+                h->bytes_h2d += (int64_t)((size_t)(r1 - r0) * row_bytes);
+            } else {
+                const int c = item - n_frame_items;
+                const size_t o = (size_t)c * CHUNK, len = std::min(CHUNK, label_bytes - o);
+                if (!(cache_ok && memcmp(hl + o, lsrc + o, len) == 0)) {
+                    const int32_t* src = reinterpret_cast<const int32_t*>(lsrc + o);
+                    int32_t* dst = reinterpret_cast<int32_t*>(hl + o);
+                    int mx = -1;
+                    const size_t n = len / sizeof(int32_t);
+                    for (size_t i = 0; i < n; ++i) { const int32_t v = src[i]; dst[i] = v; mx = v > mx ? v : mx; }
+                    chunk_max[c] = mx;
+                    e = cudaMemcpyAsync(dl + o, hl + o, len, cudaMemcpyHostToDevice, st);
+                    h->bytes_h2d += (int64_t)len;
+                }
+            }
+            if (e != cudaSuccess) cuda_err.store((int)e);
+        });
+        if (cuda_err.load()) return fail(PCM_E_CUDA, "pcm_update: staging copy failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
+        h->label_cache_px = npx;
+        if (auto_labels) {
+            int mx = -1;
+            for (int c = 0; c < n_label_items; ++c) mx = std::max(mx, chunk_max[c]);
+            if (mx < 0) return fail(PCM_E_LABEL, "pcm_update: label map has no non-negative label");
+            n_labels = mx + 1;
+        }
+    } else if (n_frame_items) {
+        uint8_t* hf = h->h_frame.as<uint8_t>();
+        std::atomic<int> cuda_err{0};
+        const int device = h->device;
+        HostPool::instance().parallel_for(n_frame_items, [&](int item) {
+            cudaSetDevice(device);
             const int r0 = item * rows_per_chunk, r1 = std::min(ch, r0 + rows_per_chunk);
             for (int r = r0; r < r1; ++r)
                 memcpy(hf + (size_t)r * row_bytes, frame + (size_t)(cy + r) * stride + (size_t)cx * 3, row_bytes);
-            e = cudaMemcpyAsync(df + (size_t)r0 * row_bytes, hf + (size_t)r0 * row_bytes, (size_t)(r1 - r0) * row_bytes,
-                                cudaMemcpyHostToDevice, st);
+            cudaError_t e = cudaMemcpyAsync(df + (size_t)r0 * row_bytes, hf + (size_t)r0 * row_bytes, (size_t)(r1 - r0) * row_bytes,
+                                            cudaMemcpyHostToDevice, st);
             h->bytes_h2d += (int64_t)((size_t)(r1 - r0) * row_bytes);
-        } else {
-            const int c = item - n_frame_items;
-            const size_t o = (size_t)c * CHUNK, len = std::min(CHUNK, label_bytes - o);
-            if (!(cache_ok && memcmp(hl + o, lsrc + o, len) == 0)) {
-                const int32_t* src = reinterpret_cast<const int32_t*>(lsrc + o);
-                int32_t* dst = reinterpret_cast<int32_t*>(hl + o);
-                int mx = -1;
-                const size_t n = len / sizeof(int32_t);
-                for (size_t i = 0; i < n; ++i) { const int32_t v = src[i]; dst[i] = v; mx = v > mx ? v : mx; }
-                chunk_max[c] = mx;
-                e = cudaMemcpyAsync(dl + o, hl + o, len, cudaMemcpyHostToDevice, st);
-                h->bytes_h2d += (int64_t)len;
-            }
-        }
-        if (e != cudaSuccess) cuda_err.store((int)e);
-    });
-    if (cuda_err.load()) return fail(PCM_E_CUDA, "pcm_update: staging copy failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
-    h->label_cache_px = npx;
-    h->trace.lap(HostTrace::UPD_STAGE);
-    if (auto_labels) {
-        int mx = -1;
-        for (int c = 0; c < n_label_items; ++c) mx = std::max(mx, chunk_max[c]);
-        if (mx < 0) return fail(PCM_E_LABEL, "pcm_update: label map has no non-negative label");
-        n_labels = mx + 1;
+            if (e != cudaSuccess) cuda_err.store((int)e);
+        });
+        if (cuda_err.load()) return fail(PCM_E_CUDA, "pcm_update: staging copy failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
     }
+    h->trace.lap(HostTrace::UPD_STAGE);
     const float* d_priors = nullptr;
     if (priors) {
         CUDA_TRY(h->h_priors.reserve(sizeof(float) * (size_t)n_labels));
@@ -1152,10 +1260,14 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
     }
     const int crop_rect[4] = {0, 0, cw, ch};
     rc = enqueue_update(h, h->frame.as<uint8_t>(), ch, cw, (int64_t)row_bytes, crop_rect, h->labels.as<int32_t>(),
-                        n_labels, d_priors, params, h->mask.as<uint8_t>(), cw, 0, 0, h->keep_pre);
+                        n_labels, d_priors, params, h->mask.as<uint8_t>(), W, cx, cy, h->keep_pre);
     if (rc) return rc;
     h->trace.lap(HostTrace::UPD_ENQUEUE);
-    return finish_host_update(h, rect, mask, mask_row_stride, mask_pixel_stride);
+    rc = finish_host_update(h, rect, mask, mask_row_stride, mask_pixel_stride);
+    if (rc) return rc;
+    h->resident_labels = n_labels;
+    h->resident_cw = cw; h->resident_ch = ch;
+    return PCM_OK;
 }
 
 static int enqueue_iou(pcm_handle* h, const uint8_t* d_mask, int64_t mask_row_stride, const uint8_t* d_truth,
@@ -1196,9 +1308,11 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const size_t npx = (size_t)height * width, tbytes = npx * truth_channels;
-    CUDA_TRY(h->h_mask.reserve(npx));
-    CUDA_TRY(h->mask.reserve(npx));
-    CUDA_TRY(h->h_frame.reserve(tbytes));
+    const size_t trow = (size_t)width * truth_channels;
+    const bool direct = HostRegistry::instance().contains(truth, (size_t)(height - 1) * truth_row_stride + trow);
+    int rc = ensure_mirror(h, height, width);
+    if (rc) return rc;
+    if (!direct) CUDA_TRY(h->h_frame.reserve(tbytes));
     CUDA_TRY(h->frame.reserve(tbytes));
     CUDA_TRY(h->counts.reserve(2 * sizeof(int64_t)));
     CUDA_TRY(h->h_small.reserve(64));
@@ -1211,17 +1325,22 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
     uint8_t* ht = h->h_frame.as<uint8_t>();
     uint8_t* dm = h->mask.as<uint8_t>();
     uint8_t* dt = h->frame.as<uint8_t>();
-    // one pool dispatch: an item is a band of rows of the truth or of the mask; the worker packs
-    // it densely into pinned memory and queues its own H2D copy
-    const size_t trow = (size_t)width * truth_channels;
+    if (direct) {
+        CUDA_TRY(cudaMemcpy2DAsync(dt, trow, truth, (size_t)truth_row_stride, trow, (size_t)height, cudaMemcpyHostToDevice, st));
+        h->bytes_h2d += (int64_t)tbytes;
+    }
+    // one pool dispatch: an item is a band of rows of the truth (packed densely into pinned memory, its H2D copy queued by
+    // the worker) or of the mask.  A mask band is first COMPARED with the pinned mirror of what the device already holds
+    // (the crop pcm_update produced, bands uploaded by an earlier call): only a band that differs is copied and re-sent.
     const int rows_t = std::max(1, (int)((1u << 18) / std::max<size_t>(trow, 1)));   // 256 KiB bands: enough items for
-    const int rows_m = std::max(1, (int)((1u << 18) / (size_t)width));               // every pool thread at 1080p
-    const int n_t = (height + rows_t - 1) / rows_t, n_m = (height + rows_m - 1) / rows_m;
+    const int rows_m = h->mir_band_rows;                                             // every pool thread at 1080p
+    const int n_t = direct ? 0 : (height + rows_t - 1) / rows_t, n_m = (height + rows_m - 1) / rows_m;
+    uint8_t* band_ok = h->mir_ok.data();
     std::atomic<int> cuda_err{0};
     const int device = h->device;
     pool.parallel_for(n_t + n_m, [&](int item) {
         cudaSetDevice(device);
-        cudaError_t e;
+        cudaError_t e = cudaSuccess;
         if (item < n_t) {
             const int r0 = item * rows_t, r1 = std::min(height, r0 + rows_t);
             for (int r = r0; r < r1; ++r) memcpy(ht + (size_t)r * trow, truth + (size_t)r * truth_row_stride, trow);
@@ -1229,23 +1348,42 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
                                 cudaMemcpyHostToDevice, st);
             h->bytes_h2d += (int64_t)((size_t)(r1 - r0) * trow);
         } else {
-            const int r0 = (item - n_t) * rows_m, r1 = std::min(height, r0 + rows_m);
-            for (int r = r0; r < r1; ++r) {
-                const uint8_t* src = mask + (size_t)r * mask_row_stride;
-                uint8_t* dst = hm + (size_t)r * width;
-                gather_strided(src, mask_pixel_stride, dst, width);
+            const int b = item - n_t;
+            const int r0 = b * rows_m, r1 = std::min(height, r0 + rows_m);
+            int r = r0;
+            if (band_ok[b]) {
+                uint8_t tmp[4096];
+                for (; r < r1; ++r) {                           // rows equal to the mirror need nothing
+                    const uint8_t* src = mask + (size_t)r * mask_row_stride;
+                    const uint8_t* have = hm + (size_t)r * width;
+                    bool same = true;
+                    if (mask_pixel_stride == 1) same = memcmp(src, have, (size_t)width) == 0;
+                    else
+                        for (int c0 = 0; c0 < width && same; c0 += (int)sizeof tmp) {
+                            const int n = std::min<int>((int)sizeof tmp, width - c0);
+                            gather_strided(src + (size_t)c0 * mask_pixel_stride, mask_pixel_stride, tmp, n);
+                            same = memcmp(tmp, have + c0, (size_t)n) == 0;
+                        }
+                    if (!same) break;
+                }
             }
-            e = cudaMemcpyAsync(dm + (size_t)r0 * width, hm + (size_t)r0 * width, (size_t)(r1 - r0) * width,
-                                cudaMemcpyHostToDevice, st);
-            h->bytes_h2d += (int64_t)((size_t)(r1 - r0) * width);
+            if (r < r1) {                                       // from the first differing row on: refresh mirror and device
+                for (int q = r; q < r1; ++q) gather_strided(mask + (size_t)q * mask_row_stride, mask_pixel_stride, hm + (size_t)q * width, width);
+                e = cudaMemcpyAsync(dm + (size_t)r * width, hm + (size_t)r * width, (size_t)(r1 - r) * width, cudaMemcpyHostToDevice, st);
+                h->bytes_h2d += (int64_t)((size_t)(r1 - r) * width);
+                band_ok[b] = 1;
+            }
         }
         if (e != cudaSuccess) cuda_err.store((int)e);
     });
-    if (cuda_err.load()) return fail(PCM_E_CUDA, "pcm_iou: staging copy failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
+    if (cuda_err.load()) {
+        h->mir_ok.assign(h->mir_ok.size(), 0);
+        return fail(PCM_E_CUDA, "pcm_iou: staging copy failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
+    }
     h->trace.lap(HostTrace::IOU_STAGE);
     CUDA_TRY(cudaMemsetAsync(h->counts.p, 0, 2 * sizeof(int64_t), st));
-    int rc = pcm_iou_device(h, h->mask.as<uint8_t>(), width, h->frame.as<uint8_t>(), (int64_t)width * truth_channels,
-                            truth_channels, height, width, h->counts.as<int64_t>());
+    rc = pcm_iou_device(h, h->mask.as<uint8_t>(), width, h->frame.as<uint8_t>(), (int64_t)width * truth_channels,
+                        truth_channels, height, width, h->counts.as<int64_t>());
     if (rc) return rc;
     int64_t* hc = h->h_small.as<int64_t>() + 2;
     CUDA_TRY(cudaMemcpyAsync(hc, h->counts.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -1254,7 +1392,26 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
     h->trace.lap(HostTrace::IOU_WAIT);
     counts[0] = hc[0];
     counts[1] = hc[1];
-    h->last_valid = false;   // frame / mask scratch was reused
+    h->last_valid = false;   // frame scratch was reused
+    return PCM_OK;
+}
+
+extern "C" int pcm_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return fail(PCM_E_INVALID, "pcm_host_register: NULL / empty range");
+    if (HostRegistry::instance().contains(p, bytes)) return PCM_OK;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PCM_E_CUDA, "pcm_host_register: cudaHostRegister failed: %s", cudaGetErrorString(e));
+    }
+    HostRegistry::instance().add(p, bytes);
+    return PCM_OK;
+}
+
+extern "C" int pcm_host_unregister(void* p) {
+    if (!p) return fail(PCM_E_INVALID, "pcm_host_unregister: NULL");
+    if (!HostRegistry::instance().remove(p)) return fail(PCM_E_STATE, "pcm_host_unregister: %p was not registered here", p);
+    CUDA_TRY(cudaHostUnregister(p));
     return PCM_OK;
 }
 

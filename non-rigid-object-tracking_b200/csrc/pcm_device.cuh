@@ -13,9 +13,8 @@ namespace pcm {
 // ---- tile geometry of the fused score kernel ---------------------------------
 // A tile is TILE_W columns x 4 * PPT rows: 8 warps = 4 row groups x 2 column halves, a thread walks PPT
 // vertically adjacent pixels of one column.  PPT is a compile-time parameter of the kernel (6, 7 or 8);
-// the host picks, per launch, the value with the shortest makespan: ceil(tiles / CTA slots) * PPT
-// (a 1080p crop on 296 slots: 32-row tiles = 1020 tiles = 3.45 rounds -> 4 x 8 row-steps, 28-row tiles =
-// 1170 tiles = 3.95 rounds -> 4 x 7).
+// the host picks it per launch (pcm_api.cu, enqueue_update): 8 whenever there are at least as many
+// tiles as CTA slots, fewer rows for small crops where every CTA has a single tile.
 constexpr int TILE_W = 64;            // output pixels per tile row
 #ifndef PCM_NTHREADS
 #define PCM_NTHREADS 256

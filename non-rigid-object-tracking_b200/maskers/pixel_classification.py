@@ -78,6 +78,8 @@ class PixelClassificationNonRigidMasker(Masker):
         self.segment_fn = segment_fn or (None if (self.native_quickshift or self.native_felzenszwalb)
                                          else make_segment_provider(params["over_segmentation"]))
         self._qs_noise_shape = None
+        self._seg_prev = None                  # (provider's array object, crop shape) of the label map resident on the device
+        self.reuse_resident_labels = True      # False: every update sends its label map, whatever the provider returns
         self._prior_fn = prior_fn              # SiftPrior() on first use (SIFT + FLANN objects are not free to build)
         self.prevForegroundMask = None
 
@@ -197,6 +199,7 @@ class PixelClassificationNonRigidMasker(Masker):
                                      key=(self.cache_tag, self.index, (x, y, w, h)))
             return self.prior_fn(self.prevFrame, self.prevForegroundMask, crop, segs, n)
         n_labels, priors = 0, None             # 0: the library takes max(label) + 1 while staging
+        same_labels, self._seg_next = False, None
         if self.native_quickshift:
             # quickshift(crop, kernel_size=3, max_dist=6, ratio=0.5, random_seed=42) (:71); the label
             # map stays on the device and only travels to the host when the SIFT prior needs it
@@ -227,15 +230,23 @@ class PixelClassificationNonRigidMasker(Masker):
                     else:
                         segments, n_labels = segment()
             else:
-                segments = np.ascontiguousarray(self.segment_fn(crop), np.int32)
+                raw = self.segment_fn(crop)
+                # a provider that hands back the very same READ-ONLY array vouches that the map has not changed: it is
+                # still on the device from the previous update and does not travel again (pcm_update, labels == NULL)
+                same_labels = (self.reuse_resident_labels and self._seg_prev is not None and raw is self._seg_prev[0] and self._seg_prev[1] == (h, w)
+                               and isinstance(raw, np.ndarray) and not raw.flags.writeable)
+                self._seg_next = (raw, (h, w))
+                segments = np.ascontiguousarray(raw, np.int32)
             if want_prior:
                 n_labels = int(segments.max()) + 1
                 with stages.stage("sift_prior"):
                     priors = prior(segments, n_labels)
 
         p, blend = self._frame_params()
+        self._seg_prev = None
         with stages.stage("gpu_update_call"):
-            self.native.update(frame, (x, y, w, h), segments, n_labels, priors, p, mask, channel=2)
+            self.native.update(frame, (x, y, w, h), None if same_labels else segments, n_labels, priors, p, mask, channel=2)
+        self._seg_prev, self._seg_next = self._seg_next, None
         return self._advance(blend, crop, mask[ys, xs, 2])
 
     # -- state machine shared by update() and update_resident() (reference :81-87, :114-126) ----------

@@ -77,6 +77,8 @@ def load_library():
         "pcm_quickshift_device": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
         "pcm_felzenszwalb": (I, [P, I, I, L, P, D, D, I, P, I, P, C.POINTER(I)]),
         "pcm_felzenszwalb_graph": (I, [I, I, P, P, P, D, I, P, C.POINTER(I)]),
+        "pcm_host_register": (I, [P, C.c_size_t]),
+        "pcm_host_unregister": (I, [P]),
         "pcm_run_frames": (I, [P, I, I, L, P, L, P, I]),
         "pcm_prior_device": (I, [P, P, P, I, P, L, I, I, P, P, I, P, I, I, I, P]),
         "pcm_fit_rows": (I, [P, P, P, I, I, C.c_longlong]),
@@ -116,6 +118,7 @@ EXPORTED_SYMBOLS = [
     "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device", "pcm_felzenszwalb", "pcm_felzenszwalb_graph",
     "pcm_prior_device", "pcm_run_frames", "pcm_fit_forest", "pcm_fit_rows", "pcm_pca_moments", "pcm_pca_residuals", "pcm_convert", "pcm_gather_features",
     "pcm_set_debug", "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_transfer_bytes", "pcm_set_label_cache", "pcm_profile_enable", "pcm_profile_read",
+    "pcm_host_register", "pcm_host_unregister",
 ]
 
 KERNEL_NAMES = ["score", "segment_reduce", "segment_decide", "segment_resolve", "mask_dilate", "iou", "planes"]
@@ -172,6 +175,26 @@ def felzenszwalb(frame, rect, scale=100, sigma=0.5, min_size=50):
     if rc:
         raise PcmError(rc, lib.pcm_last_error().decode())
     return out, n.value
+
+
+def host_register(arr):
+    """Page-lock a long-lived C-contiguous array (cudaHostRegister): `Handle.update` / `Handle.iou_counts` then copy a
+    frame or truth image inside it straight from this memory instead of staging it.  Keep the array alive until
+    `host_unregister(arr)`."""
+    lib = load_library()
+    if not arr.flags.c_contiguous:
+        raise ValueError("host_register needs a C-contiguous array")
+    rc = lib.pcm_host_register(C.c_void_p(arr.ctypes.data), arr.nbytes)
+    if rc:
+        raise PcmError(rc, lib.pcm_last_error().decode())
+    return arr
+
+
+def host_unregister(arr):
+    lib = load_library()
+    rc = lib.pcm_host_unregister(C.c_void_p(arr.ctypes.data))
+    if rc:
+        raise PcmError(rc, lib.pcm_last_error().decode())
 
 
 def felzenszwalb_graph(n_vertices, a, b, cost, scale, min_size):
