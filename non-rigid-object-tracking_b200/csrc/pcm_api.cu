@@ -75,11 +75,14 @@ struct HostTrace {
     long calls[N] = {0};
     std::chrono::steady_clock::time_point t;
     void start() { if (trace_enabled()) t = std::chrono::steady_clock::now(); }
+    long seen[N] = {0};
     void lap(int id) {
         if (!trace_enabled()) return;
         auto now = std::chrono::steady_clock::now();
-        ms[id] += std::chrono::duration<double, std::milli>(now - t).count();
-        calls[id]++;
+        if (++seen[id] > 8) {                 // the first calls allocate (pinned memory, events): not what is being traced
+            ms[id] += std::chrono::duration<double, std::milli>(now - t).count();
+            calls[id]++;
+        }
         t = now;
     }
     void report() const {
@@ -1034,7 +1037,7 @@ static int ensure_mirror(pcm_handle* h, int H, int W) {
     CUDA_TRY(h->h_mask.reserve(n));
     CUDA_TRY(h->mask.reserve(n));
     h->mir_H = H; h->mir_W = W;
-    h->mir_band_rows = std::max(1, (int)((1u << 18) / (size_t)W));          // ~256 KiB bands
+    h->mir_band_rows = std::max(1, (int)((1u << 16) / (size_t)W));          // ~64 KiB bands: enough items to balance the pool
     h->mir_ok.assign((size_t)(H + h->mir_band_rows - 1) / h->mir_band_rows, 0);
     return PCM_OK;
 }

@@ -72,7 +72,7 @@ def test_registered_buffers_and_mask_mirror():
         counts = h.iou_counts(mask[:, :, 2], truths[0])
         sent = h.transfer_bytes[0] - b0[0] - hgt * wid
         assert counts == orc.iou_counts(mask[:, :, 2], truths[0])
-        assert 0 < sent <= 2 * (1 << 18) + 2 * wid, sent
+        assert 0 < sent <= 2 * (1 << 16) + 2 * wid, sent
         # a different mask image with other content: whatever differs is refreshed
         other = np.zeros((hgt, wid, 3), np.uint8)
         other[:, :, 2] = (rng.random((hgt, wid)) < 0.5) * 255
