@@ -290,6 +290,8 @@ struct pcm_handle {
     int mir_H = 0, mir_W = 0, mir_band_rows = 0;
     std::vector<uint8_t> mir_ok;
     cudaEvent_t band_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;   // host path: row bands of a page-locked caller frame travel here (BandFeed)
+    cudaEvent_t feed_events[4] = {nullptr, nullptr, nullptr, nullptr};
     int resident_labels = 0;      // n_labels of the label map the last host pcm_update left on the device (0: none)
     int resident_cw = 0, resident_ch = 0;
 
@@ -631,6 +633,8 @@ extern "C" void pcm_destroy(pcm_handle* h) {
     for (PinBuf* b : {&h->h_frame, &h->h_labels, &h->h_priors, &h->h_mask, &h->h_small, &h->h_noise}) b->release();
     for (auto& t : h->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t e : h->band_events) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->feed_events) if (e) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto e : h->free_events) cudaEventDestroy(e);
     h->err_buf.release();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -832,9 +836,26 @@ static int validate_update(pcm_handle* h, int H, int W, const int rect[4], int n
 }
 
 // Enqueue K1..K3 for one crop.  All pointers are device pointers.
+// rows of `width` bytes, `spitch` / `dpitch` apart: ONE flat copy when both sides are contiguous (a 2-D copy of a
+// page-locked caller buffer runs row by row and was measured at about half the PCIe rate)
+static cudaError_t copy_rows_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                                   cudaMemcpyKind kind, cudaStream_t st) {
+    if (height == 0 || width == 0) return cudaSuccess;
+    if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * height, kind, st);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, st);
+}
+
+// feed != NULL (host path with a page-locked caller frame): the crop rows are not on the device yet.  They are copied in a
+// few row bands on the handle's copy stream, and the colour conversion (K0) and scoring (K1) of a band start as soon as its
+// rows (plus the vertical halo of its last tile row) have arrived -- the copy of band b+1 overlaps the kernels of band b.
+struct BandFeed {
+    const uint8_t* src;       // first byte of the crop in the caller's frame
+    size_t spitch;            // bytes between its rows
+};
 static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, int64_t stride, const int rect[4],
                           const int32_t* d_labels, int S, const float* d_priors, const pcm_update_params* p,
-                          uint8_t* d_mask, int64_t mask_stride, int mask_cx, int mask_cy, bool want_pre) {
+                          uint8_t* d_mask, int64_t mask_stride, int mask_cx, int mask_cy, bool want_pre,
+                          const BandFeed* feed = nullptr) {
     const int cx = rect[0], cy = rect[1], cw = rect[2], ch = rect[3];
     const size_t npx = (size_t)cw * ch;
     cudaStream_t st = h->stream;
@@ -872,11 +893,18 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     pa.rmin = h->rmin.as<int>();
     pa.rmax = h->rmax.as<int>();
     pa.n_flagged = reinterpret_cast<int*>(seg + sl.nflag);
-    pa.early = (pdl_enabled() && st == h->own_stream && h->chain_tail) ? 1 : 0;
-    {
+    pa.early = (pdl_enabled() && st == h->own_stream && h->chain_tail && !feed) ? 1 : 0;
+    // rows [r0, r1) of the crop; only the first launch of a frame resets the per-label accumulators
+    auto launch_k0 = [&](int r0, int r1, bool first) -> int {
+        PlanesArgs b = pa;
+        b.cy = cy + r0;
+        b.ch = r1 - r0;
+        b.planes = pa.planes + (long long)r0 * pitch;
+        if (!first) b.n_labels = 0;
+        b.reset_flagged = first ? 1 : 0;
         // persistent blocks: the 6.6 KB of lookup tables are staged once per block, so a block
         // should convert many pixel groups
-        const long long groups = (long long)ch * ((cw + 3) / 4);
+        const long long groups = (long long)(r1 - r0) * ((cw + 3) / 4);
         static const int per_sm = [] { const char* e = getenv("PCM_K0_BLOCKS_PER_SM"); int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
         const int blocks = (int)std::min<long long>((groups + 255) / 256, (long long)h->sm_count * per_sm);
         KernelTimer kt(h, 6);
@@ -884,9 +912,10 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
                          : (g.n_spaces == 1 && g.space_id[0] == PCM_SPACE_LAB) ? 2 : 0;
         typedef void (*PlanesFn)(const PlanesArgs);
         static const PlanesFn table[3] = {planes_kernel<0>, planes_kernel<1>, planes_kernel<2>};
-        CUDA_TRY(launch_chain(table[mode], dim3(std::max(blocks, 1)), dim3(256), 0, st, pa));
-    }
-    CHECK_LAUNCH(h, "planes_kernel");
+        CUDA_TRY(launch_chain(table[mode], dim3(std::max(blocks, 1)), dim3(256), 0, st, b));
+        CHECK_LAUNCH(h, "planes_kernel");
+        return PCM_OK;
+    };
 
     // ---- K1: TMA-tiled star features + forest(s) [+ novelty] -> P(fg) ------------------------
     ScoreArgs a{};
@@ -974,13 +1003,40 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(PCM_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d crop", (int)r, cw, ch);
     }
-    const int n_tiles = a.tiles_x * a.tiles_y;
-    const int grid = std::min(n_tiles, h->sm_count * occ);
-    {
+    const int tiles_y = a.tiles_y;
+    auto launch_k1 = [&](int ty0, int ty1) -> int {
+        a.tile_y0 = ty0;
+        a.tiles_y = ty1 - ty0;
+        const int n_tiles = a.tiles_x * a.tiles_y;
+        const int grid = std::min(n_tiles, h->sm_count * occ);
         KernelTimer kt(h, 0);
         CUDA_TRY(launch_chain(sv.fn, dim3(grid), dim3(NTHREADS), ls.total, st, tmap, a));
+        CHECK_LAUNCH(h, sv.name);
+        return PCM_OK;
+    };
+    int rc = PCM_OK;
+    if (!feed) {
+        if ((rc = launch_k0(0, ch, true)) || (rc = launch_k1(0, tiles_y))) return rc;
+    } else {
+        // bands of whole tile rows, at least ~512 Ki px each; band b needs the crop rows up to the lower halo of its last tile row
+        const int n_bands = (int)std::max<long long>(1, std::min<long long>({4, (long long)tiles_y, (long long)(npx >> 19)}));
+        if (!h->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        uint8_t* df = const_cast<uint8_t*>(d_frame);          // the handle's own crop buffer (rows `stride` apart)
+        const size_t row_bytes = (size_t)cw * 3;
+        int rows_done = 0;
+        for (int b = 0; b < n_bands; ++b) {
+            const int ty0 = (int)((long long)tiles_y * b / n_bands), ty1 = (int)((long long)tiles_y * (b + 1) / n_bands);
+            const int rows_end = b + 1 == n_bands ? ch : std::min(ch, ty1 * tile_h + g.n);
+            CUDA_TRY(copy_rows_async(df + (size_t)rows_done * stride, (size_t)stride, feed->src + (size_t)rows_done * feed->spitch, feed->spitch,
+                                     row_bytes, (size_t)(rows_end - rows_done), cudaMemcpyHostToDevice, h->copy_stream));
+            if (!h->feed_events[b]) CUDA_TRY(cudaEventCreateWithFlags(&h->feed_events[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(h->feed_events[b], h->copy_stream));
+            CUDA_TRY(cudaStreamWaitEvent(st, h->feed_events[b], 0));
+            if ((rc = launch_k0(rows_done, rows_end, b == 0)) || (rc = launch_k1(ty0, ty1))) return rc;
+            rows_done = rows_end;
+        }
+        h->bytes_h2d += (int64_t)(npx * 3);
     }
-    CHECK_LAUNCH(h, sv.name);
 
     // ---- K2: per-label decision (+ exact path) ------------------------------------------------
     DecideArgs da{};
@@ -1054,7 +1110,7 @@ static int finish_host_update(pcm_handle* h, const int rect[4], uint8_t* mask, i
     for (int b = 0; b < n_bands; ++b) {
         const int r0 = (int)((long long)ch * b / n_bands), r1 = (int)((long long)ch * (b + 1) / n_bands);
         const size_t o = (size_t)(cy + r0) * W + cx;
-        CUDA_TRY(cudaMemcpy2DAsync(hm + o, (size_t)W, dm + o, (size_t)W, (size_t)cw, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(copy_rows_async(hm + o, (size_t)W, dm + o, (size_t)W, (size_t)cw, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, st));
         if (b + 1 < n_bands) {
             if (!h->band_events[b]) CUDA_TRY(cudaEventCreateWithFlags(&h->band_events[b], cudaEventDisableTiming));
             CUDA_TRY(cudaEventRecord(h->band_events[b], st));
@@ -1070,7 +1126,7 @@ static int finish_host_update(pcm_handle* h, const int rect[4], uint8_t* mask, i
         }
         if (b == 0) h->trace.lap(HostTrace::UPD_WAIT);
         const int r0 = (int)((long long)ch * b / n_bands), r1 = (int)((long long)ch * (b + 1) / n_bands);
-        const int parts = std::min(pool.size(), std::max(1, (int)(((size_t)(r1 - r0) * cw) >> 16)));
+        const int parts = std::min(pool.size(), std::max(1, (int)(((size_t)(r1 - r0) * cw) >> 14)));
         pool.parallel_for(parts, [&](int part) {
             const int a0 = r0 + (int)((long long)(r1 - r0) * part / parts), a1 = r0 + (int)((long long)(r1 - r0) * (part + 1) / parts);
             for (int r = a0; r < a1; ++r)
@@ -1175,10 +1231,7 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
     h->resident_labels = 0;
 
     uint8_t* df = h->frame.as<uint8_t>();
-    if (direct) {
-        CUDA_TRY(cudaMemcpy2DAsync(df, row_bytes, crop0, (size_t)stride, row_bytes, (size_t)ch, cudaMemcpyHostToDevice, st));
-        h->bytes_h2d += (int64_t)(npx * 3);
-    }
+    const BandFeed feed{crop0, (size_t)stride};      // direct: enqueue_update copies the rows itself, band by band
     // One dispatch of the host pool stages everything else: an item is a ~1 MiB chunk of crop rows or
     // of the label map; the worker copies it into pinned memory and queues its H2D copy itself,
     // so the DMA of finished chunks overlaps the staging of the others.  A label chunk whose
@@ -1263,7 +1316,7 @@ extern "C" int pcm_update(pcm_handle* h, const uint8_t* frame, int H, int W, int
     }
     const int crop_rect[4] = {0, 0, cw, ch};
     rc = enqueue_update(h, h->frame.as<uint8_t>(), ch, cw, (int64_t)row_bytes, crop_rect, h->labels.as<int32_t>(),
-                        n_labels, d_priors, params, h->mask.as<uint8_t>(), W, cx, cy, h->keep_pre);
+                        n_labels, d_priors, params, h->mask.as<uint8_t>(), W, cx, cy, h->keep_pre, direct ? &feed : nullptr);
     if (rc) return rc;
     h->trace.lap(HostTrace::UPD_ENQUEUE);
     rc = finish_host_update(h, rect, mask, mask_row_stride, mask_pixel_stride);
@@ -1329,7 +1382,7 @@ extern "C" int pcm_iou(pcm_handle* h, const uint8_t* mask, int64_t mask_row_stri
     uint8_t* dm = h->mask.as<uint8_t>();
     uint8_t* dt = h->frame.as<uint8_t>();
     if (direct) {
-        CUDA_TRY(cudaMemcpy2DAsync(dt, trow, truth, (size_t)truth_row_stride, trow, (size_t)height, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(copy_rows_async(dt, trow, truth, (size_t)truth_row_stride, trow, (size_t)height, cudaMemcpyHostToDevice, st));
         h->bytes_h2d += (int64_t)tbytes;
     }
     // one pool dispatch: an item is a band of rows of the truth (packed densely into pinned memory, its H2D copy queued by

@@ -54,15 +54,17 @@ private:
         int n = 0;
         if (const char* e = getenv("PCM_HOST_THREADS")) n = atoi(e);
         if (n <= 0) {
-            // measured on the 16-vCPU B200 host: staging saturates with 4-6 threads.  Under a
-            // one-process-per-GPU launcher the cores are shared by LOCAL_WORLD_SIZE ranks.
+            // the strided mask scatter / gather of a 1080p frame is bound by per-core memory bandwidth on the B200 hosts
+            // (16 cores, ~10 GB/s each: measured 0.14 ms with 6 threads, less with more), so take three quarters of the
+            // cores this rank may use, up to 12.  Under a one-process-per-GPU launcher the cores are shared by
+            // LOCAL_WORLD_SIZE ranks.
             const unsigned hw = std::thread::hardware_concurrency();
             int ranks = 1;
             if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e);
             if (ranks < 1) ranks = 1;
             const int cores = (int)hw / ranks;
             n = cores * 3 / 4;
-            if (n > 6) n = 6;
+            if (n > 12) n = 12;
             if (cores < 4) spin_us_ = 50;     // no spare core to spin on
         }
         if (const char* e = getenv("PCM_HOST_SPIN_US")) spin_us_ = atoi(e);

@@ -96,6 +96,7 @@ struct PlanesArgs {
     int* rmax;
     int* n_flagged;
     int early;                // 1: the predecessor on the stream is this handle's own K3 / K5 (see below)
+    int reset_flagged;        // 1: first K0 launch of a frame (a frame fed in row bands has several; n_labels = 0 in the others)
 };
 
 // MODE 1: features "<n> hsv_lab" (config.yaml:30), MODE 2: "<n> lab" (benchmark.py:48), MODE 0: any
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
     // foreign kernel that writes `frame`, so K0 waits before it reads or resets anything.
     if (!a.early) grid_dependency_wait();
     grid_launch_dependents();
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *a.tile_counter = 0; *a.n_flagged = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *a.tile_counter = 0; if (a.reset_flagged) *a.n_flagged = 0; }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_labels; i += gridDim.x * blockDim.x) {
         a.sum[i] = 0.0; a.asum[i] = 0.0; a.area[i] = 0; a.rmin[i] = 0x7fffffff; a.rmax[i] = -1;
     }
@@ -320,7 +321,8 @@ __device__ __forceinline__ void segment_flush(const SegAcc& s, int lab, double s
 
 struct ScoreArgs {
     int cw, ch;                      // crop size
-    int tiles_x, tiles_y;
+    int tiles_x, tiles_y;            // tiles of THIS launch: tile rows [tile_y0, tile_y0 + tiles_y)
+    int tile_y0;
     Geom g;
     unsigned* tile_counter;          // dynamic tile scheduler (zeroed by K0)
     DevForest f0, f1;
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
             const uint32_t bar = bars_s + 8 * buf;
             mbar_expect_tx(bar, box_bytes);
             // one {RS, PH, 1} box per plane, each to its fixed plane slot of the buffer
-            const int x = (t % a.tiles_x) * TILE_W - g.HX, y = (t / a.tiles_x) * TILE_H - g.n;
+            const int x = (t % a.tiles_x) * TILE_W - g.HX, y = (a.tile_y0 + t / a.tiles_x) * TILE_H - g.n;
             for (int pl = 0; pl < g.n_planes; ++pl)
                 tma_load_3d(tiles_s + buf * tile_bytes + pl * g.PS, &tmap, x, y, pl, bar);
         }
@@ -650,7 +652,7 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
         mbar_wait(bars_s + 8 * buf, (phase >> buf) & 1u);
         phase ^= 1u << buf;
 
-        const int tx0 = (tile % a.tiles_x) * TILE_W, ty0 = (tile / a.tiles_x) * TILE_H;
+        const int tx0 = (tile % a.tiles_x) * TILE_W, ty0 = (a.tile_y0 + tile / a.tiles_x) * TILE_H;
         const int ox = tx0 + col;
         uint32_t pix[PIX_PER_THREAD];
 #pragma unroll

@@ -30,11 +30,11 @@ def _want_mask(forest, frame, rect, seg, k=3):
     return orc.dilate(orc.saliency_mask(scores, seg), k)
 
 
-def test_registered_buffers_and_mask_mirror():
+@pytest.mark.parametrize("hgt,wid", [(540, 960), (1000, 1100)])      # the larger frame travels in two row bands
+def test_registered_buffers_and_mask_mirror(hgt, wid):
     from pcm import capi
     from pcm.providers import grid_segments
     rng = np.random.default_rng(5)
-    hgt, wid = 540, 960
     h, forest = _setup(rng, hgt, wid)
     prm = capi.Handle.make_params(0, dilation_kernel=3)
     frames = [rng.integers(0, 256, (hgt, wid, 3), dtype=np.uint8) for _ in range(3)]
@@ -86,6 +86,34 @@ def test_registered_buffers_and_mask_mirror():
         for a in frames + truths:
             capi.host_unregister(a)
     step(2, False)
+    h.close()
+
+
+def test_registered_sub_crop_in_row_bands():
+    """A crop that is not the whole frame, large enough to be fed in several row bands (2-D copies from the page-locked
+    frame on the copy stream, K0 / K1 per band): same mask as the staged path and the oracle."""
+    from pcm import capi
+    from pcm.providers import grid_segments
+    rng = np.random.default_rng(8)
+    hgt, wid = 1300, 1500
+    h, forest = _setup(rng, hgt, wid)
+    prm = capi.Handle.make_params(0, dilation_kernel=5)
+    frame = rng.integers(0, 256, (hgt, wid, 3), dtype=np.uint8)
+    rect = (37, 21, 1401, 1233)                          # 1.7 M px: three bands; odd width
+    x, y, w, hh = rect
+    seg = grid_segments(frame[y:y + hh, x:x + w], 14)
+    want = _want_mask(forest, frame, rect, seg, 5)
+    staged = np.zeros((hgt, wid, 3), np.uint8)
+    h.update(frame, rect, seg, 0, None, prm, staged)
+    assert np.array_equal(staged[y:y + hh, x:x + w, 2], want)
+    capi.host_register(frame)
+    try:
+        for _ in range(3):
+            direct = np.zeros((hgt, wid, 3), np.uint8)
+            h.update(frame, rect, seg, 0, None, prm, direct)
+            assert np.array_equal(direct, staged)
+    finally:
+        capi.host_unregister(frame)
     h.close()
 
 
