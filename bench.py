@@ -466,7 +466,7 @@ def run_b200(args, rank, world, local_rank):
     # the same loop with the label-chunk cache off: all four inputs travel every step
     h.set_label_cache(False)
     masker.reuse_resident_labels = False
-    n2 = max(3, e2e_steps // 3)
+    n2 = max(3, e2e_steps // 3) if not args.no_resent else 1
     host_step(0)
     barrier()
     moved2 = h.transfer_bytes
@@ -822,6 +822,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-only", action="store_true", help="tuning aid: shorten the device-resident leg")
+    ap.add_argument("--no-resent", action="store_true", help="tuning aid: shorten the labels-resent-every-step e2e leg")
     ap.add_argument("--no-register", action="store_true", help="e2e leg: do not page-lock the host frames (every input is staged)")
     ap.add_argument("--workload", default="1080p", choices=["1080p", "sweep"],
                     help="1080p: frames/s (default, the driver's metric); sweep: benchmark.py grid, sequences/s")

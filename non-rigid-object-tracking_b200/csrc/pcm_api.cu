@@ -70,7 +70,7 @@ static bool trace_enabled() {
     return v == 1;
 }
 struct HostTrace {
-    enum { UPD_SYNC, UPD_STAGE, UPD_ENQUEUE, UPD_WAIT, UPD_SCATTER, IOU_STAGE, IOU_WAIT, N };
+    enum { UPD_SYNC, UPD_STAGE, UPD_ENQUEUE, UPD_WAIT, UPD_D2H, UPD_SCATTER, IOU_STAGE, IOU_WAIT, N };
     double ms[N] = {0};
     long calls[N] = {0};
     std::chrono::steady_clock::time_point t;
@@ -88,10 +88,13 @@ struct HostTrace {
     void report() const {
         if (!trace_enabled()) return;
         static const char* names[N] = {"update: reserve+sync", "update: stage+H2D issue", "update: enqueue kernels",
-                                       "update: wait (H2D, kernels, D2H)", "update: scatter mask", "iou: stage+H2D issue",
+                                       "update: wait (H2D, kernels, first D2H band)", "update: wait for later D2H bands", "update: scatter mask",
+                                       "iou: verify mask / stage+H2D issue",
                                        "iou: kernel+D2H wait"};
-        for (int i = 0; i < N; ++i)
-            if (calls[i]) fprintf(stderr, "[pcm trace] %-34s %8.3f ms/call over %ld calls\n", names[i], ms[i] / calls[i], calls[i]);
+        for (int i = 0; i < N; ++i) {                   // laps that occur several times per call are summed per call
+            const long per = calls[i < IOU_STAGE ? UPD_SYNC : IOU_WAIT];
+            if (calls[i] && per) fprintf(stderr, "[pcm trace] %-46s %8.3f ms/call over %ld calls\n", names[i], ms[i] / per, per);
+        }
     }
 };
 
@@ -1125,7 +1128,7 @@ static int finish_host_update(pcm_handle* h, const int rect[4], uint8_t* mask, i
             int rc = check_label_error(h);                // last band: waits for the stream
             if (rc) return rc;
         }
-        if (b == 0) h->trace.lap(HostTrace::UPD_WAIT);
+        h->trace.lap(b == 0 ? HostTrace::UPD_WAIT : HostTrace::UPD_D2H);
         const int r0 = (int)((long long)ch * b / n_bands), r1 = (int)((long long)ch * (b + 1) / n_bands);
         const int parts = std::min(pool.size(), std::max(1, (int)(((size_t)(r1 - r0) * cw) >> 14)));
         pool.parallel_for(parts, [&](int part) {
@@ -1134,8 +1137,8 @@ static int finish_host_update(pcm_handle* h, const int rect[4], uint8_t* mask, i
                 scatter_strided(hm + (size_t)(cy + r) * W + cx, mask + (size_t)(cy + r) * mask_row_stride + (size_t)cx * mask_pixel_stride,
                                 mask_pixel_stride, cw);
         });
+        h->trace.lap(HostTrace::UPD_SCATTER);
     }
-    h->trace.lap(HostTrace::UPD_SCATTER);
     return PCM_OK;
 }
 
