@@ -411,10 +411,27 @@ def run_b200(args, rank, world, local_rank):
                 "k1_ms": k1_ms, "kernel_share_of_step": k1_ms / step_kernel_ms if step_kernel_ms else None,
                 "per_kernel_ms": {k: (v[0] / v[1] if v[1] else 0.0) for k, v in prof.items()},
                 "limiter": "shared-memory instruction rate (1 LDS/clk/SM; 9.07 LDS per pixel-tree), see DESIGN.md section 4"}
-    traffic_file = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    # the bound that actually binds K1: one shared-memory instruction per clock per SM.  Trees walked per pixel, averaged
+    # over the timed steps (two blended 20-tree forests up to frame 199 of the sequence, one afterwards)
+    trees = [PARAMS["n_estimators"] * (2 if sequence_state(s % SEQ_FRAMES, MODEL_FRAMES)[1] >= 0 else 1)
+             for s in range(args.warmup, n_total)]
+    sm_mhz = clocks.summary().get("sm_mhz") or 1965.0
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    lds_ms = 1e3 * WIDTH * HEIGHT * (sum(trees) / len(trees)) * 9.07 / 32 / (sm_count * sm_mhz * 1e6)
+    roofline["lds_bound"] = {"lds_per_pixel_tree": 9.07, "trees_per_pixel_mean": sum(trees) / len(trees), "sm_mhz": sm_mhz,
+                             "bound_ms": lds_ms, "frac": lds_ms / k1_ms if k1_ms else None,
+                             "note": "K1 against its own binding resource (profiles/r01_b_k1_instruction_mix.txt): time the "
+                                     "shared-memory pipe needs at one instruction per clock per SM / measured K1 time"}
+    # DRAM / L2 bytes per launch of every kernel of the chain: from the committed ncu capture of this same command
+    # (tools/ncu_traffic.py -> profiles/r02_traffic.json); `traffic` is K1's DRAM bytes per launch
+    traffic_file = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.isfile(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file))["dram_bytes_per_launch"]
+            tr = json.load(open(traffic_file))
+            roofline["traffic"] = tr["kernels"]["score"]["dram_bytes"]
+            roofline["traffic_by_kernel"] = tr["kernels"]
+            roofline["traffic_frame"] = tr["frame"]
+            roofline["traffic_source"] = "profiles/r02_traffic.json (ncu, per launch)"
         except Exception:
             pass
 
@@ -665,6 +682,8 @@ def extra_config_4k(device, args):
     # end to end: Masker.update x 4 + IoU x 4 per frame with host buffers
     mask_h = np.zeros_like(frames[0])
     E2E = 12
+    for a in frames + truths:
+        capi.host_register(a)
 
     def host_step(s):
         f = s % NG
@@ -679,6 +698,8 @@ def extra_config_4k(device, args):
     for s in range(E2E):
         host_step(s)
     e2e_s = time.perf_counter() - t0
+    for a in frames + truths:
+        capi.host_unregister(a)
     for m in maskers:
         m.close()
     px = sum(r[2] * r[3] for r in rects)
