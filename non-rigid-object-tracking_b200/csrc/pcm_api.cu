@@ -1516,8 +1516,16 @@ static int enqueue_quickshift(pcm_handle* h, const uint8_t* d_frame, int64_t str
             const double x = v / 255.0;
             lin[v] = x > 0.04045 ? pow((x + 0.055) / 1.055, 2.4) : x / 12.92;
         }
-        CUDA_TRY(h->qs_lin.reserve(sizeof lin));
+        // + the table of qs_exp_neg: 2^(j/64) as float64 high part and the remainder
+        double tab[128];
+        for (int j = 0; j < 64; ++j) {
+            const long double v = exp2l((long double)j / 64.0L);
+            tab[2 * j] = (double)v;
+            tab[2 * j + 1] = (double)(v - (long double)tab[2 * j]);
+        }
+        CUDA_TRY(h->qs_lin.reserve(sizeof lin + sizeof tab));
         CUDA_TRY(cudaMemcpy(h->qs_lin.p, lin, sizeof lin, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->qs_lin.as<char>() + sizeof lin, tab, sizeof tab, cudaMemcpyHostToDevice));
     }
     QsArgs a{};
     a.frame = d_frame; a.stride = stride; a.cx = cx; a.cy = cy; a.cw = cw; a.ch = ch;
@@ -1531,14 +1539,17 @@ static int enqueue_quickshift(pcm_handle* h, const uint8_t* d_frame, int64_t str
     a.kw = kw;
     a.inv = -0.5 / (kernel_size * kernel_size);
     a.max_dist = max_dist;
+    a.exp_tab = h->qs_lin.as<double>() + 256;
+    a.pw = (max_dist >= 0 && max_dist < (double)kw) ? (int)floor(max_dist) : kw;
     const int flat_blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
     qs_lab_kernel<<<flat_blocks, 256, 0, st>>>(a);
     CHECK_LAUNCH(h, "qs_lab_kernel");
     const dim3 grid((cw + QS_BW - 1) / QS_BW, (ch + QS_BH - 1) / QS_BH);
     const size_t tile = (size_t)(QS_BW + 2 * kw) * (QS_BH + 2 * kw) * sizeof(double);
-    qs_window_kernel<false><<<grid, QS_BW * QS_BH, 3 * tile, st>>>(a);
+    qs_window_kernel<false><<<grid, QS_BW * QS_BH, 3 * tile + (128 + 2 * kw + 1) * sizeof(double), st>>>(a);
     CHECK_LAUNCH(h, "qs_window_kernel<density>");
-    qs_window_kernel<true><<<grid, QS_BW * QS_BH, 4 * tile, st>>>(a);
+    const size_t ptile = (size_t)(QS_BW + 2 * a.pw) * (QS_BH + 2 * a.pw) * sizeof(double);
+    qs_window_kernel<true><<<grid, QS_BW * QS_BH, 4 * ptile, st>>>(a);
     CHECK_LAUNCH(h, "qs_window_kernel<parent>");
     CUDA_TRY(cudaMemsetAsync(h->qs_flag.p, 0, n * sizeof(int), st));
     qs_root_kernel<<<flat_blocks, 256, 0, st>>>(a.parent, a.root, h->qs_flag.as<int>(), (int)n);

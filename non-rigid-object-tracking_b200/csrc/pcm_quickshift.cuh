@@ -33,7 +33,31 @@ struct QsArgs {
     int kw;                    // window half width = ceil(3 * kernel_size)
     double inv;                // -0.5 / kernel_size^2
     double max_dist;
+    const double* exp_tab;     // [64][2]: 2^(j/64) as a high and a low part (qs_exp_neg)
+    int pw;                    // half width of the PARENT search window: min(kw, floor(max_dist)), see qs_window_kernel
 };
+
+// exp(x) for x <= 0, table driven: x = (64 m + j) ln2/64 + r, |r| <= ln2/128,
+//   exp(x) = 2^m * 2^(j/64) * (1 + r + r^2/2 + r^3/6 + r^4/24 + r^5/120)        (truncation 3.5e-17 relative)
+// 2^(j/64) comes from a 64-entry table held as high + low parts (shared memory, `tab`).  About 1 ulp, like the CUDA math
+// library's exp() -- which needs about twice the float64 operations, and this kernel is bound by the float64 pipe
+// (profiles/README.md).  Arguments below -700 (results near the subnormal range) go to exp() itself.
+__device__ __forceinline__ double qs_exp_neg(double x, const double* __restrict__ tab) {
+    if (x < -700.0) return exp(x);
+    const double t = fma(x, 92.33248261689366, 6755399441055744.0);          // 64 / ln2; 1.5 * 2^52 rounds to an integer
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -0x1.62e42fefa0000p-7, x);                             // ln2 / 64, high 36 bits: exact product
+    r = fma(kd, -0x1.cf79abc9e3b3ap-46, r);
+    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    q = fma(r, q, 1.0 / 6.0);
+    q = fma(r, q, 0.5);
+    q = fma(r * r, q, r);                                                      // exp(r) - 1
+    const int j = k & 63;
+    const double hi = tab[2 * j], lo = tab[2 * j + 1];
+    const double v = hi + fma(hi, q, lo);
+    return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+}
 
 __global__ void __launch_bounds__(256) qs_lab_kernel(const QsArgs a) {
     const int n = a.cw * a.ch;
@@ -80,14 +104,20 @@ __device__ __forceinline__ double qs_dist(double l0, double a0, double b0, doubl
 // shared memory once and reused by the (2w+1)^2 taps of every pixel.
 constexpr int QS_BW = 32, QS_BH = 8, QS_MAX_KW = 15;
 
+// PARENT pass window: the reference takes the nearest higher-density pixel of the whole (2 kw + 1)^2 window and then
+// cuts the link if it is longer than max_dist (:parent_flat[dist_parent_flat > max_dist] = self).  A pixel farther than
+// max_dist in the image plane alone can therefore never end up as the parent, and if no candidate within that radius is
+// close enough the answer is "self" whatever lies outside: searching |dr|, |dc| <= pw = min(kw, floor(max_dist)) in the
+// same raster order gives the identical result with (2 pw + 1)^2 instead of (2 kw + 1)^2 taps (169 instead of 361 for
+// the reference's parameters).
 template <bool PARENT>
 __global__ void __launch_bounds__(QS_BW * QS_BH) qs_window_kernel(const QsArgs a) {
     extern __shared__ double qs_smem[];
-    const int kw = a.kw, TW = QS_BW + 2 * kw, TH = QS_BH + 2 * kw;
+    const int kw = PARENT ? a.pw : a.kw, TW = QS_BW + 2 * kw, TH = QS_BH + 2 * kw;
     double* sL = qs_smem;
     double* sA = sL + TW * TH;
     double* sB = sA + TW * TH;
-    double* sD = sB + TW * TH;            // densities (PARENT only)
+    double* sD = sB + TW * TH;            // densities (PARENT) / exp table + squares (density pass)
     const int x0 = blockIdx.x * QS_BW, y0 = blockIdx.y * QS_BH;
     const size_t ps = (size_t)a.cw * a.ch;
     for (int i = threadIdx.x; i < TW * TH; i += QS_BW * QS_BH) {
@@ -100,6 +130,12 @@ __global__ void __launch_bounds__(QS_BW * QS_BH) qs_window_kernel(const QsArgs a
         sB[i] = in ? a.lab[2 * ps + o] : 0.0;
         if (PARENT) sD[i] = in ? a.dens[o] : 0.0;
     }
+    double* tab = sD;                      // density pass: [128] exp table, then [2 kw + 1] squares of the column offsets
+    double* sq = sD + 128;
+    if (!PARENT) {
+        for (int i = threadIdx.x; i < 128; i += QS_BW * QS_BH) tab[i] = a.exp_tab[i];
+        for (int i = threadIdx.x; i < 2 * kw + 1; i += QS_BW * QS_BH) { const double t = (double)(i - kw); sq[i] = __dmul_rn(t, t); }
+    }
     __syncthreads();
     const int lx = threadIdx.x % QS_BW, ly = threadIdx.x / QS_BW;
     const int c = x0 + lx, r = y0 + ly;
@@ -109,13 +145,23 @@ __global__ void __launch_bounds__(QS_BW * QS_BH) qs_window_kernel(const QsArgs a
     const int me = (ly + kw) * TW + (lx + kw);
     const double l0 = sL[me], a0 = sA[me], b0 = sB[me];
     if (!PARENT) {
+        // the Cython loop's order: channels, then rows, then columns; separate multiplies and adds
         double acc = 0.0;
         for (int r_ = r_min; r_ < r_max; ++r_) {
             const int row = (r_ - y0 + kw) * TW + kw - x0;
+            const double tr = (double)(r - r_), dr2 = __dmul_rn(tr, tr);
+            const double* sqc = sq + kw + c;                   // sqc[-c_] = (c - c_)^2
             for (int c_ = c_min; c_ < c_max; ++c_) {
                 const int j = row + c_;
-                const double d = qs_dist(l0, a0, b0, sL[j], sA[j], sB[j], r - r_, c - c_);
-                acc = __dadd_rn(acc, exp(__dmul_rn(d, a.inv)));
+                double t = __dsub_rn(l0, sL[j]);
+                double d = __dmul_rn(t, t);
+                t = __dsub_rn(a0, sA[j]);
+                d = __dadd_rn(d, __dmul_rn(t, t));
+                t = __dsub_rn(b0, sB[j]);
+                d = __dadd_rn(d, __dmul_rn(t, t));
+                d = __dadd_rn(d, dr2);
+                d = __dadd_rn(d, sqc[-c_]);
+                acc = __dadd_rn(acc, qs_exp_neg(__dmul_rn(d, a.inv), tab));
             }
         }
         const size_t o = (size_t)r * a.cw + c;
