@@ -389,6 +389,14 @@ def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, ou
                 group = dist.new_group(ranks=members)          # collective: every rank creates every group, same order
                 if rank in members:
                     shares[v] = Share(dist, group, members.index(rank), len(members))
+        # a group's communicator is built by its first collective (NCCL: about a second with eight ranks): do that here,
+        # with the process group itself, before the clock starts -- in the same clip order on every rank
+        for v in clip_order(items):
+            if v in shares:
+                warm = torch.zeros(1, device=dev) if dev is not None else torch.zeros(1)
+                dist.all_reduce(warm, group=shares[v].group)
+        if dev is not None:
+            torch.cuda.synchronize(dev)
         dist.barrier()
     stages.reset()
     t0 = time.time()
