@@ -52,13 +52,17 @@ def build_items(videos=None, hyper=None):
 
 
 def item_cost(item):
-    """Relative cost of a sequence on the GPU path: frames x per-frame kernel time (two blended forests; the PCA novelty
-    pass costs about as much as the deepest forests; the device-side prior adds two small kernels)."""
+    """Relative cost of a sequence on the resident GPU path, in "light frames".  Calibrated on a B200 against a serial run of
+    the whole grid (bench.py --workload sweep --sweep-workers 1; profiles/README.md, round 2):
+        seconds ~ 8.1 ms + frames x (0.05 + 0.15 novelty + 0.07 depth-10 + 0.07 30-trees + 0.06 prior + 0.04 hsv_lab) ms
+    -- the fixed part (masker and handle set-up, model export, job list, one synchronisation) weighs as much as 160 light
+    frames, which is what balances the 32-frame clips against the 280-frame ones."""
     _, _, v, p = item
     frames = CLIP_FRAMES.get(v, 100)
-    per_frame = 1.0 + (2.5 if p.get("novelty_detection") else 0.0) + (0.6 if int(p.get("max_depth") or 0) >= 10 else 0.0) + \
-        (0.3 if int(p.get("n_estimators") or 0) >= 30 else 0.0) + (0.3 if p.get("prior_weight") else 0.0)
-    return frames * per_frame + 60.0          # + masker set-up, model export, job list (about 60 light frames)
+    per_frame = 1.0 + (3.0 if p.get("novelty_detection") else 0.0) + (1.4 if int(p.get("max_depth") or 0) >= 10 else 0.0) + \
+        (1.4 if int(p.get("n_estimators") or 0) >= 30 else 0.0) + (1.2 if p.get("prior_weight") else 0.0) + \
+        (0.8 if str(p.get("features")).endswith("hsv_lab") else 0.0)
+    return frames * per_frame + 160.0
 
 
 def forest_key(item):
