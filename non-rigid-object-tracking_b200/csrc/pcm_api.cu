@@ -597,8 +597,8 @@ extern "C" int pcm_create(int device, pcm_handle** out) {
             CUDA_TRY(cudaMemcpy(ds.d_tables, &ds.h_tables, sizeof(ColorTables), cudaMemcpyHostToDevice));
             for (int i = 0; i < N_SCORE_VARIANTS; ++i)
                 CUDA_TRY(cudaFuncSetAttribute(score_variant(i).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ds.max_smem_optin));
-            CUDA_TRY(cudaFuncSetAttribute(qs_window_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds.max_smem_optin));
-            CUDA_TRY(cudaFuncSetAttribute(qs_window_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds.max_smem_optin));
+            CUDA_TRY(cudaFuncSetAttribute(qs_density_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ds.max_smem_optin));
+            CUDA_TRY(cudaFuncSetAttribute(qs_parent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ds.max_smem_optin));
             ds.ready = true;
         }
     }
@@ -1546,11 +1546,15 @@ static int enqueue_quickshift(pcm_handle* h, const uint8_t* d_frame, int64_t str
     CHECK_LAUNCH(h, "qs_lab_kernel");
     const dim3 grid((cw + QS_BW - 1) / QS_BW, (ch + QS_BH - 1) / QS_BH);
     const size_t tile = (size_t)(QS_BW + 2 * kw) * (QS_BH + 2 * kw) * sizeof(double);
-    qs_window_kernel<false><<<grid, QS_BW * QS_BH, 3 * tile + (128 + 2 * kw + 1) * sizeof(double), st>>>(a);
-    CHECK_LAUNCH(h, "qs_window_kernel<density>");
+    {
+        const dim3 dgrid((cw + QS_DBW - 1) / QS_DBW, (ch + QS_DBH - 1) / QS_DBH);
+        const size_t dtile = (size_t)(QS_DBW + 2 * kw) * (QS_DBH + 2 * kw) * sizeof(double);
+        qs_density_kernel<<<dgrid, 256, 3 * dtile + (128 + 2 * kw + 1) * sizeof(double), st>>>(a);
+    }
+    CHECK_LAUNCH(h, "qs_density_kernel");
     const size_t ptile = (size_t)(QS_BW + 2 * a.pw) * (QS_BH + 2 * a.pw) * sizeof(double);
-    qs_window_kernel<true><<<grid, QS_BW * QS_BH, 4 * ptile, st>>>(a);
-    CHECK_LAUNCH(h, "qs_window_kernel<parent>");
+    qs_parent_kernel<<<grid, QS_BW * QS_BH, 4 * ptile, st>>>(a);
+    CHECK_LAUNCH(h, "qs_parent_kernel");
     CUDA_TRY(cudaMemsetAsync(h->qs_flag.p, 0, n * sizeof(int), st));
     qs_root_kernel<<<flat_blocks, 256, 0, st>>>(a.parent, a.root, h->qs_flag.as<int>(), (int)n);
     CHECK_LAUNCH(h, "qs_root_kernel");

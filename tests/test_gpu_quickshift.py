@@ -81,8 +81,10 @@ def test_update_from_resident_quickshift_labels():
     m2 = np.zeros_like(frame)
     h.update(frame, rect, labels, n, None, prm, m2)
     assert m1.any() and np.array_equal(m1, m2)
-    with pytest.raises(capi.PcmError):                     # the resident crop was replaced by the call above
-        h.update(frame, rect, None, n, None, prm, m1)
+    # labels == NULL with no quickshift pending: the label map the host-label update above left on the device is reused
+    m3 = np.zeros_like(frame)
+    h.update(frame, rect, None, n, None, prm, m3)
+    assert np.array_equal(m3, m2)
     h.quickshift(frame, rect, noise=None, want_labels=False)   # noise reused for the same crop size
     other = frame.copy()
     with pytest.raises(capi.PcmError):

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Times pcm_quickshift on a synthetic 1080p frame and on a SegTrack2-sized crop (run under ncu to
-profile the qs_* kernels: `ncu --set full -k regex:qs_window ... python tools/quickshift_probe.py`)."""
+profile the qs_* kernels: `ncu --set full -k regex:qs_ ... python tools/quickshift_probe.py`)."""
 import os
 import sys
 import time
