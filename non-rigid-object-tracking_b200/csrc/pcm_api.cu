@@ -597,7 +597,8 @@ extern "C" int pcm_create(int device, pcm_handle** out) {
             CUDA_TRY(cudaMemcpy(ds.d_tables, &ds.h_tables, sizeof(ColorTables), cudaMemcpyHostToDevice));
             for (int i = 0; i < N_SCORE_VARIANTS; ++i)
                 CUDA_TRY(cudaFuncSetAttribute(score_variant(i).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ds.max_smem_optin));
-            CUDA_TRY(cudaFuncSetAttribute(qs_density_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ds.max_smem_optin));
+            CUDA_TRY(cudaFuncSetAttribute(qs_density_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds.max_smem_optin));
+            CUDA_TRY(cudaFuncSetAttribute(qs_density_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds.max_smem_optin));
             CUDA_TRY(cudaFuncSetAttribute(qs_parent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ds.max_smem_optin));
             ds.ready = true;
         }
@@ -1540,6 +1541,12 @@ static int enqueue_quickshift(pcm_handle* h, const uint8_t* d_frame, int64_t str
     a.inv = -0.5 / (kernel_size * kernel_size);
     a.max_dist = max_dist;
     a.exp_tab = h->qs_lin.as<double>() + 256;
+    {
+        // largest possible squared 5-D distance: Lab * ratio spans L 0..100, a / b about -128..128 (generous), plus the
+        // window corner; the exp argument is that times |inv|
+        const double span = ratio * ratio * (100.0 * 100.0 + 2.0 * 256.0 * 256.0) + 2.0 * (double)kw * kw;
+        a.exp_guard = !(span * -a.inv < 690.0);
+    }
     a.pw = (max_dist >= 0 && max_dist < (double)kw) ? (int)floor(max_dist) : kw;
     const int flat_blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
     qs_lab_kernel<<<flat_blocks, 256, 0, st>>>(a);
@@ -1549,7 +1556,9 @@ static int enqueue_quickshift(pcm_handle* h, const uint8_t* d_frame, int64_t str
     {
         const dim3 dgrid((cw + QS_DBW - 1) / QS_DBW, (ch + QS_DBH - 1) / QS_DBH);
         const size_t dtile = (size_t)(QS_DBW + 2 * kw) * (QS_DBH + 2 * kw) * sizeof(double);
-        qs_density_kernel<<<dgrid, 256, 3 * dtile + (128 + 2 * kw + 1) * sizeof(double), st>>>(a);
+        const size_t dsmem = 3 * dtile + (128 + 2 * kw + 1) * sizeof(double);
+        if (a.exp_guard) qs_density_kernel<true><<<dgrid, 256, dsmem, st>>>(a);
+        else qs_density_kernel<false><<<dgrid, 256, dsmem, st>>>(a);
     }
     CHECK_LAUNCH(h, "qs_density_kernel");
     const size_t ptile = (size_t)(QS_BW + 2 * a.pw) * (QS_BH + 2 * a.pw) * sizeof(double);

@@ -16,6 +16,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <type_traits>
 
 namespace pcm {
 
@@ -34,6 +35,7 @@ struct QsArgs {
     double inv;                // -0.5 / kernel_size^2
     double max_dist;
     const double* exp_tab;     // [64][2]: 2^(j/64) as a high and a low part (qs_exp_neg)
+    int exp_guard;             // 1: exp arguments may fall below -700 (see qs_exp_neg)
     int pw;                    // half width of the PARENT search window: min(kw, floor(max_dist)), see qs_parent_kernel
 };
 
@@ -41,9 +43,13 @@ struct QsArgs {
 //   exp(x) = 2^m * 2^(j/64) * (1 + r + r^2/2 + r^3/6 + r^4/24 + r^5/120)        (truncation 3.5e-17 relative)
 // 2^(j/64) comes from a 64-entry table held as high + low parts (shared memory, `tab`).  About 1 ulp, like the CUDA math
 // library's exp() -- which needs about twice the float64 operations, and this kernel is bound by the float64 pipe
-// (profiles/README.md).  Arguments below -700 (results near the subnormal range) go to exp() itself.
+// (profiles/README.md).  GUARD: arguments below -700 are clamped to -700 (the exponent arithmetic below assumes a normal
+// result).  That changes no density: a window always contains its own centre, whose term is exp(0) = 1, so a term of
+// 1e-304 or less -- exact or clamped -- is absorbed without trace by the first normal-sized term added after it.  The host
+// drops the guard when the parameters cannot produce such an argument (true for the reference's ratio 0.5, kernel 3).
+template <bool GUARD>
 __device__ __forceinline__ double qs_exp_neg(double x, const double* __restrict__ tab) {
-    if (x < -700.0) return exp(x);
+    if (GUARD && (unsigned)__double2hiint(x) > 0xC085E000u) x = -700.0;      // x < -700 (integer compare: keeps the float64 pipe free)
     const double t = fma(x, 92.33248261689366, 6755399441055744.0);          // 64 / ln2; 1.5 * 2^52 rounds to an integer
     const int k = __double2loint(t);
     const double kd = t - 6755399441055744.0;
@@ -162,6 +168,7 @@ __global__ void __launch_bounds__(QS_BW * QS_BH) qs_parent_kernel(const QsArgs a
 // Cython loop.  Block = 32 x 8 threads = 32 x 32 pixels.
 constexpr int QS_DR = 4, QS_DBW = 32, QS_DBH = 8 * QS_DR;
 
+template <bool GUARD>
 __global__ void __launch_bounds__(256) qs_density_kernel(const QsArgs a) {
     extern __shared__ double qs_smem[];
     const int kw = a.kw, TW = QS_DBW + 2 * kw, TH = QS_DBH + 2 * kw;
@@ -192,18 +199,20 @@ __global__ void __launch_bounds__(256) qs_density_kernel(const QsArgs a) {
 #pragma unroll
     for (int p = 0; p < QS_DR; ++p) {
         const int me = (ly * QS_DR + p + kw) * TW + (lx + kw);
-        l0[p] = sL[me]; a0[p] = sA[me]; b0[p] = sB[me]; acc[p] = 0.0;
+        l0[p] = sL[me]; a0[p] = sA[me]; b0[p] = sB[me]; acc[p] = 0.0;       // rows below the crop read the zero padding
     }
-    const int r_lo = max(rb - kw, 0), r_hi = min(rb + QS_DR - 1 + kw + 1, a.ch);     // union of the pixels' row ranges
     const double* sqc = sq + kw + c;                                               // sqc[-c_] = (c - c_)^2
-    for (int r_ = r_lo; r_ < r_hi; ++r_) {
+    const double inv = a.inv;
+    // one window row for the thread's pixels; ALL: the row lies in the window of every one of them (no tests in the loop)
+    auto window_row = [&](int r_, auto all) {
+        constexpr bool ALL = decltype(all)::value;
         const int row = (r_ - y0 + kw) * TW + kw - x0;
         double dr2[QS_DR];
         bool on[QS_DR];
 #pragma unroll
         for (int p = 0; p < QS_DR; ++p) {
             const int dr = rb + p - r_;
-            on[p] = dr >= -kw && dr <= kw && rb + p < a.ch;
+            on[p] = ALL || (dr >= -kw && dr <= kw);
             const double t = (double)dr;
             dr2[p] = __dmul_rn(t, t);
         }
@@ -212,20 +221,27 @@ __global__ void __launch_bounds__(256) qs_density_kernel(const QsArgs a) {
             const double L = sL[j], A = sA[j], B = sB[j], dc2 = sqc[-c_];
 #pragma unroll
             for (int p = 0; p < QS_DR; ++p) {
-                if (on[p]) {
-                    double t = __dsub_rn(l0[p], L);
-                    double d = __dmul_rn(t, t);
-                    t = __dsub_rn(a0[p], A);
-                    d = __dadd_rn(d, __dmul_rn(t, t));
-                    t = __dsub_rn(b0[p], B);
-                    d = __dadd_rn(d, __dmul_rn(t, t));
-                    d = __dadd_rn(d, dr2[p]);
-                    d = __dadd_rn(d, dc2);
-                    acc[p] = __dadd_rn(acc[p], qs_exp_neg(__dmul_rn(d, a.inv), tab));
-                }
+                // the Cython loop's order: channels, then rows, then columns; separate multiplies and adds
+                double t = __dsub_rn(l0[p], L);
+                double d = __dmul_rn(t, t);
+                t = __dsub_rn(a0[p], A);
+                d = __dadd_rn(d, __dmul_rn(t, t));
+                t = __dsub_rn(b0[p], B);
+                d = __dadd_rn(d, __dmul_rn(t, t));
+                d = __dadd_rn(d, dr2[p]);
+                d = __dadd_rn(d, dc2);
+                const double e = qs_exp_neg<GUARD>(__dmul_rn(d, inv), tab);
+                if (ALL) acc[p] = __dadd_rn(acc[p], e);
+                else if (on[p]) acc[p] = __dadd_rn(acc[p], e);       // (a select: rows outside this pixel's window add nothing)
             }
         }
-    }
+    };
+    // rows of the union of the windows, clipped to the crop; in [all_lo, all_hi) every pixel of the thread takes part
+    const int r_lo = max(rb - kw, 0), r_hi = min(rb + QS_DR - 1 + kw + 1, a.ch);
+    const int all_lo = min(max(rb + QS_DR - 1 - kw, r_lo), r_hi), all_hi = max(min(rb + kw + 1, r_hi), all_lo);
+    for (int r_ = r_lo; r_ < all_lo; ++r_) window_row(r_, std::false_type{});
+    for (int r_ = all_lo; r_ < all_hi; ++r_) window_row(r_, std::true_type{});
+    for (int r_ = all_hi; r_ < r_hi; ++r_) window_row(r_, std::false_type{});
 #pragma unroll
     for (int p = 0; p < QS_DR; ++p) {
         if (rb + p < a.ch) {
