@@ -99,32 +99,83 @@ class ModelCache:
             return value
 
 
+def clip_open_cost(video):
+    """What a rank pays for every clip it touches, whatever its share of the clip's sequences: decoding and uploading the
+    clip and waiting for the ranks it shares the clip with (measured: 0.23 s for the 279-frame clip = 16 light frames per
+    clip frame)."""
+    return 16.0 * CLIP_FRAMES.get(video, 100)
+
+
+def clip_prepare_cost(video):
+    """Host work that exists once per clip and is split between the ranks sharing it (over-segmentation maps, SIFT
+    detection: ~11 ms of CPU per frame on the rank's four-odd cores); charged to the clip's sequences in equal parts."""
+    return 55.0 * CLIP_FRAMES.get(video, 100)
+
+
+def shard_cost(shard, all_items):
+    """What `partition` balances: the shard's sequences, their part of the preparation of their clips, and the opening of
+    every clip the shard touches."""
+    clip_n = {}
+    for it in all_items:
+        clip_n[it[2]] = clip_n.get(it[2], 0) + 1
+    return sum(item_cost(it) + clip_prepare_cost(it[2]) / clip_n[it[2]] for it in shard) + \
+        sum(clip_open_cost(v) for v in {it[2] for it in shard})
+
+
 def partition(items, world):
-    """Contiguous, cost-balanced split of the grid with CLIP LOCALITY: the sequences are ordered clip by clip (heaviest
-    clip first; inside a clip by features, max_depth, ... so that neighbours share their fitted models) and the ordered
-    list is cut into `world` runs of equal cost.  A rank therefore works on one or two clips -- what it has to decode,
-    over-segment and run SIFT on -- instead of on all of them; fits are cheap GPU work and may repeat on two ranks.
-    Returns `world` lists of items; deterministic."""
-    clip_cost = {}
+    """Contiguous split of the grid with CLIP LOCALITY: the sequences are ordered clip by clip (heaviest clip first; inside
+    a clip by features, max_depth, ... so that neighbours share their fitted models) and the ordered list is cut into
+    `world` runs that MINIMISE THE SLOWEST RANK, where a rank costs the sum of its sequences (`item_cost` plus the
+    sequence's part of its clip's preparation) plus `clip_open_cost` for every clip it touches -- so a cut lands on a clip
+    boundary whenever that is nearly balanced, instead of leaving one rank to open two long clips (dynamic programme over
+    the cut positions).  Returns `world` lists of items; deterministic."""
+    clip_cost, clip_n = {}, {}
     for it in items:
         clip_cost[it[2]] = clip_cost.get(it[2], 0.0) + item_cost(it)
+        clip_n[it[2]] = clip_n.get(it[2], 0) + 1
 
     def key(it):
         p = it[3]
         return (-clip_cost[it[2]], it[2], str(p.get("features")), p.get("max_depth") or 0, p.get("n_estimators") or 0, it[0])
     ordered = sorted(items, key=key)
-    total = sum(item_cost(it) for it in ordered)
+    n = len(ordered)
     shards = [[] for _ in range(world)]
     if not ordered:
         return shards
-    acc, r = 0.0, 0
-    for k, it in enumerate(ordered):
-        left = len(ordered) - k                      # items still to place, this one included
-        # move on when this rank has its share -- but never leave a later rank without an item
-        while r < world - 1 and shards[r] and (acc >= total * (r + 1) / world - 1e-9 or left <= world - 1 - r):
-            r += 1
-        shards[r].append(it)
-        acc += item_cost(it)
+    if world >= n:                                   # one sequence per rank, the rest stay empty-handed
+        for k, it in enumerate(ordered):
+            shards[k].append(it)
+        return shards
+    cost = [item_cost(it) + clip_prepare_cost(it[2]) / clip_n[it[2]] for it in ordered]
+    prefix = [0.0]
+    for c in cost:
+        prefix.append(prefix[-1] + c)
+    clips = [it[2] for it in ordered]
+    first_of_run = [k == 0 or clips[k] != clips[k - 1] for k in range(n)]     # the list is grouped by clip
+    opens = [0.0] * (n + 1)                                                    # opens[k] = open cost of clip runs starting before k
+    for k in range(n):
+        opens[k + 1] = opens[k] + (clip_open_cost(clips[k]) if first_of_run[k] else 0.0)
+
+    def run_cost(a, b):                              # items a .. b-1
+        touched = opens[b] - opens[a] + (0.0 if first_of_run[a] else clip_open_cost(clips[a]))
+        return prefix[b] - prefix[a] + touched
+    INF = float("inf")
+    best = [[INF] * (n + 1) for _ in range(world + 1)]      # best[r][k]: smallest possible maximum over r runs covering k items
+    cut = [[0] * (n + 1) for _ in range(world + 1)]
+    best[0][0] = 0.0
+    for r in range(1, world + 1):
+        for k in range(r, n - (world - r) + 1):
+            for a in range(r - 1, k):
+                if best[r - 1][a] == INF:
+                    continue
+                v = max(best[r - 1][a], run_cost(a, k))
+                if v < best[r][k] - 1e-9:
+                    best[r][k], cut[r][k] = v, a
+    k = n
+    for r in range(world, 0, -1):
+        a = cut[r][k]
+        shards[r - 1] = ordered[a:k]
+        k = a
     return shards
 
 
