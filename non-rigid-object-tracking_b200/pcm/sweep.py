@@ -52,17 +52,19 @@ def build_items(videos=None, hyper=None):
 
 
 def item_cost(item):
-    """Relative cost of a sequence on the resident GPU path, in "light frames".  Calibrated on a B200 against a serial run of
-    the whole grid (bench.py --workload sweep --sweep-workers 1; profiles/README.md, round 2):
-        seconds ~ 8.1 ms + frames x (0.05 + 0.15 novelty + 0.07 depth-10 + 0.07 30-trees + 0.06 prior + 0.04 hsv_lab) ms
-    -- the fixed part (masker and handle set-up, model export, job list, one synchronisation) weighs as much as 160 light
+    """Relative cost of a sequence on the resident GPU path, in "light frames" (31 us).  Calibrated on a B200 against a
+    serial run of the whole grid (bench.py --workload sweep --sweep-workers 1, least squares over the 256 per-sequence
+    times of benchmark_results.csv, 14 % rms error; profiles/README.md, round 2), per frame in us:
+        31 + 64 novelty + 42 depth-10 + 31 30-trees + 18 prior + 86 novelty x hsv_lab
+    plus a fixed 8 ms per sequence (masker and handle set-up, model export, job list, one synchronisation) = 260 light
     frames, which is what balances the 32-frame clips against the 280-frame ones."""
     _, _, v, p = item
     frames = CLIP_FRAMES.get(v, 100)
-    per_frame = 1.0 + (3.0 if p.get("novelty_detection") else 0.0) + (1.4 if int(p.get("max_depth") or 0) >= 10 else 0.0) + \
-        (1.4 if int(p.get("n_estimators") or 0) >= 30 else 0.0) + (1.2 if p.get("prior_weight") else 0.0) + \
-        (0.8 if str(p.get("features")).endswith("hsv_lab") else 0.0)
-    return frames * per_frame + 160.0
+    nov = bool(p.get("novelty_detection"))
+    per_frame = 1.0 + (2.1 if nov else 0.0) + (1.35 if int(p.get("max_depth") or 0) >= 10 else 0.0) + \
+        (1.0 if int(p.get("n_estimators") or 0) >= 30 else 0.0) + (0.6 if p.get("prior_weight") else 0.0) + \
+        (2.8 if nov and str(p.get("features")).endswith("hsv_lab") else 0.0)
+    return frames * per_frame + 260.0
 
 
 def forest_key(item):
