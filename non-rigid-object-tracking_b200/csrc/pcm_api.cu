@@ -293,6 +293,7 @@ struct pcm_handle {
     int mir_H = 0, mir_W = 0, mir_band_rows = 0;
     std::vector<uint8_t> mir_ok;
     cudaEvent_t band_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> ahead_events;   // pcm_run_frames: frames in flight
     cudaStream_t copy_stream = nullptr;   // host path: row bands of a page-locked caller frame travel here (BandFeed)
     cudaEvent_t feed_events[4] = {nullptr, nullptr, nullptr, nullptr};
     int resident_labels = 0;      // n_labels of the label map the last host pcm_update left on the device (0: none)
@@ -638,6 +639,7 @@ extern "C" void pcm_destroy(pcm_handle* h) {
     for (auto& t : h->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t e : h->band_events) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->feed_events) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ahead_events) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto e : h->free_events) cudaEventDestroy(e);
     h->err_buf.release();
@@ -1745,9 +1747,21 @@ extern "C" int pcm_run_frames(pcm_handle* h, int frame_h, int frame_w, int64_t f
     if (!h || !d_mask || (!jobs && n_jobs > 0)) return fail(PCM_E_INVALID, "pcm_run_frames: NULL argument");
     if (n_jobs < 0 || frame_h <= 0 || frame_w <= 0 || mask_row_stride < frame_w) return fail(PCM_E_INVALID, "pcm_run_frames: bad size");
     CUDA_TRY(cudaSetDevice(h->device));
+    // At most `ahead` frames are in flight on the stream: the thread waits (blocking-sync event, CPU yielded) for frame
+    // k - ahead before it enqueues frame k.  Without the limit a long sequence fills the stream's launch queue and the
+    // thread then blocks INSIDE a launch call, which serialises the launches of the other sequence threads of the
+    // process (the sweep runs 8 - 16 of them, each on its own stream).  PCM_RUN_AHEAD=0 switches the limit off.
+    static const int ahead = [] { const char* e = getenv("PCM_RUN_AHEAD"); int v = e ? atoi(e) : 32; return v < 0 ? 0 : v; }();
+    if (ahead > 0 && (int)h->ahead_events.size() < ahead) {
+        const size_t old = h->ahead_events.size();
+        h->ahead_events.resize((size_t)ahead, nullptr);
+        for (size_t i = old; i < h->ahead_events.size(); ++i)
+            CUDA_TRY(cudaEventCreateWithFlags(&h->ahead_events[i], cudaEventDisableTiming | cudaEventBlockingSync));
+    }
     for (int k = 0; k < n_jobs; ++k) {
         const pcm_frame_job& j = jobs[k];
         int rc;
+        if (ahead > 0 && k >= ahead) CUDA_TRY(cudaEventSynchronize(h->ahead_events[k % ahead]));
         if (j.d_priors_out) {
             rc = pcm_prior_device(h, j.d_pts_prev, j.d_des_prev, j.n_prev,
                                   d_mask + (int64_t)j.prev_rect[1] * mask_row_stride + j.prev_rect[0], mask_row_stride,
@@ -1768,6 +1782,7 @@ extern "C" int pcm_run_frames(pcm_handle* h, int frame_h, int frame_w, int64_t f
                              j.clear_mask == 2 ? rect : nullptr);
             if (rc) return rc;
         }
+        if (ahead > 0 && k + ahead < n_jobs) CUDA_TRY(cudaEventRecord(h->ahead_events[k % ahead], h->stream));
     }
     return PCM_OK;
 }
