@@ -313,8 +313,9 @@ int pcm_convert(pcm_handle* h, const uint8_t* bgr, int height, int width, int64_
 int pcm_gather_features(pcm_handle* h, const uint8_t* frame, int frame_h, int frame_w, int64_t frame_stride,
                         const int rect[4], int16_t* X);
 
-/* Keep the per-stage buffers that only the parity taps need (today: the 0/255 map before
- * dilation, one extra byte per pixel written by the dilation kernel).  Off by default. */
+/* Bit 0: keep the per-stage buffers that only the parity taps need -- the float64 P(fg) map (and the novelty map) the
+ * score kernel otherwise does not store, and the 0/255 map before dilation.  Bit 1 (test hook): every label takes the
+ * exact sequential-float32 path of the decision kernel, not only the labels inside the guard band.  Off by default. */
 int pcm_set_debug(pcm_handle* h, int on);
 
 /* Stage dumps of the LAST pcm_update / pcm_update_device on this handle

@@ -260,7 +260,7 @@ struct pcm_handle {
     int64_t prof_n[PCM_NUM_KERNELS] = {0};
 
     // per-update scratch (device)
-    DevBuf frame, labels, priors, planes, sched, p1, sa, seg, rmin, rmax, decision, scores, flagged, mask, pre, counts;
+    DevBuf frame, labels, priors, planes, sched, p1, sa, seg, rmin, rmax, cmin, cmax, decision, scores, flagged, mask, pre, counts;
     // pinned staging (host)
     PinBuf h_frame, h_labels, h_priors, h_mask, h_small;
 
@@ -304,7 +304,9 @@ struct pcm_handle {
     bool last_novelty = false;
     bool last_valid = false;
     bool last_pre = false;
-    bool keep_pre = false;        // pcm_set_debug: K3 also writes the pre-dilation map
+    bool last_maps = false;       // the last update kept its P(fg) / novelty maps
+    bool keep_pre = false;        // pcm_set_debug bit 0: K3 also writes the pre-dilation map, K1 the per-pixel P(fg) / novelty maps
+    bool force_exact = false;     // pcm_set_debug bit 1: every label takes K2's exact path (tests)
     HostTrace trace;
 };
 
@@ -626,7 +628,7 @@ extern "C" void pcm_destroy(pcm_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto& m : h->models) free_model(m);
-    for (DevBuf* b : {&h->frame, &h->labels, &h->priors, &h->planes, &h->sched, &h->p1, &h->sa, &h->seg, &h->rmin, &h->rmax, &h->decision,
+    for (DevBuf* b : {&h->frame, &h->labels, &h->priors, &h->planes, &h->sched, &h->p1, &h->sa, &h->seg, &h->rmin, &h->rmax, &h->cmin, &h->cmax, &h->decision,
                       &h->scores, &h->flagged, &h->mask, &h->pre, &h->counts})
         b->release();
     h->prior_scratch.release();
@@ -865,12 +867,18 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     const int cx = rect[0], cy = rect[1], cw = rect[2], ch = rect[3];
     const size_t npx = (size_t)cw * ch;
     cudaStream_t st = h->stream;
-    CUDA_TRY(h->p1.reserve(npx * sizeof(double)));
-    if (p->novelty) CUDA_TRY(h->sa.reserve(npx * sizeof(double)));
+    // the per-pixel P(fg) / novelty maps are kept only for pcm_debug_last (pcm_set_debug); K2 recomputes what it needs
+    const bool keep_maps = want_pre;
+    if (keep_maps) {
+        CUDA_TRY(h->p1.reserve(npx * sizeof(double)));
+        if (p->novelty) CUDA_TRY(h->sa.reserve(npx * sizeof(double)));
+    }
     const SegLayout sl = seg_layout(S);
     CUDA_TRY(h->seg.reserve(sl.total));
     CUDA_TRY(h->rmin.reserve(sizeof(int) * (size_t)S));
     CUDA_TRY(h->rmax.reserve(sizeof(int) * (size_t)S));
+    CUDA_TRY(h->cmin.reserve(sizeof(int) * (size_t)S));
+    CUDA_TRY(h->cmax.reserve(sizeof(int) * (size_t)S));
     CUDA_TRY(h->decision.reserve((size_t)S));
     CUDA_TRY(h->scores.reserve(sizeof(float) * (size_t)S));
     if (want_pre) CUDA_TRY(h->pre.reserve(npx));
@@ -898,6 +906,8 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     pa.area = reinterpret_cast<int*>(seg + sl.area);
     pa.rmin = h->rmin.as<int>();
     pa.rmax = h->rmax.as<int>();
+    pa.cmin = h->cmin.as<int>();
+    pa.cmax = h->cmax.as<int>();
     pa.n_flagged = reinterpret_cast<int*>(seg + sl.nflag);
     pa.early = (pdl_enabled() && st == h->own_stream && h->chain_tail && !feed) ? 1 : 0;
     // rows [r0, r1) of the crop; only the first launch of a frame resets the per-label accumulators
@@ -945,13 +955,13 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
         a.pca0 = m0.pca;
         if (a.blend) a.pca1 = h->models[p->model_next].pca;
     }
-    a.p1_out = h->p1.as<double>();
-    a.sa_out = a.novelty ? h->sa.as<double>() : nullptr;
+    a.p1_out = keep_maps ? h->p1.as<double>() : nullptr;
+    a.sa_out = (keep_maps && a.novelty) ? h->sa.as<double>() : nullptr;
     a.seg.labels = d_labels;
     a.seg.n_labels = S;
     a.seg.thr = p->outlier_threshold;
     a.seg.sum = pa.sum; a.seg.asum = pa.asum; a.seg.area = pa.area;
-    a.seg.rmin = pa.rmin; a.seg.rmax = pa.rmax; a.seg.err = h->d_err;
+    a.seg.rmin = pa.rmin; a.seg.rmax = pa.rmax; a.seg.cmin = pa.cmin; a.seg.cmax = pa.cmax; a.seg.err = h->d_err;
 
     // forests live in shared memory whenever one CTA's tiles + forests fit, else they are read through L1
     ScoreSmem ls = score_smem_layout(a.g, a.f0, a.f1, a.blend, a.novelty, true);
@@ -1049,12 +1059,17 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     DecideArgs da{};
     da.p1 = a.p1_out; da.sa = a.sa_out; da.labels = d_labels; da.cw = cw; da.thr = p->outlier_threshold;
     da.sum = pa.sum; da.asum = pa.asum; da.area = pa.area; da.rmin = pa.rmin; da.rmax = pa.rmax;
+    da.cmin = pa.cmin; da.cmax = pa.cmax;
+    da.ps.planes = pa.planes; da.ps.pitch = pitch; da.ps.plane_stride = plane_stride; da.ps.cw = cw; da.ps.ch = ch;
+    da.ps.g = g; da.ps.f0 = a.f0; da.ps.f1 = a.f1; da.ps.depth = a.depth; da.ps.blend = a.blend;
+    da.ps.w0 = a.w0; da.ps.w1 = a.w1; da.ps.novelty = a.novelty; da.ps.pca0 = a.pca0; da.ps.pca1 = a.pca1;
     da.priors = d_priors;
     da.n_labels = S;
     da.prior_weight = p->prior_weight;
     da.decision = h->decision.as<uint8_t>();
     da.scores = h->scores.as<float>();
     da.n_flagged = reinterpret_cast<int*>(seg + sl.nflag);
+    da.force_exact = h->force_exact ? 1 : 0;
     {
         KernelTimer kt(h, 2);
         CUDA_TRY(launch_chain(segment_decide_kernel, dim3((S + 255) / 256), dim3(256), 0, st, da));
@@ -1089,6 +1104,7 @@ static int enqueue_update(pcm_handle* h, const uint8_t* d_frame, int H, int W, i
     h->last_novelty = a.novelty;
     h->last_valid = true;
     h->last_pre = want_pre;
+    h->last_maps = keep_maps;
     h->chain_tail = true;
     return PCM_OK;
 }
@@ -1751,7 +1767,7 @@ extern "C" int pcm_run_frames(pcm_handle* h, int frame_h, int frame_w, int64_t f
     // k - ahead before it enqueues frame k.  Without the limit a long sequence fills the stream's launch queue and the
     // thread then blocks INSIDE a launch call, which serialises the launches of the other sequence threads of the
     // process (the sweep runs 8 - 16 of them, each on its own stream).  PCM_RUN_AHEAD=0 switches the limit off.
-    static const int ahead = [] { const char* e = getenv("PCM_RUN_AHEAD"); int v = e ? atoi(e) : 32; return v < 0 ? 0 : v; }();
+    static const int ahead = [] { const char* e = getenv("PCM_RUN_AHEAD"); int v = e ? atoi(e) : 8; return v < 0 ? 0 : v; }();      // measured (256-sequence sweep, 16 threads): 0 -> 52-69, 8 -> 73-81, 32 -> 76-78 sequences/s
     if (ahead > 0 && (int)h->ahead_events.size() < ahead) {
         const size_t old = h->ahead_events.size();
         h->ahead_events.resize((size_t)ahead, nullptr);
@@ -1999,6 +2015,8 @@ extern "C" int pcm_debug_last(pcm_handle* h, double* p1, double* sa, float* scor
     const size_t npx = (size_t)h->last_cw * h->last_ch;
     const int S = h->last_S;
     const SegLayout sl = seg_layout(S);
+    if ((p1 || sa) && !h->last_maps)
+        return fail(PCM_E_STATE, "pcm_debug_last: the per-pixel maps are not kept (call pcm_set_debug(h, 1) first)");
     if (p1) CUDA_TRY(cudaMemcpy(p1, h->p1.p, npx * sizeof(double), cudaMemcpyDeviceToHost));
     if (sa) {
         if (h->last_novelty) CUDA_TRY(cudaMemcpy(sa, h->sa.p, npx * sizeof(double), cudaMemcpyDeviceToHost));
@@ -2024,7 +2042,8 @@ extern "C" int pcm_debug_last(pcm_handle* h, double* p1, double* sa, float* scor
 
 extern "C" int pcm_set_debug(pcm_handle* h, int on) {
     if (!h) return fail(PCM_E_INVALID, "pcm_set_debug: NULL handle");
-    h->keep_pre = on != 0;
+    h->keep_pre = (on & 1) != 0;
+    h->force_exact = (on & 2) != 0;
     return PCM_OK;
 }
 

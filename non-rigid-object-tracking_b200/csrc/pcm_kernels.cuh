@@ -2,7 +2,8 @@
 //
 //  K0 planes_kernel, K1 score_kernel: pcm_score.cuh
 //  K2 segment_decide      per-label score and decision (:240-242); labels inside the guard
-//                         band are re-evaluated exactly (sequential float32, raster order)
+//                         band are re-evaluated exactly (sequential float32, raster order) from
+//                         per-pixel values the block recomputes for the label's bounding box
 //  K3 mask_dilate         decision -> 0/255 map (:242-246) fused with cv.dilate (:112)
 //  K5 iou_kernel          computeBenchmark counts (benchmark.py:8-14)
 //  + convert_kernel / gather_kernel: parity taps (pcm_convert, pcm_gather_features)
@@ -11,16 +12,100 @@
 
 namespace pcm {
 
-// K2b ----------------------------------------------------------------------------
+// K2 -----------------------------------------------------------------------------
 // score = f32( (acc/area) * (1-w) + prior * w ) > 0.5 (:241-242), acc being the
 // reference's sequential float32 accumulator.  Every one of its `area` adds rounds a partial sum of
 // magnitude <= sum|d| to float32 (relative error 2^-24), so acc differs from the exact sum by at most
 // area * 2^-24 * sum|d| and the score by 2^-24 * sum|d| * |1-w|; a label whose score is that close to
-// 0.5 (plus the roundings of the score expression itself) is re-evaluated EXACTLY by its warp: float32 accumulator, each `+=` evaluated in
-// float64 and rounded to float32, pixels in raster order (:235-238).
+// 0.5 (plus the roundings of the score expression itself) is re-evaluated EXACTLY by its block: float32 accumulator, each
+// `+=` evaluated in float64 and rounded to float32, pixels in raster order (:235-238).
+//
+// The per-pixel values d of such a label are not stored by K1 (that would be 8 - 16 bytes per pixel of every frame for
+// the sake of about one label in ten frames): the block recomputes them for the pixels of the label's bounding box from
+// the colour planes in global memory -- same nodes, same leaf values, same operations in the same order as K1
+// (ps_forest / ps_novelty below), so the values are bit-identical.  With pcm_set_debug the maps ARE stored and read back.
+struct PixelScorer {
+    const uint8_t* planes;     // K0's planar crop: plane p at planes + p * plane_stride, rows `pitch` apart
+    long long pitch, plane_stride;
+    int cw, ch;
+    Geom g;
+    DevForest f0, f1;
+    int depth, blend;
+    double w0, w1;
+    int novelty;
+    DevPCA pca0, pca1;
+};
+
+// the tile byte offset a node carries -> the plane sample of pixel (x, y) it means (0 outside the crop, like the TMA fill)
+__device__ __forceinline__ unsigned ps_sample(const PixelScorer& s, int x, int y, unsigned tap) {
+    const unsigned plane = tap / (unsigned)s.g.PS, rem = tap - plane * (unsigned)s.g.PS;
+    const int r = y + (int)(rem / (unsigned)s.g.RS) - s.g.n, c = x + (int)(rem % (unsigned)s.g.RS) - s.g.HX;
+    if (r < 0 || r >= s.ch || c < 0 || c >= s.cw) return 0u;
+    return __ldg(s.planes + (long long)plane * s.plane_stride + (long long)r * s.pitch + c);
+}
+
+// mean leaf fraction of one forest, trees added in estimator order (four walked at a time for latency)
+__device__ double ps_forest(const PixelScorer& s, const DevForest& f, int x, int y) {
+    const uint8_t* nodes = reinterpret_cast<const uint8_t*>(f.nodes);
+    const uint8_t* leaves = reinterpret_cast<const uint8_t*>(f.leaves);
+    double acc = 0.0;
+    for (int t0 = 0; t0 < f.n_trees; t0 += 4) {
+        unsigned ref[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ref[q] = (unsigned)f.trees[min(t0 + q, f.n_trees - 1)].x;
+        for (int l = 0; l < s.depth; ++l) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const NodeT nd = __ldg(reinterpret_cast<const NodeT*>(nodes + ref[q]));
+                const unsigned v = ps_sample(s, x, y, node_tap(nd));
+                ref[q] = node_left(nd) + (v > node_thr(nd) ? NODE_BYTES : 0u);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (t0 + q < f.n_trees) acc = __dadd_rn(acc, __ldg(reinterpret_cast<const double*>(leaves + ref[q])));
+    }
+    return __ddiv_rn(acc, (double)f.n_trees);
+}
+
+// novelty_error of pcm_score.cuh for one pixel: features tap by tap, plane by plane
+__device__ double ps_novelty(const PixelScorer& s, const DevPCA& pca, int x, int y) {
+    const Geom& g = s.g;
+    const int nch = 3 * g.n_spaces;
+    double t = 0.0, err = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int k = 0; k < g.K; ++k) {
+            int dr, dc;
+            star_tap(k, dr, dc);
+            const unsigned off = (unsigned)((dr + g.n) * g.RS + (dc + g.HX));
+            const bool ok = ps_sample(s, x, y, (unsigned)(nch * g.PS) + off) != 0;
+            for (int p = 0; p < nch; ++p) {
+                const int f = (p / 3) * 3 * g.K + 3 * k + (p % 3);
+                const double v = ok ? u8_to_double(ps_sample(s, x, y, (unsigned)(p * g.PS) + off)) : -1.0;
+                if (pass == 0) t = fma(v, pca.comp255[f], t);
+                else err += fabs(fma(v, 1.0 / 255.0, -fma(t, pca.comp[f], pca.mean[f])));
+            }
+        }
+        if (pass == 0) t -= pca.mean_dot_comp;
+    }
+    return err;
+}
+
+__device__ double ps_contribution(const PixelScorer& s, int x, int y, double thr) {
+    double p = ps_forest(s, s.f0, x, y);
+    if (s.blend) p = blend2(p, ps_forest(s, s.f1, x, y), s.w0, s.w1);
+    double e = 0.0;
+    if (s.novelty) {
+        e = ps_novelty(s, s.pca0, x, y);
+        if (s.blend) e = blend2(e, ps_novelty(s, s.pca1, x, y), s.w0, s.w1);
+    }
+    return contribution(p, e, thr);
+}
+
 struct DecideArgs {
-    const double* p1;
-    const double* sa;          // nullptr when novelty is off
+    const double* p1;          // per-pixel maps kept by K1 (pcm_set_debug), or nullptr: recompute (ps)
+    const double* sa;          // nullptr when novelty is off or the maps are not kept
+    PixelScorer ps;
     const int32_t* labels;
     int cw;
     double thr;
@@ -29,63 +114,78 @@ struct DecideArgs {
     const int* area;
     const int* rmin;
     const int* rmax;
+    const int* cmin;
+    const int* cmax;
     const float* priors;       // nullptr -> all -1
     int n_labels;
     double prior_weight;
     uint8_t* decision;         // [S] 0/1
     float* scores;             // [S]
     int* n_flagged;            // number of labels that took the exact path
+    int force_exact;           // test hook (pcm_set_debug bit 1): every label takes the exact path
 };
 
 __global__ void __launch_bounds__(256) segment_decide_kernel(const DecideArgs a) {
+    __shared__ int s_list[256];
+    __shared__ int s_n;
+    __shared__ double s_d[256];
+    __shared__ unsigned char s_m[256];
     grid_dependency_wait();
     grid_launch_dependents();
-    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const double w = a.prior_weight;
     const double omw = __dsub_rn(1.0, w);
-    bool flagged = false;
-    int area = 0;
-    double prior = -1.0;
     if (s < a.n_labels) {
         // independent loads first: this kernel is one dependent-latency chain per label otherwise
-        area = a.area[s];
+        const int area = a.area[s];
         const double sum = a.sum[s], asum = a.asum[s];
-        const double pr = a.priors ? (double)a.priors[s] : -1.0;
+        const double prior = a.priors ? (double)a.priors[s] : -1.0;
         if (area <= 0) { a.decision[s] = 0; a.scores[s] = 0.f; }
         else {
-            prior = pr;
             const double sc = __dadd_rn(__dmul_rn(__ddiv_rn(sum, (double)area), omw), __dmul_rn(prior, w));
             const double band = 5.9604644775390625e-08 * asum * fabs(omw) * 1.0000001 + 2.4e-7;
-            flagged = fabs(sc - 0.5) <= band;
             a.decision[s] = sc > 0.5;
             a.scores[s] = (float)sc;
+            if (a.force_exact || fabs(sc - 0.5) <= band) s_list[atomicAdd(&s_n, 1)] = s;
         }
     }
-    unsigned todo = __ballot_sync(0xffffffffu, flagged);
-    if (todo && lane == 0) atomicAdd(a.n_flagged, __popc(todo));
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int L = __shfl_sync(0xffffffffu, s, src);
-        const int lo = a.rmin[L] * a.cw, hi = (a.rmax[L] + 1) * a.cw;
-        float acc = 0.f;   // identical in every lane
-        for (int base = lo; base < hi; base += 32) {
-            const int idx = base + lane;
-            const bool mine = (idx < hi) && (a.labels[idx] == L);
-            const double d = mine ? contribution(a.p1[idx], a.sa ? a.sa[idx] : 0.0, a.thr) : 0.0;
-            unsigned m = __ballot_sync(0xffffffffu, mine);
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                acc = __double2float_rn(__dadd_rn((double)acc, __shfl_sync(0xffffffffu, d, b)));
+    __syncthreads();
+    const int n_flagged = s_n;
+    if (n_flagged == 0) return;
+    if (threadIdx.x == 0) atomicAdd(a.n_flagged, n_flagged);
+    for (int f = 0; f < n_flagged; ++f) {
+        const int L = s_list[f];
+        const int r0 = a.rmin[L], r1 = a.rmax[L], c0 = a.cmin[L], c1 = a.cmax[L];
+        const int bw = c1 - c0 + 1, npos = bw * (r1 - r0 + 1);
+        float acc = 0.f;                                   // thread 0: the reference's float32 accumulator
+        for (int base = 0; base < npos; base += 256) {
+            const int q = base + threadIdx.x;
+            bool mine = false;
+            double d = 0.0;
+            if (q < npos) {
+                const int r = r0 + q / bw, c = c0 + q % bw;
+                const int idx = r * a.cw + c;
+                mine = a.labels[idx] == L;
+                if (mine) d = a.p1 ? contribution(a.p1[idx], a.sa ? a.sa[idx] : 0.0, a.thr) : ps_contribution(a.ps, c, r, a.thr);
             }
+            s_m[threadIdx.x] = mine;
+            s_d[threadIdx.x] = d;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int n = min(256, npos - base);
+                for (int i = 0; i < n; ++i)                // raster order inside the bounding box = raster order of the crop
+                    if (s_m[i]) acc = __double2float_rn(__dadd_rn((double)acc, s_d[i]));
+            }
+            __syncthreads();
         }
-        if (lane == src) {
-            const float sc = __double2float_rn(__dadd_rn(__dmul_rn(__ddiv_rn((double)acc, (double)area), omw),
+        if (threadIdx.x == 0) {
+            const double prior = a.priors ? (double)a.priors[L] : -1.0;
+            const float sc = __double2float_rn(__dadd_rn(__dmul_rn(__ddiv_rn((double)acc, (double)a.area[L]), omw),
                                                          __dmul_rn(prior, w)));
-            a.scores[s] = sc;
-            a.decision[s] = sc > 0.5f;
+            a.scores[L] = sc;
+            a.decision[L] = sc > 0.5f;
         }
     }
 }

@@ -94,6 +94,8 @@ struct PlanesArgs {
     int* area;
     int* rmin;
     int* rmax;
+    int* cmin;
+    int* cmax;
     int* n_flagged;
     int early;                // 1: the predecessor on the stream is this handle's own K3 / K5 (see below)
     int reset_flagged;        // 1: first K0 launch of a frame (a frame fed in row bands has several; n_labels = 0 in the others)
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(256) planes_kernel(const PlanesArgs a) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { *a.tile_counter = 0; if (a.reset_flagged) *a.n_flagged = 0; }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_labels; i += gridDim.x * blockDim.x) {
         a.sum[i] = 0.0; a.asum[i] = 0.0; a.area[i] = 0; a.rmin[i] = 0x7fffffff; a.rmax[i] = -1;
+        a.cmin[i] = 0x7fffffff; a.cmax[i] = -1;
     }
     __syncthreads();
     const int groups_per_row = (a.cw + 3) >> 2;
@@ -267,8 +270,8 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
 }
 
 // ---- per-label accumulation (np.unique :97 + first loop of compileSaliencyMap :235-238) ----
-// d = p1 - (max(sa, thr) - thr) per pixel (:237); per label: sum d, sum |d|, area, first /
-// last row.  Runs in K1's epilogue: the 32 lanes of a warp hold 32 consecutive pixels of one
+// d = p1 - (max(sa, thr) - thr) per pixel (:237); per label: sum d, sum |d|, area, bounding
+// box.  Runs in K1's epilogue: the 32 lanes of a warp hold 32 consecutive pixels of one
 // row; lanes with equal labels are combined with shuffles so that a warp issues one set of
 // atomics per distinct label.
 struct SegAcc {
@@ -280,6 +283,8 @@ struct SegAcc {
     int* area;                 // [S]
     int* rmin;                 // [S] init INT_MAX
     int* rmax;                 // [S] init -1
+    int* cmin;                 // [S] bounding columns of the label (K2's exact path visits only the box)
+    int* cmax;
     int* err;                  // STICKY per-handle word: set to 1 on an out-of-range label, cleared by the host once read
 };
 
@@ -291,7 +296,7 @@ __device__ __forceinline__ double contribution(double p1, double sa, double thr)
 // sum of magnitudes `as`.  lab < 0: the lane does not take part.  Lanes with equal labels are
 // combined (shuffles for the float64 sums, redux.sync for the integers) and the group's
 // leader issues one set of atomics.
-__device__ __forceinline__ void segment_flush(const SegAcc& s, int lab, double sm, double as, int cnt, int r0, int r1) {
+__device__ __forceinline__ void segment_flush(const SegAcc& s, int lab, double sm, double as, int cnt, int r0, int r1, int col) {
     const int lane = threadIdx.x & 31;
     unsigned todo = __ballot_sync(0xffffffffu, lab >= 0);
     while (todo) {
@@ -308,12 +313,16 @@ __device__ __forceinline__ void segment_flush(const SegAcc& s, int lab, double s
         const int n = __reduce_add_sync(0xffffffffu, mine ? cnt : 0);
         const int lo = __reduce_min_sync(0xffffffffu, mine ? r0 : 0x7fffffff);
         const int hi = __reduce_max_sync(0xffffffffu, mine ? r1 : -1);
+        const int cl = __reduce_min_sync(0xffffffffu, mine ? col : 0x7fffffff);
+        const int ch = __reduce_max_sync(0xffffffffu, mine ? col : -1);
         if (lane == leader) {
             atomicAdd(s.sum + L, x);
             atomicAdd(s.asum + L, y);
             atomicAdd(s.area + L, n);
             atomicMin(s.rmin + L, lo);
             atomicMax(s.rmax + L, hi);
+            atomicMin(s.cmin + L, cl);
+            atomicMax(s.cmax + L, ch);
         }
         todo &= ~members;
     }
@@ -332,8 +341,8 @@ struct ScoreArgs {
     double w0, w1;                   // np.average weights
     int novelty;                     // 0/1
     DevPCA pca0, pca1;
-    double* p1_out;                  // [ch*cw]
-    double* sa_out;                  // [ch*cw] (novelty only)
+    double* p1_out;                  // [ch*cw], or NULL: not kept (only pcm_set_debug keeps the per-pixel maps; K2's exact
+    double* sa_out;                  // path recomputes the few pixels it needs).  sa_out: novelty only
     SegAcc seg;                      // per-label accumulators (epilogue)
 };
 
@@ -718,13 +727,15 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
             int l = lab[i];
             if (ox < a.cw && oy < a.ch) {
                 const size_t o = (size_t)oy * a.cw + ox;
-                a.p1_out[o] = p[i];
-                if (a.novelty) a.sa_out[o] = e[i];
+                if (a.p1_out) {
+                    a.p1_out[o] = p[i];
+                    if (a.novelty) a.sa_out[o] = e[i];
+                }
                 if (l < 0 || l >= a.seg.n_labels) { *a.seg.err = 1; l = -1; }
             }
             const bool change = (l != run_lab) && run_lab >= 0;
             if (__any_sync(0xffffffffu, change)) {
-                segment_flush(a.seg, change ? run_lab : -1, run_sum, run_abs, run_cnt, run_r0, run_r1);
+                segment_flush(a.seg, change ? run_lab : -1, run_sum, run_abs, run_cnt, run_r0, run_r1, ox);
                 if (change) run_lab = -1;
             }
             if (l >= 0) {
@@ -733,7 +744,7 @@ __global__ void __launch_bounds__(NTHREADS, PCM_MIN_CTAS) score_kernel(const __g
                 run_sum += d; run_abs += fabs(d); run_cnt++; run_r1 = oy;
             }
         }
-        segment_flush(a.seg, run_lab, run_sum, run_abs, run_cnt, run_r0, run_r1);
+        segment_flush(a.seg, run_lab, run_sum, run_abs, run_cnt, run_r0, run_r1, ox);
         __syncthreads();   // tile buffer `buf` may be refilled; sched[buf^1] is visible
     }
 }

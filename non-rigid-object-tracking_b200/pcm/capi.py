@@ -225,9 +225,19 @@ class Handle:
         if debug:
             self.set_debug(True)
 
-    def set_debug(self, on=True):
-        """Keep the stage buffers `debug_last` reports (pre-dilation map)."""
-        self._check(self.lib.pcm_set_debug(self._h, int(bool(on))))
+    def set_debug(self, on=True, force_exact=False):
+        """on: keep the stage buffers `debug_last` reports (P(fg) / novelty maps, pre-dilation map); force_exact: every
+        label takes the exact sequential-float32 path of the decision kernel (test hook)."""
+        self._check(self.lib.pcm_set_debug(self._h, int(bool(on)) | (2 if force_exact else 0)))
+
+    def debug_scores(self, n_labels):
+        """Per-label results of the last update that exist without `set_debug`: scores, areas, number of labels that took
+        the exact path."""
+        scores = np.empty(n_labels, np.float32)
+        areas = np.empty(n_labels, np.int64)
+        nx = C.c_int32(0)
+        self._check(self.lib.pcm_debug_last(self._h, None, None, _ptr(scores), _ptr(areas), None, C.byref(nx)))
+        return dict(scores=scores, areas=areas, n_exact=nx.value)
 
     def _check(self, rc):
         if rc:

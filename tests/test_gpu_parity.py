@@ -257,6 +257,77 @@ def test_guard_band_labels_take_exact_path():
     h.close()
 
 
+@pytest.mark.parametrize("keep_maps", [False, True])
+@pytest.mark.parametrize("novelty,blend", [(False, False), (True, True), (False, True)])
+def test_exact_path_recomputes_what_it_needs(keep_maps, novelty, blend):
+    """K1 does not store P(fg) (unless pcm_set_debug asks for it); a label on the exact path gets its per-pixel values
+    recomputed by K2 from the colour planes.  With EVERY label forced onto that path (test hook) the float32 scores must
+    equal the reference's sequential accumulation bit for bit -- random forests of several depths, two blended models,
+    the PCA novelty term, crop borders, labels of every shape."""
+    from pcm import capi
+    from pcm.providers import voronoi_segments
+    rng = np.random.default_rng(21 + 2 * novelty + blend)
+    hgt, wid, n, spaces = 75, 118, 3, ["lab", "rgb"]
+    F = 3 * (1 + 8 * n) * len(spaces)
+    frame = rng.integers(0, 256, (hgt + 9, wid + 14, 3), dtype=np.uint8)
+    rect = (6, 4, wid, hgt)
+    crop = frame[4:4 + hgt, 6:6 + wid]
+    t0 = _random_forest_arrays(rng, 7, 6, F)
+    t1 = _random_forest_arrays(rng, 50, 3, F)            # more trees than the constant bank holds top levels for
+    h = capi.Handle(0)
+    h.set_debug(keep_maps, force_exact=True)
+    h.set_features(n, spaces)
+    h.add_model_arrays(0, t0)
+    h.add_model_arrays(1, t1)
+    X = orc.get_features_int(orc.build_planes(crop, spaces), n)
+    thr = 0.0
+    pcas = []
+    if novelty:
+        for m in range(2):
+            mean, comp = rng.random(F), rng.normal(size=F)
+            comp /= np.linalg.norm(comp)
+            h.set_novelty(m, mean, comp)
+            pcas.append((mean, comp))
+        thr = 40.0
+    tau = 0.7
+    w0, w1 = (1 - tau, tau) if blend else (1.0, 0.0)
+    seg = voronoi_segments(crop, 45, seed=5)
+    S = int(seg.max()) + 1
+    prm = capi.Handle.make_params(0, 1 if blend else -1, w0, w1, novelty=novelty, dilation_kernel=3, outlier_threshold=thr)
+    mask = np.zeros(frame.shape, np.uint8)
+    h.update(frame, rect, seg, S, None, prm, mask)
+    d = h.debug_scores(S)
+    p1 = orc.forest_p1(orc.forest_from_arrays(t0, F), X)
+    sa = np.zeros(hgt * wid)
+    if blend:
+        p1 = orc.blend(p1, orc.forest_p1(orc.forest_from_arrays(t1, F), X), tau)
+    if novelty:
+        sa = orc.novelty_error(X, pcas[0][0], pcas[0][1].reshape(1, -1))
+        if blend:
+            sa = orc.blend(sa, orc.novelty_error(X, pcas[1][0], pcas[1][1].reshape(1, -1)), tau)
+    scores, areas = orc.saliency_scores(p1, sa, seg, thr, np.full(S, -1, np.float32), 0.0)
+    assert d["n_exact"] == S and np.array_equal(d["areas"], areas)
+    if novelty:                                          # the novelty error itself is only pinned to 1e-5 (north_star)
+        assert np.allclose(d["scores"], scores, rtol=NOVELTY_RTOL, atol=1e-6)
+    else:
+        assert np.array_equal(d["scores"], scores)
+        assert np.array_equal(mask[4:4 + hgt, 6:6 + wid, 2], orc.dilate(orc.saliency_mask(scores, seg), 3))
+    # stored maps and recomputed values must give the SAME bits: compare against the other mode
+    h2 = capi.Handle(0)
+    h2.set_debug(not keep_maps, force_exact=True)
+    h2.set_features(n, spaces)
+    h2.add_model_arrays(0, t0)
+    h2.add_model_arrays(1, t1)
+    for m, (mean, comp) in enumerate(pcas):
+        h2.set_novelty(m, mean, comp)
+    mask2 = np.zeros(frame.shape, np.uint8)
+    h2.update(frame, rect, seg, S, None, prm, mask2)
+    assert np.array_equal(h2.debug_scores(S)["scores"], d["scores"])
+    assert np.array_equal(mask2, mask)
+    h.close()
+    h2.close()
+
+
 def test_priors_and_prior_weight():
     from pcm import capi
     rng = np.random.default_rng(12)
