@@ -249,24 +249,14 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
         -- for every clip of the shard, in the same (step, clip) order on every rank: the ranks that share a clip split
         the per-frame host work and all-reduce the pieces (main thread only)."""
         needs = clip_needs(all_items or items)
-
-        def one(v):
+        for v in order_v:
             cfg = sequence_config(base, polygons, v, items[0][3], videos_path, truth_path)
-            if step == "sift":
-                if needs[v][1] and gpu_prior:
-                    clips[v].prepare(cfg, [], True)
-            elif step in needs[v][0]:
-                clips[v].prepare(cfg, [step], False)
-        with stages.stage("prepare_clips"):
-            if not shares and len(order_v) > 1:
-                # no rank shares a clip with this one (single-GPU run): nothing here is a collective, so the clips are
-                # prepared side by side instead of one after the other
-                from concurrent.futures import ThreadPoolExecutor
-                with ThreadPoolExecutor(max_workers=len(order_v)) as pool:
-                    list(pool.map(one, order_v))
-            else:
-                for v in order_v:
-                    one(v)
+            with stages.stage("prepare_clips"):
+                if step == "sift":
+                    if needs[v][1] and gpu_prior:
+                        clips[v].prepare(cfg, [], True)
+                elif step in needs[v][0]:
+                    clips[v].prepare(cfg, [step], False)
 
     def ready_after(step, k):
         """Sequence k can start once `step` is prepared (its label maps, and the SIFT features if it uses the prior)."""
