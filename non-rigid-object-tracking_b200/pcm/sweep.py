@@ -245,6 +245,8 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
     PREPARE_STEPS = ("quickshift", "felzenszwalb", "sift")
 
     def prepare_clips(step):
+        # (measured, round 2: preparing the clips of a single-GPU run side by side instead of one after the other made the
+        # sweep SLOWER -- 55-64 instead of 79 sequences/s: every clip's frames are already spread over all host cores)
         """One kind of what all sequences of a clip share -- the label maps of an over-segmentation, or the SIFT features
         -- for every clip of the shard, in the same (step, clip) order on every rank: the ranks that share a clip split
         the per-frame host work and all-reduce the pieces (main thread only)."""
