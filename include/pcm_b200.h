@@ -209,6 +209,16 @@ int pcm_felzenszwalb(const uint8_t* frame, int frame_h, int frame_w, int64_t fra
                      double scale, double sigma, int min_size, const double* kernel, int kernel_radius,
                      int32_t* labels_out, int* n_labels_out);
 
+/* skimage.segmentation.slic(crop, n_segments, compactness, sigma, max_iter = 10, start_label) of scikit-image 0.17.2
+ * (:74-75: n_segments = 250, compactness = 10, sigma = 1, start_label = 0) on the crop `rect` of a HOST frame: Gaussian,
+ * rgb2lab, k-means from a regular seed grid, connectivity enforcement.  HOST code (no handle, no device), like
+ * pcm_felzenszwalb; parity pinned only against oracle/slic_oracle.py (scikit-image is not available here).
+ *   kernel      2 * kernel_radius + 1 Gaussian weights (scipy's _gaussian_kernel1d), or NULL to compute them from sigma
+ *   labels_out  h*w int32, labels start_label .. ; n_labels_out = largest label + 1 */
+int pcm_slic(const uint8_t* frame, int frame_h, int frame_w, int64_t frame_stride, const int rect[4], int n_segments,
+             double compactness, double sigma, const double* kernel, int kernel_radius, int max_iter, int start_label,
+             int32_t* labels_out, int* n_labels_out);
+
 /* Parity tap: the cost-ordered merge, union-find and min-size passes of pcm_felzenszwalb on a caller-provided
  * edge list (n_edges edges a[i]-b[i] with non-negative cost[i]; `scale` is the k of k/|C|, already on the scale
  * of the costs).  Same host code as pcm_felzenszwalb after its edge construction; checked against the

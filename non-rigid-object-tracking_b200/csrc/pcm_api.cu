@@ -35,6 +35,9 @@ int felzenszwalb(const uint8_t* frame, int64_t stride, int cx, int cy, int w, in
                  int min_size, const double* kernel, int radius, int32_t* labels_out);
 int felzenszwalb_graph(int n_vertices, int n_edges, const int32_t* a, const int32_t* b, const double* cost, double scale,
                        int min_size, int32_t* labels_out);
+// pcm_slic.cpp
+int slic(const uint8_t* frame, int64_t stride, int cx, int cy, int w, int h, int n_segments, double compactness, double sigma,
+         const double* kernel, int radius, int max_iter, int start_label, int32_t* labels_out);
 }
 
 // ---------------------------------------------------------------------------------
@@ -1704,6 +1707,22 @@ extern "C" int pcm_felzenszwalb(const uint8_t* frame, int H, int W, int64_t stri
     const int n = felzenszwalb(frame, stride, rect[0], rect[1], rect[2], rect[3], scale, sigma, min_size, kernel,
                                kernel_radius, labels_out);
     if (n < 0) return fail(PCM_E_INVALID, "pcm_felzenszwalb: bad arguments");
+    if (n_labels_out) *n_labels_out = n;
+    return PCM_OK;
+}
+
+extern "C" int pcm_slic(const uint8_t* frame, int H, int W, int64_t stride, const int rect[4], int n_segments,
+                        double compactness, double sigma, const double* kernel, int kernel_radius, int max_iter,
+                        int start_label, int32_t* labels_out, int* n_labels_out) {
+    if (!frame || !rect || !labels_out) return fail(PCM_E_INVALID, "pcm_slic: NULL argument");
+    if (rect[2] <= 0 || rect[3] <= 0 || rect[0] < 0 || rect[1] < 0 || rect[0] + rect[2] > W || rect[1] + rect[3] > H)
+        return fail(PCM_E_INVALID, "pcm_slic: rect outside the frame");
+    if ((long long)rect[2] * rect[3] > (1LL << 28)) return fail(PCM_E_LIMIT, "pcm_slic: crop too large");
+    if (kernel && kernel_radius < 0) return fail(PCM_E_INVALID, "pcm_slic: kernel_radius %d", kernel_radius);
+    if (start_label < 0) return fail(PCM_E_INVALID, "pcm_slic: start_label %d", start_label);
+    const int n = slic(frame, stride, rect[0], rect[1], rect[2], rect[3], n_segments, compactness, sigma, kernel, kernel_radius,
+                       max_iter, start_label, labels_out);
+    if (n < 0) return fail(PCM_E_INVALID, "pcm_slic: bad arguments (n_segments >= 1, compactness > 0, max_iter >= 0)");
     if (n_labels_out) *n_labels_out = n;
     return PCM_OK;
 }

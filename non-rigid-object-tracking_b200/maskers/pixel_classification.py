@@ -71,11 +71,11 @@ class PixelClassificationNonRigidMasker(Masker):
         self.native = capi.Handle(device)
         self.native.set_features(self.n_neighbors, self.spaces)
         # over-segmentation (:70-75), SURVEY §8 f-1: quickshift runs on the GPU (pcm_quickshift),
-        # felzenszwalb in the library's host code (pcm_felzenszwalb: inherently sequential); SLIC has
-        # no native implementation and uses a stand-in provider
+        # felzenszwalb and SLIC in the library's host code (pcm_felzenszwalb: inherently sequential; pcm_slic)
         self.native_quickshift = segment_fn is None and params["over_segmentation"] == "quickshift"
         self.native_felzenszwalb = segment_fn is None and params["over_segmentation"] == "felzenszwalb"
-        self.segment_fn = segment_fn or (None if (self.native_quickshift or self.native_felzenszwalb)
+        self.native_slic = segment_fn is None and params["over_segmentation"] == "SLIC"
+        self.segment_fn = segment_fn or (None if (self.native_quickshift or self.native_felzenszwalb or self.native_slic)
                                          else make_segment_provider(params["over_segmentation"]))
         self._qs_noise_shape = None
         self._seg_prev = None                  # (provider's array object, crop shape) of the label map resident on the device
@@ -229,6 +229,10 @@ class PixelClassificationNonRigidMasker(Masker):
                         segments, n_labels = cache.get_or_compute((self.cache_tag, "felzenszwalb", self.index, (x, y, w, h)), segment)
                     else:
                         segments, n_labels = segment()
+            elif self.native_slic:
+                # slic(crop, n_segments=250, compactness=10, sigma=1, start_label=0) (:75)
+                with stages.stage("slic"):
+                    segments, n_labels = capi.slic(frame, (x, y, w, h), n_segments=250, compactness=10.0, sigma=1.0, start_label=0)
             else:
                 raw = self.segment_fn(crop)
                 # a provider that hands back the very same READ-ONLY array vouches that the map has not changed: it is

@@ -14,9 +14,10 @@ UNITS = [("pcm_api.cu", [], "pcm_api.o"),
          ("pcm_score_inst.cu", ["-DPCM_PPT=7"], "pcm_score_ppt7.o"),
          ("pcm_score_inst.cu", ["-DPCM_PPT=8"], "pcm_score_ppt8.o"),
          ("pcm_host_simd.cpp", [], "pcm_host_simd.o"),
-         ("pcm_felzenszwalb.cpp", [], "pcm_felzenszwalb.o")]
+         ("pcm_felzenszwalb.cpp", [], "pcm_felzenszwalb.o"),
+         ("pcm_slic.cpp", [], "pcm_slic.o")]
 DEPS = ["pcm_api.cu", "pcm_score_inst.cu", "pcm_score_variants.h", "pcm_score.cuh", "pcm_kernels.cuh", "pcm_device.cuh", "pcm_host.h",
-        "pcm_host_simd.cpp", "pcm_felzenszwalb.cpp", "pcm_quickshift.cuh", "pcm_forest_fit.cuh", "pcm_prior.cuh",
+        "pcm_host_simd.cpp", "pcm_felzenszwalb.cpp", "pcm_slic.cpp", "pcm_quickshift.cuh", "pcm_forest_fit.cuh", "pcm_prior.cuh",
         os.path.join("..", "..", "include", "pcm_b200.h")]
 
 NVCC_FLAGS = [

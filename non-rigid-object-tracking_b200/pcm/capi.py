@@ -77,6 +77,7 @@ def load_library():
         "pcm_quickshift_device": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
         "pcm_felzenszwalb": (I, [P, I, I, L, P, D, D, I, P, I, P, C.POINTER(I)]),
         "pcm_felzenszwalb_graph": (I, [I, I, P, P, P, D, I, P, C.POINTER(I)]),
+        "pcm_slic": (I, [P, I, I, L, P, I, D, D, P, I, I, I, P, C.POINTER(I)]),
         "pcm_host_register": (I, [P, C.c_size_t]),
         "pcm_host_unregister": (I, [P]),
         "pcm_run_frames": (I, [P, I, I, L, P, L, P, I]),
@@ -115,7 +116,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_use_own_stream", "pcm_get_stream", "pcm_synchronize",
     "pcm_set_features", "pcm_num_features", "pcm_add_model", "pcm_set_novelty", "pcm_num_models", "pcm_crop_rect",
-    "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device", "pcm_felzenszwalb", "pcm_felzenszwalb_graph",
+    "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device", "pcm_felzenszwalb", "pcm_felzenszwalb_graph", "pcm_slic",
     "pcm_prior_device", "pcm_run_frames", "pcm_fit_forest", "pcm_fit_rows", "pcm_pca_moments", "pcm_pca_residuals", "pcm_convert", "pcm_gather_features",
     "pcm_set_debug", "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_transfer_bytes", "pcm_set_label_cache", "pcm_profile_enable", "pcm_profile_read",
     "pcm_host_register", "pcm_host_unregister",
@@ -172,6 +173,28 @@ def felzenszwalb(frame, rect, scale=100, sigma=0.5, min_size=50):
     n = C.c_int(0)
     rc = lib.pcm_felzenszwalb(_ptr(frame), frame.shape[0], frame.shape[1], frame.strides[0], r, float(scale), float(sigma),
                               int(min_size), _ptr(kernel), radius, _ptr(out), C.byref(n))
+    if rc:
+        raise PcmError(rc, lib.pcm_last_error().decode())
+    return out, n.value
+
+
+def slic(frame, rect, n_segments=250, compactness=10.0, sigma=1.0, max_iter=10, start_label=0):
+    """SLIC superpixels of the crop `rect` (defaults = the reference's call, pixel_classification.py:75).  Host code in the
+    library; returns (labels int32 HxW, n_labels).  The Gaussian weights are computed here the way scipy.ndimage does."""
+    lib = load_library()
+    if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3 or frame.strides[2] != 1 or frame.strides[1] != 3:
+        frame = np.ascontiguousarray(frame, np.uint8)
+    r = (C.c_int * 4)(*[int(v) for v in rect])
+    kernel, radius = None, 0
+    if sigma > 0:
+        radius = int(4.0 * float(sigma) + 0.5)
+        x = np.arange(-radius, radius + 1)
+        phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+        kernel = np.ascontiguousarray(phi / phi.sum(), np.float64)
+    out = np.empty((rect[3], rect[2]), np.int32)
+    n = C.c_int(0)
+    rc = lib.pcm_slic(_ptr(frame), frame.shape[0], frame.shape[1], frame.strides[0], r, int(n_segments), float(compactness),
+                      float(sigma), _ptr(kernel), radius, int(max_iter), int(start_label), _ptr(out), C.byref(n))
     if rc:
         raise PcmError(rc, lib.pcm_last_error().decode())
     return out, n.value

@@ -42,10 +42,10 @@ def voronoi_segments(crop, n_sites=200, seed=0):
 def make_segment_provider(name, **kw):
     """Resolve `params.over_segmentation` (config.yaml:29) to a label provider.
 
-    'grid[:block]' and 'voronoi[:sites]' are the deterministic stand-ins; the
-    reference's names ('quickshift', 'felzenszwalb', 'SLIC') map to the grid
-    provider with a block size giving a comparable superpixel count until a
-    native over-segmenter lands.
+    'grid[:block]' and 'voronoi[:sites]' are deterministic test providers.  The reference's names ('quickshift',
+    'felzenszwalb', 'SLIC') normally never get here -- the masker runs all three natively (pcm_quickshift on the GPU,
+    pcm_felzenszwalb / pcm_slic in the library's host code); asked for explicitly they map to the grid
+    provider with a block size giving a comparable superpixel count.
     """
     name = str(name)
     if name.startswith("grid"):
@@ -55,8 +55,6 @@ def make_segment_provider(name, **kw):
         sites = int(name.split(":")[1]) if ":" in name else kw.get("n_sites", 200)
         return lambda crop: voronoi_segments(crop, sites, kw.get("seed", 0))
     if name in ("quickshift", "felzenszwalb", "SLIC"):
-        # 'quickshift' and 'felzenszwalb' normally never get here: the masker runs them natively
-        # (pcm_quickshift on the GPU, pcm_felzenszwalb in the library's host code)
         block = {"quickshift": 6, "felzenszwalb": 10, "SLIC": 12}[name]
         return lambda crop: grid_segments(crop, block)
     raise ValueError("unknown over_segmentation %r" % name)
