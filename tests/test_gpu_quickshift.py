@@ -120,3 +120,35 @@ def test_masker_uses_native_quickshift():
         assert b.update(bbox=box, frame=frames[i], mask=mb, color=None) is None
         assert ma[..., 2].any() and np.array_equal(ma, mb)
     a.close(); b.close()
+
+
+def test_masker_uses_native_slic():
+    """config over_segmentation: SLIC -> the plugin runs pcm_slic (host code of the library) and produces the same mask as
+    the same masker fed the oracle's label map through segment_fn (oracle/slic_oracle.py; parity unpinned against
+    scikit-image itself)."""
+    import slic_oracle as so
+    from maskers import getMaskerByName
+    from test_gpu_parity import _random_forest_arrays
+    rng = np.random.default_rng(10)
+    frames = read_video("Video", "soldier")
+    cfg = dict(multi_selection=False, params=dict(n_estimators=20, max_depth=5, n_components=1, novelty_detection=False,
+                                                  over_segmentation="SLIC", features="6 lab", dilation_kernel=7,
+                                                  prior_weight=0.0))
+    trees = _random_forest_arrays(rng, 12, 5, 3 * 49)
+
+    def make(**kw):
+        m = getMaskerByName("PC", debug=False, frame=frames[0], config=cfg, poly_roi=None, update_mask=False, **kw)
+        m.native.add_model_arrays(0, trees)
+        m.models.append({"n_frame": 0, "model": None})
+        m.novelty_det.append({"n_frame": 0, "model": None, "threshold": 0.0})
+        return m
+    a = make()
+    b = make(segment_fn=lambda crop: so.slic(crop, n_segments=250, compactness=10, sigma=1, start_label=0))
+    assert a.native_slic and not b.native_slic
+    for i in range(3):
+        ma, mb = np.zeros_like(frames[i]), np.zeros_like(frames[i])
+        box = (340 - 4 * i, 20, 90, 180)
+        assert a.update(bbox=box, frame=frames[i], mask=ma, color=None) is None
+        assert b.update(bbox=box, frame=frames[i], mask=mb, color=None) is None
+        assert ma[..., 2].any() and np.array_equal(ma, mb)
+    a.close(); b.close()
