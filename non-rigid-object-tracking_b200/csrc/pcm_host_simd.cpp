@@ -43,9 +43,16 @@ __attribute__((target("ssse3"))) static int scatter3_ssse3(const uint8_t* s, uin
         const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i));
         __m128i* q = reinterpret_cast<__m128i*>(d + 3 * i);
         const __m128i a = _mm_loadu_si128(q), b = _mm_loadu_si128(q + 1), c = _mm_loadu_si128(q + 2);
-        _mm_storeu_si128(q, _mm_or_si128(_mm_andnot_si128(k0, a), _mm_shuffle_epi8(v, p0)));
-        _mm_storeu_si128(q + 1, _mm_or_si128(_mm_andnot_si128(k1, b), _mm_shuffle_epi8(v, p1)));
-        _mm_storeu_si128(q + 2, _mm_or_si128(_mm_andnot_si128(k2, c), _mm_shuffle_epi8(v, p2)));
+        const __m128i na = _mm_or_si128(_mm_andnot_si128(k0, a), _mm_shuffle_epi8(v, p0));
+        const __m128i nb = _mm_or_si128(_mm_andnot_si128(k1, b), _mm_shuffle_epi8(v, p1));
+        const __m128i nc = _mm_or_si128(_mm_andnot_si128(k2, c), _mm_shuffle_epi8(v, p2));
+        // a mask changes little from frame to frame: where the caller's bytes already hold the new values nothing is
+        // stored, so the cache lines stay clean and the scatter costs their read only
+        const __m128i same = _mm_and_si128(_mm_and_si128(_mm_cmpeq_epi8(na, a), _mm_cmpeq_epi8(nb, b)), _mm_cmpeq_epi8(nc, c));
+        if (_mm_movemask_epi8(same) == 0xffff) continue;
+        _mm_storeu_si128(q, na);
+        _mm_storeu_si128(q + 1, nb);
+        _mm_storeu_si128(q + 2, nc);
     }
     return i;
 }
