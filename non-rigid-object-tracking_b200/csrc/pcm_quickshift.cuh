@@ -166,7 +166,10 @@ __global__ void __launch_bounds__(QS_BW * QS_BH) qs_parent_kernel(const QsArgs a
 // the one-pixel-per-thread kernel above was bound by the shared-memory pipe as much as by the float64 pipe).  Every
 // pixel still adds its window in raster order (rows ascending, columns ascending inside a row), exactly like the
 // Cython loop.  Block = 32 x 8 threads = 32 x 32 pixels.
-constexpr int QS_DR = 4, QS_DBW = 32, QS_DBH = 8 * QS_DR;
+#ifndef PCM_QS_DR
+#define PCM_QS_DR 4                 // tuning experiments (profiles/README.md): rows per thread
+#endif
+constexpr int QS_DR = PCM_QS_DR, QS_DBW = 32, QS_DBH = 8 * QS_DR;
 
 template <bool GUARD>
 __global__ void __launch_bounds__(256) qs_density_kernel(const QsArgs a) {
