@@ -161,13 +161,15 @@ __global__ void __launch_bounds__(QS_BW * QS_BH) qs_parent_kernel(const QsArgs a
     a.parent[r * a.cw + c] = best;
 }
 
-// Density pass, register-blocked: a thread owns QS_DR vertically adjacent pixels, so the Lab values of a window position
-// are fetched from shared memory once for all of them (0.9 instead of 3 shared-memory loads per pixel-tap; round 2:
-// the one-pixel-per-thread kernel above was bound by the shared-memory pipe as much as by the float64 pipe).  Every
-// pixel still adds its window in raster order (rows ascending, columns ascending inside a row), exactly like the
-// Cython loop.  Block = 32 x 8 threads = 32 x 32 pixels.
+// Density pass.  A thread owns QS_DR vertically adjacent pixels and fetches the Lab values of a window position from
+// shared memory once for all of them; every pixel still adds its window in raster order (rows ascending, columns
+// ascending inside a row), exactly like the Cython loop.  Block = 32 x 8 threads = 32 x (8 QS_DR) pixels.
+// Measured at 1080p (round 2, profiles/README.md): QS_DR = 1 / 2 / 3 / 4 / 6 / 8 -> 1.43 / 1.47 / 1.53 / 1.57 / 1.65 /
+// 2.68 ms.  Sharing the fetches (0.9 instead of 3 shared-memory loads per pixel-tap at QS_DR = 4) does NOT pay: the kernel
+// waits on float64 dependency chains (top stall `wait`, float64 pipe 61 %), and one pixel per thread keeps more warps
+// resident (31 KB of shared memory per block instead of 61 KB).  Default: 1.
 #ifndef PCM_QS_DR
-#define PCM_QS_DR 4                 // tuning experiments (profiles/README.md): rows per thread
+#define PCM_QS_DR 1                 // rows per thread (see above)
 #endif
 constexpr int QS_DR = PCM_QS_DR, QS_DBW = 32, QS_DBH = 8 * QS_DR;
 
