@@ -168,10 +168,13 @@ __global__ void __launch_bounds__(QS_BW * QS_BH) qs_parent_kernel(const QsArgs a
 // 2.68 ms.  Sharing the fetches (0.9 instead of 3 shared-memory loads per pixel-tap at QS_DR = 4) does NOT pay: the kernel
 // waits on float64 dependency chains (top stall `wait`, float64 pipe 61 %), and one pixel per thread keeps more warps
 // resident (31 KB of shared memory per block instead of 61 KB).  Default: 1.
+#ifndef PCM_QS_UNROLL
+#define PCM_QS_UNROLL 2             // taps of a window row in flight per thread (independent exp chains): 1 / 2 / 4 -> 1.43 / 1.38 / 1.38 ms
+#endif
 #ifndef PCM_QS_DR
 #define PCM_QS_DR 1                 // rows per thread (see above)
 #endif
-constexpr int QS_DR = PCM_QS_DR, QS_DBW = 32, QS_DBH = 8 * QS_DR;
+constexpr int QS_DR = PCM_QS_DR, QS_DBW = 32, QS_DBH = 8 * QS_DR, QS_UNROLL = PCM_QS_UNROLL;
 
 template <bool GUARD>
 __global__ void __launch_bounds__(256) qs_density_kernel(const QsArgs a) {
@@ -221,6 +224,7 @@ __global__ void __launch_bounds__(256) qs_density_kernel(const QsArgs a) {
             const double t = (double)dr;
             dr2[p] = __dmul_rn(t, t);
         }
+#pragma unroll QS_UNROLL
         for (int c_ = c_min; c_ < c_max; ++c_) {
             const int j = row + c_;
             const double L = sL[j], A = sA[j], B = sB[j], dc2 = sqc[-c_];
