@@ -145,14 +145,21 @@ __global__ void __launch_bounds__(QS_BW * QS_BH) qs_parent_kernel(const QsArgs a
     const double l0 = sL[me], a0 = sA[me], b0 = sB[me];
     const double cur = sD[me];
     double closest = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+    int closest_ceil = 0x7fffffff;         // ceil(closest): an integer s is < closest exactly when s < closest_ceil
     int best = r * a.cw + c;
     for (int r_ = r_min; r_ < r_max; ++r_) {
         const int row = (r_ - y0 + kw) * TW + kw - x0;
+        const int dr2 = (r - r_) * (r - r_);
         for (int c_ = c_min; c_ < c_max; ++c_) {
             const int j = row + c_;
-            if (sD[j] > cur) {
+            // the squared distance is at least its (exactly representable) image-plane part, whatever the roundings of the
+            // colour terms: a tap that far away cannot beat the current candidate and its Lab values are not even fetched
+            if (sD[j] > cur && dr2 + (c - c_) * (c - c_) < closest_ceil) {
                 const double d = qs_dist(l0, a0, b0, sL[j], sA[j], sB[j], r - r_, c - c_);
-                if (d < closest) { closest = d; best = r_ * a.cw + c_; }
+                if (d < closest) {
+                    closest = d; best = r_ * a.cw + c_;
+                    closest_ceil = d < 1073741824.0 ? (int)ceil(d) : 0x7fffffff;
+                }
             }
         }
     }
