@@ -63,7 +63,7 @@ private:
             if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e);
             if (ranks < 1) ranks = 1;
             const int cores = (int)hw / ranks;
-            n = cores * 3 / 4;
+            n = cores <= 6 ? cores : cores * 3 / 4;      // the calling thread works too: a rank with four cores uses all four
             if (n > 12) n = 12;
             if (cores < 4) spin_us_ = 50;     // no spare core to spin on
         }
