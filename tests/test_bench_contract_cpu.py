@@ -69,3 +69,20 @@ def test_cpu_sequence_port_runs_like_main_py(tmp_path):
     assert 0.3 < iou <= 1.0 and secs > 0
     t_imp, t_train, n = l2.split(";")
     assert float(t_imp) > 0 and float(t_train) > 0 and int(n) == 2
+
+
+def test_committed_traffic_capture_is_well_formed():
+    """bench.py copies profiles/r02_traffic.json (tools/ncu_traffic.py over an ncu capture of the same command) into
+    roofline.traffic / traffic_by_kernel: all five kernels of the chain, per-launch DRAM and L2 bytes, the cold-cache
+    figure of the --set full capture for K1."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tr = json.load(open(os.path.join(root, "profiles", "r02_traffic.json")))
+    assert set(tr["kernels"]) == {"planes", "score", "segment_decide", "mask_dilate", "iou"}
+    for k, v in tr["kernels"].items():
+        assert v["launches"] >= 10 and v["dram_bytes"] >= 0 and v["lts_bytes"] > 0 and v["duration_us"] > 0, k
+    npx = 1920 * 1080
+    assert tr["kernels"]["score"]["algorithmic_bytes"] == 11 * npx
+    assert tr["kernels"]["score"]["dram_bytes_cold_cache"] > 7 * npx          # planes + labels from a flushed L2
+    assert tr["frame"]["compulsory_bytes"] == 10 * npx
