@@ -198,12 +198,6 @@ int pcm_quickshift_device(pcm_handle* h, const uint8_t* d_frame, int frame_h, in
                           const int rect[4], double ratio, double kernel_size, double max_dist,
                           const double* d_noise, int32_t* d_labels_out, int* n_labels_out);
 
-/* The same without waiting: the segment count goes to d_n_labels_out (one int32 on the device), nothing is synchronised.
- * For callers that over-segment a whole clip and read all counts once at the end. */
-int pcm_quickshift_device_async(pcm_handle* h, const uint8_t* d_frame, int frame_h, int frame_w, int64_t frame_stride,
-                                const int rect[4], double ratio, double kernel_size, double max_dist,
-                                const double* d_noise, int32_t* d_labels_out, int32_t* d_n_labels_out);
-
 /* skimage.segmentation.felzenszwalb(crop, scale, sigma, min_size) of scikit-image 0.17.2 (:72-73) on
  * the crop `rect` of a HOST frame.  HOST code (no handle, no device): the edge-ordered merge is
  * inherently sequential, and it is not part of the per-frame hot path.  Edges of equal cost are

@@ -1624,21 +1624,6 @@ extern "C" int pcm_quickshift_device(pcm_handle* h, const uint8_t* d_frame, int 
     return read_qs_count(h, n_labels_out);
 }
 
-extern "C" int pcm_quickshift_device_async(pcm_handle* h, const uint8_t* d_frame, int H, int W, int64_t stride, const int rect[4],
-                                           double ratio, double kernel_size, double max_dist, const double* d_noise,
-                                           int32_t* d_labels_out, int32_t* d_n_labels_out) {
-    if (!h || !d_frame || !rect || !d_labels_out || !d_n_labels_out) return fail(PCM_E_INVALID, "pcm_quickshift_device_async: NULL argument");
-    if (rect[2] <= 0 || rect[3] <= 0 || rect[0] < 0 || rect[1] < 0 || rect[0] + rect[2] > W || rect[1] + rect[3] > H)
-        return fail(PCM_E_INVALID, "pcm_quickshift_device_async: rect outside the frame");
-    CUDA_TRY(cudaSetDevice(h->device));
-    h->qs_valid = false;
-    int rc = enqueue_quickshift(h, d_frame, stride, rect[0], rect[1], rect[2], rect[3], ratio, kernel_size, max_dist, d_noise,
-                                d_labels_out);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(d_n_labels_out, h->qs_count.p, sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
-    return PCM_OK;
-}
-
 extern "C" int pcm_quickshift(pcm_handle* h, const uint8_t* frame, int H, int W, int64_t stride, const int rect[4],
                               double ratio, double kernel_size, double max_dist, const double* noise,
                               int32_t* labels_out, int* n_labels_out) {

@@ -185,15 +185,10 @@ class ClipContext:
                     d_noise = torch.from_numpy(noise).to(self.dev)
                     torch.cuda.synchronize(self.dev)
                     fb = self.H * self.W * 3
-                    # every crop is enqueued without waiting; the segment counts come back in one copy at the end
-                    d_n = torch.zeros(len(flat), dtype=torch.int32, device=self.dev)
-                    torch.cuda.synchronize(self.dev)
                     for k, r in enumerate(flat):
-                        self.handle.quickshift_device_async(self.d_frames.data_ptr() + (k // T) * fb, self.H, self.W, self.W * 3, r,
-                                                            0.5, 3, 6, d_noise.data_ptr(), d.data_ptr() + 4 * int(offsets[k]),
-                                                            d_n.data_ptr() + 4 * k)
-                    self.handle.synchronize()
-                    n_labels.extend(int(v) for v in d_n.cpu().numpy())
+                        n_labels.append(self.handle.quickshift_device(self.d_frames.data_ptr() + (k // T) * fb, self.H, self.W,
+                                                                      self.W * 3, r, 0.5, 3, 6, d_noise.data_ptr(),
+                                                                      d.data_ptr() + 4 * int(offsets[k])))
                 host = None
             elif kind == "felzenszwalb":
                 self._check_collective("felzenszwalb label maps")
