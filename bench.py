@@ -34,6 +34,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "non-rigid-object-tracking_b200")
 sys.path.insert(0, PKG)
+import pcm  # noqa: E402,F401  (sets CUDA_DEVICE_MAX_CONNECTIONS before anything initialises CUDA)
 
 import numpy as np  # noqa: E402
 
