@@ -271,6 +271,35 @@ class PixelClassificationNonRigidMasker(Masker):
                                     prior_weight=params["prior_weight"])
         return p, blend
 
+    def _frame_schedule(self, n):
+        """The pcm_update_params columns of the next `n` frames -- (model_cur, model_next, w_cur, w_next,
+        outlier_threshold), one numpy array each -- and the state after them: what n rounds of
+        _frame_params() / _advance(quiet=True) produce, computed per model span instead of per frame
+        (reference :81-87, :114-118)."""
+        cur_a, next_a = np.empty(n, np.int32), np.empty(n, np.int32)
+        w_cur, w_next, thr = np.empty(n, np.float64), np.empty(n, np.float64), np.empty(n, np.float64)
+        done = 0
+        while done < n:
+            cur = self.current_model
+            blend = bool(self.multi_selection) and len(self.models) > cur + 1
+            if blend:
+                first, last = self.models[cur]["n_frame"], self.models[cur + 1]["n_frame"]
+                k = min(n - done, max(1, last - self.index))    # the frame that reaches `last` switches models
+                tmp = np.arange(self.index, self.index + k, dtype=np.int64) - first
+                frac = tmp / np.float64(last - first)
+                w_cur[done:done + k], w_next[done:done + k] = 1 - frac, frac
+            else:
+                k = n - done
+                w_cur[done:done + k], w_next[done:done + k] = 1.0, 0.0
+            cur_a[done:done + k], next_a[done:done + k] = cur, cur + 1 if blend else -1
+            thr[done:done + k] = self.novelty_det[cur]["threshold"]
+            self.index += k
+            done += k
+            if blend and self.index >= last:
+                self.current_model += 1
+        self.prevFrame = self.prevForegroundMask = None
+        return cur_a, next_a, w_cur, w_next, thr
+
     def _advance(self, blend, crop, mask_crop, quiet=False):
         cur = self.current_model
         self.index += 1

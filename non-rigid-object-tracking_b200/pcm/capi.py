@@ -423,7 +423,8 @@ class Handle:
                                               int(crop_w), int(crop_h), int(n_labels), v(d_priors)))
 
     def run_frames(self, frame_h, frame_w, frame_stride, d_mask, mask_stride, jobs, n_jobs):
-        """Enqueue `n_jobs` FrameJob records (a ctypes array) back to back; asynchronous (pcm_run_frames)."""
+        """Enqueue `n_jobs` FrameJob records (a ctypes array, or the address of records laid out like one) back to back;
+        asynchronous (pcm_run_frames)."""
         self._check(self.lib.pcm_run_frames(self._h, int(frame_h), int(frame_w), int(frame_stride), C.c_void_p(d_mask),
                                             int(mask_stride), jobs, int(n_jobs)))
 

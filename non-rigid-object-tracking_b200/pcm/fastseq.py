@@ -377,6 +377,49 @@ def _frame_loop(clip, maskers, rects, arena, sift, d_mask, d_counts, d_pri, gpu_
                                     d_counts.data_ptr() + 16 * k)
 
 
+JOB_DTYPE = np.dtype(capi.FrameJob)
+
+
+def build_jobs(m, n, rects, frames_ptr, frame_bytes, arena, sift, priors_ptr, truth_ptr, n_truth, H, W, counts_ptr):
+    """The `pcm_frame_job` records of the next `n` frames of the single-target masker `m` (whose state machine is
+    advanced past them), as a numpy record array laid out like the C struct: frame k of the clip at `frames_ptr`,
+    crop `rects[k]`, label map k of `arena`; with `sift` (a SiftStore) frames 1.. carry the prior step; the first
+    `n_truth` frames carry the IoU step (truth planes H x W at `truth_ptr`, two int64 each at `counts_ptr`).  Filled
+    column by column: a per-frame Python loop over ctypes fields held the interpreter lock for ~14 us per frame, which
+    the sweep's 16 sequence threads share."""
+    jobs = np.zeros(n, JOB_DTYPE)
+    index = np.arange(n, dtype=np.uint64)
+    rect = np.asarray(rects, np.int32).reshape(n, 4)
+    jobs["d_frame"] = np.uint64(frames_ptr) + index * np.uint64(frame_bytes)
+    jobs["rect"] = rect
+    jobs["d_labels"] = np.uint64(arena.d_labels.data_ptr()) + np.uint64(4) * np.asarray(arena.offsets[:n], np.uint64)
+    jobs["n_labels"] = np.asarray(arena.n_labels[:n], np.int32)
+    jobs["clear_mask"][1:] = 2
+    params = m.config["params"]
+    p = jobs["params"]
+    p["model_cur"], p["model_next"], p["w_cur"], p["w_next"], p["outlier_threshold"] = m._frame_schedule(n)
+    p["novelty"] = int(bool(params["novelty_detection"]))
+    p["dilation_kernel"] = int(params["dilation_kernel"])
+    p["prior_weight"] = float(params["prior_weight"])
+    if sift is not None and n > 1:
+        off = np.asarray(sift.offsets[:n + 1], np.int64)
+        pts, des = np.uint64(sift.d_pts.data_ptr()), np.uint64(sift.d_des.data_ptr())
+        start = off[:-1].astype(np.uint64)
+        count = (off[1:] - off[:-1]).astype(np.int32)
+        jobs["d_pts_prev"][1:], jobs["d_des_prev"][1:] = pts + np.uint64(8) * start[:-1], des + np.uint64(128) * start[:-1]
+        jobs["n_prev"][1:], jobs["prev_rect"][1:] = count[:-1], rect[:-1]
+        jobs["d_pts"][1:], jobs["d_des"][1:] = pts + np.uint64(8) * start[1:], des + np.uint64(128) * start[1:]
+        jobs["n_cur"][1:] = count[1:]
+        jobs["d_priors_out"][1:] = priors_ptr
+    t = min(n, n_truth)
+    if t > 0:
+        jobs["d_truth"][:t] = np.uint64(truth_ptr) + index[:t] * np.uint64(H * W)
+        jobs["truth_stride"][:t] = W
+        jobs["truth_channels"][:t] = 1
+        jobs["d_counts"][:t] = np.uint64(counts_ptr) + np.uint64(16) * index[:t]
+    return jobs
+
+
 def run_sequence_fast(config, clip, device=0, model_cache=None, cache_tag=None, tracker_provider=None, stream=None,
                       out_path=None):
     """`run_sequence` over a ClipContext.  `stream`: a torch.cuda.Stream owned by the calling thread (created when
@@ -436,32 +479,13 @@ def run_sequence_fast(config, clip, device=0, model_cache=None, cache_tag=None, 
         if T == 1 and not host_prior:
             # single target, everything device-side: the whole sequence is ONE native call (pcm_run_frames)
             m = maskers[0]
-            jobs = (capi.FrameJob * n)()
-            frames_ptr, mask_ptr = clip.d_frames.data_ptr(), d_mask.data_ptr()
-            truth_ptr = clip.d_truth.data_ptr() if clip.d_truth is not None else 0
-            counts_ptr = d_counts.data_ptr()
-            pri_ptr = d_pri[0].data_ptr() if gpu_prior else 0
-            for index in range(n):
-                j = jobs[index]
-                rect = rects[index][0]
-                j.d_frame = frames_ptr + index * fb
-                j.rect[:] = rect
-                j.d_labels = arena.ptr(index)
-                j.n_labels = arena.n_labels[index]
-                j.clear_mask = 2 if index > 0 else 0
-                p, blend = m._frame_params()
-                j.params = p
-                if gpu_prior and index > 0:
-                    j.d_pts_prev, j.d_des_prev, j.n_prev = sift.pts_ptr(index - 1), sift.des_ptr(index - 1), sift.count(index - 1)
-                    j.prev_rect[:] = rects[index - 1][0]
-                    j.d_pts, j.d_des, j.n_cur = sift.pts_ptr(index), sift.des_ptr(index), sift.count(index)
-                    j.d_priors_out = pri_ptr
-                if index < clip.n_truth:
-                    j.d_truth, j.truth_stride, j.truth_channels = truth_ptr + index * H * W, W, 1
-                    j.d_counts = counts_ptr + 16 * index
-                m._advance(blend, None, None, quiet=True)
+            jobs = build_jobs(m, n, [r[0] for r in rects[:n]], clip.d_frames.data_ptr(), fb, arena, sift if gpu_prior else None,
+                              d_pri[0].data_ptr() if gpu_prior else 0,
+                              clip.d_truth.data_ptr() if clip.d_truth is not None else 0, clip.n_truth, H, W,
+                              d_counts.data_ptr())
+            mask_ptr = d_mask.data_ptr()
             with stages.stage("enqueue"):
-                m.native.run_frames(H, W, W * 3, mask_ptr, W, jobs, n)
+                m.native.run_frames(H, W, W * 3, mask_ptr, W, jobs.ctypes.data, n)
         else:
             _frame_loop(clip, maskers, rects, arena, sift, d_mask, d_counts, d_pri if gpu_prior else None, gpu_prior,
                         host_prior, model_cache, cache_tag)

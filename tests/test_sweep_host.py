@@ -229,3 +229,72 @@ def test_clip_share_splits_and_combines_world_size_2_gloo():
     for _, _, flat, desc in got:
         assert np.array_equal(flat, want)
         assert np.array_equal(desc[:, 0], np.arange(11)) and np.array_equal(desc[:, 1], 255 - np.arange(11))
+
+
+class _FakeTensor:
+    def __init__(self, address):
+        self.address = address
+
+    def data_ptr(self):
+        return self.address
+
+
+def _bare_masker(frame_numbers, multi_selection, index=0, current_model=0, novelty=True, prior_weight=0.1):
+    from maskers.pixel_classification import PixelClassificationNonRigidMasker
+    m = object.__new__(PixelClassificationNonRigidMasker)
+    m.config = dict(params=dict(novelty_detection=novelty, dilation_kernel=7, prior_weight=prior_weight))
+    m.multi_selection, m.index, m.current_model = multi_selection, index, current_model
+    m.models = [dict(n_frame=f) for f in frame_numbers]
+    m.novelty_det = [dict(n_frame=f, threshold=0.25 + 0.125 * k) for k, f in enumerate(frame_numbers)]
+    m.prevFrame = m.prevForegroundMask = None
+    return m
+
+
+@pytest.mark.parametrize("frame_numbers,multi,n,index,with_prior,n_truth", [
+    ([0, 93, 186], True, 279, 0, True, 279),          # frog: two blended spans, the third model alone
+    ([0, 93, 186], True, 40, 90, False, 12),          # starts inside a span, crosses one switch
+    ([0, 10], False, 32, 0, True, 0),                 # multi_selection off: the first model throughout
+    ([0], True, 1, 0, True, 5),                       # a single frame
+    ([0, 5, 7], True, 20, 6, False, 20),              # already past the next selection: switches after one frame
+])
+def test_build_jobs_equals_the_per_frame_fill(frame_numbers, multi, n, index, with_prior, n_truth):
+    """fastseq.build_jobs (column-wise numpy fill of the pcm_frame_job records) against the per-frame ctypes fill
+    driven by the masker's own _frame_params() / _advance() state machine: same bytes, same final state."""
+    from pcm import capi, fastseq
+    rng = np.random.RandomState(3)
+    H, W, fb = 240, 320, 240 * 320 * 3
+    rects = [tuple(int(v) for v in rng.randint(0, 100, 4)) for _ in range(n)]
+    sizes = rng.randint(50, 500, n)
+    arena = fastseq.LabelArena(_FakeTensor(0x7f0000001000), np.concatenate([[0], np.cumsum(sizes)]).tolist(),
+                               [int(v) for v in rng.randint(2, 90, n)])
+    counts = rng.randint(0, 40, n)
+    sift = fastseq.SiftStore(None, None, _FakeTensor(0x7f1000000000), _FakeTensor(0x7f2000000000),
+                             np.concatenate([[0], np.cumsum(counts)]).tolist()) if with_prior else None
+    frames_ptr, pri_ptr, truth_ptr, counts_ptr = 0x7f3000000000, 0x7f4000000100 if with_prior else 0, 0x7f5000000000, 0x7f6000000000
+
+    a = _bare_masker(frame_numbers, multi, index=index)
+    jobs = (capi.FrameJob * n)()
+    for k in range(n):
+        j = jobs[k]
+        j.d_frame = frames_ptr + k * fb
+        j.rect[:] = rects[k]
+        j.d_labels = arena.ptr(k)
+        j.n_labels = arena.n_labels[k]
+        j.clear_mask = 2 if k > 0 else 0
+        p, blend = a._frame_params()
+        j.params = p
+        if with_prior and k > 0:
+            j.d_pts_prev, j.d_des_prev, j.n_prev = sift.pts_ptr(k - 1), sift.des_ptr(k - 1), sift.count(k - 1)
+            j.prev_rect[:] = rects[k - 1]
+            j.d_pts, j.d_des, j.n_cur = sift.pts_ptr(k), sift.des_ptr(k), sift.count(k)
+            j.d_priors_out = pri_ptr
+        if k < n_truth:
+            j.d_truth, j.truth_stride, j.truth_channels = truth_ptr + k * H * W, W, 1
+            j.d_counts = counts_ptr + 16 * k
+        a._advance(blend, None, None, quiet=True)
+
+    b = _bare_masker(frame_numbers, multi, index=index)
+    fast = fastseq.build_jobs(b, n, rects, frames_ptr, fb, arena, sift, pri_ptr, truth_ptr, n_truth, H, W, counts_ptr)
+    assert fast.dtype.itemsize == capi.C.sizeof(capi.FrameJob) and fast.flags.c_contiguous
+    assert fast.tobytes() == bytes(jobs)
+    assert (b.index, b.current_model) == (a.index, a.current_model)
