@@ -69,19 +69,41 @@ static inline int join(std::vector<int>& parent, int rn, int rm) {
 
 struct Edge { double cost; int a, b; };
 
-// stable LSD radix sort by cost: non-negative doubles order like their bit patterns
+// Stable sort by cost (non-negative doubles order like their bit patterns; equal costs keep their edge order).
+// The 64-bit keys are not sorted whole: an LSD radix sort orders the edges by the UPPER key half (four 8-bit digits, one
+// histogram pass for all of them, digits that are the same everywhere skipped), and the runs that still tie there --
+// short ones: the upper half holds the exponent and 20 mantissa bits -- are ordered by the lower half, stably.
 static void sort_edges(std::vector<Edge>& e) {
-    std::vector<Edge> tmp(e.size());
+    const size_t n = e.size();
+    if (n < 2) return;
     auto key = [](const Edge& x) { uint64_t u; memcpy(&u, &x.cost, 8); return u; };
-    for (int shift = 0; shift < 64; shift += 11) {
-        size_t count[2049] = {0};
-        for (const Edge& x : e) count[((key(x) >> shift) & 2047) + 1]++;
+    std::vector<Edge> tmp(n);
+    size_t count[4][257] = {};
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t k = key(e[i]);
+        count[0][((k >> 32) & 255) + 1]++;
+        count[1][((k >> 40) & 255) + 1]++;
+        count[2][((k >> 48) & 255) + 1]++;
+        count[3][((k >> 56) & 255) + 1]++;
+    }
+    for (int p = 0; p < 4; ++p) {
+        size_t* c = count[p];
         bool single = false;
-        for (int i = 1; i <= 2048; ++i) if (count[i] == e.size()) single = true;
+        for (int i = 1; i <= 256; ++i) if (c[i] == n) single = true;
         if (single) continue;                                   // every key has the same digit here
-        for (int i = 1; i <= 2048; ++i) count[i] += count[i - 1];
-        for (const Edge& x : e) tmp[count[(key(x) >> shift) & 2047]++] = x;
+        for (int i = 1; i <= 256; ++i) c[i] += c[i - 1];
+        const int shift = 32 + 8 * p;
+        for (size_t i = 0; i < n; ++i) tmp[c[(key(e[i]) >> shift) & 255]++] = e[i];
         e.swap(tmp);
+    }
+    for (size_t i = 0; i < n;) {
+        const uint64_t hi = key(e[i]) >> 32;
+        size_t j = i + 1;
+        bool differ = false;
+        for (; j < n && (key(e[j]) >> 32) == hi; ++j) differ |= key(e[j]) != key(e[i]);
+        if (differ)
+            std::stable_sort(e.begin() + i, e.begin() + j, [&](const Edge& x, const Edge& y) { return key(x) < key(y); });
+        i = j;
     }
 }
 
@@ -91,23 +113,31 @@ static int merge_sorted_edges(std::vector<Edge>& edges, size_t n, double sc, int
     sort_edges(edges);
 
     std::vector<int> parent(n), size(n, 1);
-    std::vector<double> cint(n, 0.0);
+    // limit[root] = Int(C) + scale / |C|, the merge threshold of the component: it changes only when the component does,
+    // so it is evaluated at the merge (the same two operations on the same operands) instead of at every test
+    std::vector<double> limit(n, 0.0 + sc / 1);
     std::iota(parent.begin(), parent.end(), 0);
     for (const Edge& e : edges) {
         const int s0 = find_root(parent, e.a), s1 = find_root(parent, e.b);
         if (s0 == s1) continue;
-        if (e.cost < std::min(cint[s0] + sc / size[s0], cint[s1] + sc / size[s1])) {
+        if (e.cost < std::min(limit[s0], limit[s1])) {
             const int total = size[s0] + size[s1];
             const int r = join(parent, s0, s1);
             size[r] = total;
-            cint[r] = e.cost;
+            limit[r] = e.cost + sc / total;
         }
     }
+    // min-size pass: same edge order; it ends as soon as no component below min_size is left
+    size_t small = 0;
+    for (size_t i = 0; i < n; ++i) small += parent[i] == (int)i && size[i] < min_size;
     for (const Edge& e : edges) {
+        if (small == 0) break;
         const int s0 = find_root(parent, e.a), s1 = find_root(parent, e.b);
         if (s0 == s1) continue;
         if (size[s0] < min_size || size[s1] < min_size) {
             const int total = size[s0] + size[s1];
+            small -= (size[s0] < min_size) + (size[s1] < min_size);
+            small += total < min_size;
             size[join(parent, s0, s1)] = total;
         }
     }
@@ -145,18 +175,30 @@ int felzenszwalb(const uint8_t* frame, int64_t stride, int cx, int cy, int w, in
     }
     const double sc = scale / 255.0;
     // edges in scikit-image's order: right, down, down-right, up-right
-    std::vector<Edge> edges;
-    edges.reserve(4 * n);
-    auto cost = [&](int r0, int c0, int r1, int c1) {
-        const double* p = &img[((size_t)r0 * w + c0) * 3];
-        const double* q = &img[((size_t)r1 * w + c1) * 3];
+    std::vector<Edge> edges((size_t)h * (w - 1) + (size_t)(h - 1) * w + 2 * (size_t)(h - 1) * (w - 1));
+    Edge* out = edges.data();
+    auto cost = [&](const double* p, const double* q) {
         const double d0 = p[0] - q[0], d1 = p[1] - q[1], d2 = p[2] - q[2];
         return std::sqrt((d0 * d0 + d1 * d1) + d2 * d2);
     };
-    for (int r = 0; r < h; ++r) for (int c = 1; c < w; ++c) edges.push_back({cost(r, c, r, c - 1), r * w + c, r * w + c - 1});
-    for (int r = 1; r < h; ++r) for (int c = 0; c < w; ++c) edges.push_back({cost(r, c, r - 1, c), r * w + c, (r - 1) * w + c});
-    for (int r = 1; r < h; ++r) for (int c = 1; c < w; ++c) edges.push_back({cost(r, c, r - 1, c - 1), r * w + c, (r - 1) * w + c - 1});
-    for (int r = 1; r < h; ++r) for (int c = 1; c < w; ++c) edges.push_back({cost(r, c - 1, r - 1, c), (r - 1) * w + c, r * w + c - 1});
+    const double* im = img.data();
+    const size_t rs = (size_t)w * 3;
+    for (int r = 0; r < h; ++r) {
+        const double* row = im + r * rs;
+        for (int c = 1; c < w; ++c) *out++ = {cost(row + 3 * c, row + 3 * c - 3), r * w + c, r * w + c - 1};
+    }
+    for (int r = 1; r < h; ++r) {
+        const double* row = im + r * rs;
+        for (int c = 0; c < w; ++c) *out++ = {cost(row + 3 * c, row + 3 * c - rs), r * w + c, (r - 1) * w + c};
+    }
+    for (int r = 1; r < h; ++r) {
+        const double* row = im + r * rs;
+        for (int c = 1; c < w; ++c) *out++ = {cost(row + 3 * c, row + 3 * c - rs - 3), r * w + c, (r - 1) * w + c - 1};
+    }
+    for (int r = 1; r < h; ++r) {
+        const double* row = im + r * rs;
+        for (int c = 1; c < w; ++c) *out++ = {cost(row + 3 * c - 3, row + 3 * c - rs), (r - 1) * w + c, r * w + c - 1};
+    }
     return merge_sorted_edges(edges, n, sc, min_size, labels_out);
 }
 

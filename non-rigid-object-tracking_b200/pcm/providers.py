@@ -8,6 +8,7 @@ packages that are not in this image (SURVEY.md §8c "parity unpinned"):
 
 Both sides of every parity test consume the SAME provider output.
 """
+import cv2 as cv
 import numpy as np
 
 
@@ -66,10 +67,12 @@ def truth_boxes(truth_frames, fallback):
     boxes = []
     prev = tuple(int(v) for v in fallback)
     for t in truth_frames:
-        g = t if t.ndim == 2 else t[..., 0]
-        ys, xs = np.nonzero(g > 127)
-        if len(xs):
-            prev = (int(xs.min()), int(ys.min()), int(xs.max() - xs.min() + 1), int(ys.max() - ys.min() + 1))
+        # OpenCV end to end (no index arrays, no interpreter lock held for the frame): the sweep computes the boxes of
+        # a clip on the thread every sequence of the clip waits for
+        g = t if t.ndim == 2 else cv.extractChannel(t, 0)
+        x, y, w, h = cv.boundingRect(cv.threshold(np.ascontiguousarray(g), 127, 255, cv.THRESH_BINARY)[1])
+        if w > 0 and h > 0:
+            prev = (int(x), int(y), int(w), int(h))
         boxes.append(prev)
     return boxes
 

@@ -54,3 +54,40 @@ def test_felzenszwalb_synthetic(case):
     n = _check(frame, rect, **kw)
     if case == "flat":
         assert n == 1
+
+
+@pytest.mark.parametrize("case", ["lower_half_ties", "few_distinct", "zeros_and_tiny", "wide_range"])
+def test_edge_order_is_the_stable_cost_order(case):
+    """The product sorts the upper half of the cost bits by radix and orders what ties there by the lower half; the
+    partition of an explicit edge list (pcm_felzenszwalb_graph) must be the one a stable argsort of the whole costs
+    gives -- on costs that differ ONLY in the lower half, on long runs of equal costs, on exact zeros and on costs
+    spread over many binades."""
+    from pcm import capi
+    rng = np.random.default_rng(5)
+    h, w = 30, 41
+    seg = np.arange(h * w).reshape(h, w)
+    e0 = np.concatenate([seg[:, 1:].ravel(), seg[1:].ravel(), seg[1:, 1:].ravel(), seg[:h - 1, 1:].ravel()])
+    e1 = np.concatenate([seg[:, :w - 1].ravel(), seg[:h - 1].ravel(), seg[:h - 1, :w - 1].ravel(), seg[1:, :w - 1].ravel()])
+    n = e0.size
+    if case == "lower_half_ties":              # one upper half, 32 random lower bits
+        costs = (np.float64(0.25).view(np.uint64) + rng.integers(0, 2 ** 32, n, dtype=np.uint64)).view(np.float64)
+    elif case == "few_distinct":               # runs of thousands of equal keys: edge order decides
+        costs = rng.choice(np.array([0.0, 0.125, 0.1250000001, 0.3, 1.7]), n)
+    elif case == "zeros_and_tiny":
+        costs = np.where(rng.random(n) < 0.5, 0.0, rng.random(n) * 1e-300)
+    else:
+        costs = np.exp(rng.uniform(-40, 1, n))
+    order = np.argsort(costs, kind="stable")
+    for scale, min_size in ((0.4, 1), (0.05, 12)):
+        root = fo._merge(e0[order], e1[order], costs[order], h * w, scale, min_size)
+        want = np.unique(root, return_inverse=True)[1]
+        got, count = capi.felzenszwalb_graph(h * w, e0, e1, costs, scale, min_size)
+        assert count == int(want.max()) + 1
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("rect", [(4, 3, 1, 20), (2, 5, 30, 1), (7, 7, 1, 1), (0, 0, 2, 2)])
+def test_felzenszwalb_degenerate_crops(rect):
+    """One-pixel-wide, one-pixel-high and single-pixel crops: edge classes that do not exist there are simply absent."""
+    frame = np.random.default_rng(23).integers(0, 256, (32, 40, 3), dtype=np.uint8)
+    _check(frame, rect, scale=100, sigma=0.5, min_size=3)

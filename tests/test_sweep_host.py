@@ -298,3 +298,29 @@ def test_build_jobs_equals_the_per_frame_fill(frame_numbers, multi, n, index, wi
     assert fast.dtype.itemsize == capi.C.sizeof(capi.FrameJob) and fast.flags.c_contiguous
     assert fast.tobytes() == bytes(jobs)
     assert (b.index, b.current_model) == (a.index, a.current_model)
+
+
+def test_truth_boxes_are_the_bounding_rectangles_of_the_truth_masks():
+    """providers.truth_boxes (OpenCV threshold + boundingRect) against its definition: min / max of the coordinates
+    where gray > 127, the previous box when the truth is empty; BGR and single-plane truth frames."""
+    from pcm import providers
+    rng = np.random.RandomState(11)
+    frames = []
+    for k in range(24):
+        g = np.zeros((60, 90), np.uint8)
+        if k % 5 != 3:                                       # every fifth frame: no truth at all
+            y, x = rng.randint(0, 50), rng.randint(0, 80)
+            g[y:y + rng.randint(1, 10), x:x + rng.randint(1, 10)] = rng.choice([128, 200, 255])
+            g[rng.randint(0, 60), rng.randint(0, 90)] = 127  # at the threshold: not foreground
+            g[rng.randint(0, 60), rng.randint(0, 90)] = 255  # a lone pixel stretches the box
+        frames.append(g)
+    want, prev = [], (1, 2, 3, 4)
+    for g in frames:
+        ys, xs = np.nonzero(g > 127)
+        if len(xs):
+            prev = (int(xs.min()), int(ys.min()), int(xs.max() - xs.min() + 1), int(ys.max() - ys.min() + 1))
+        want.append(prev)
+    assert providers.truth_boxes(frames, (1, 2, 3, 4)) == want
+    bgr = [np.stack([g, 255 - g, g // 2], axis=2) for g in frames]            # channel 0 decides
+    assert providers.truth_boxes(bgr, (1, 2, 3, 4)) == want
+    assert providers.truth_boxes([np.asfortranarray(g) for g in frames], (1, 2, 3, 4)) == want
