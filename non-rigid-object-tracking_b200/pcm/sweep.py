@@ -278,7 +278,8 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
             if getattr(local, "stream", None) is None:
                 import torch
                 local.stream = torch.cuda.Stream(device=clips[v].dev)
-            r = fastseq.run_sequence_fast(cfg, clips[v], device=device, model_cache=cache, cache_tag=v, stream=local.stream)
+            with stages.stage("sequence"):
+                r = fastseq.run_sequence_fast(cfg, clips[v], device=device, model_cache=cache, cache_tag=v, stream=local.stream)
         else:
             r = seq_mod.run_sequence(cfg, device=device, model_cache=cache, cache_tag=v, max_frames=max_frames)
         out[k] = (sid, r["mean_iou"], r["seconds"])
@@ -466,6 +467,7 @@ def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, ou
                                                           r["decode_seconds"], r["wall_seconds"])))
                       if log else None)
     t_local = time.time() - t0
+    stages.dump_timeline(".rank%d" % rank if world > 1 else "")
     all_rows = gather(local, world, dist, dev)
     t_all = t_local
     if world > 1:
