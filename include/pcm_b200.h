@@ -198,6 +198,16 @@ int pcm_quickshift_device(pcm_handle* h, const uint8_t* d_frame, int frame_h, in
                           const int rect[4], double ratio, double kernel_size, double max_dist,
                           const double* d_noise, int32_t* d_labels_out, int* n_labels_out);
 
+/* The label maps of n crops of a device-resident clip in one call (the sweep computes the maps of a whole clip before
+ * its sequences start, pixel_classification.py:71 once per frame): crop k = rects[4k .. 4k+3] of the frame at
+ * d_frames + frame_index[k] * frame_bytes, its map written at d_labels_out + label_offsets[k] (int32 elements), its
+ * segment count at n_labels_out[k] (host).  Exactly n calls of pcm_quickshift_device -- one wait per crop included, so
+ * that the stream never holds more than one crop's launches -- without returning to the caller in between. */
+int pcm_quickshift_device_batch(pcm_handle* h, int n, const uint8_t* d_frames, int64_t frame_bytes, const int32_t* frame_index,
+                                int frame_h, int frame_w, int64_t frame_stride, const int32_t* rects, double ratio,
+                                double kernel_size, double max_dist, const double* d_noise, int32_t* d_labels_out,
+                                const int64_t* label_offsets, int32_t* n_labels_out);
+
 /* skimage.segmentation.felzenszwalb(crop, scale, sigma, min_size) of scikit-image 0.17.2 (:72-73) on
  * the crop `rect` of a HOST frame.  HOST code (no handle, no device): the edge-ordered merge is
  * inherently sequential, and it is not part of the per-frame hot path.  Edges of equal cost are

@@ -1624,6 +1624,25 @@ extern "C" int pcm_quickshift_device(pcm_handle* h, const uint8_t* d_frame, int 
     return read_qs_count(h, n_labels_out);
 }
 
+extern "C" int pcm_quickshift_device_batch(pcm_handle* h, int n, const uint8_t* d_frames, int64_t frame_bytes,
+                                           const int32_t* frame_index, int H, int W, int64_t stride, const int32_t* rects,
+                                           double ratio, double kernel_size, double max_dist, const double* d_noise,
+                                           int32_t* d_labels_out, const int64_t* label_offsets, int32_t* n_labels_out) {
+    if (!h || !d_frames || !frame_index || !rects || !d_labels_out || !label_offsets || !n_labels_out)
+        return fail(PCM_E_INVALID, "pcm_quickshift_device_batch: NULL argument");
+    if (n < 0 || frame_bytes < 0) return fail(PCM_E_INVALID, "pcm_quickshift_device_batch: bad count / frame size");
+    for (int k = 0; k < n; ++k) {
+        if (frame_index[k] < 0 || label_offsets[k] < 0) return fail(PCM_E_INVALID, "pcm_quickshift_device_batch: crop %d: negative index", k);
+        int count = 0;
+        const int rect[4] = {rects[4 * k], rects[4 * k + 1], rects[4 * k + 2], rects[4 * k + 3]};
+        const int rc = pcm_quickshift_device(h, d_frames + (int64_t)frame_index[k] * frame_bytes, H, W, stride, rect, ratio, kernel_size,
+                                             max_dist, d_noise, d_labels_out + label_offsets[k], &count);
+        if (rc) return rc;
+        n_labels_out[k] = count;
+    }
+    return PCM_OK;
+}
+
 extern "C" int pcm_quickshift(pcm_handle* h, const uint8_t* frame, int H, int W, int64_t stride, const int rect[4],
                               double ratio, double kernel_size, double max_dist, const double* noise,
                               int32_t* labels_out, int* n_labels_out) {

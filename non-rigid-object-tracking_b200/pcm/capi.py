@@ -75,6 +75,7 @@ def load_library():
         "pcm_iou_device": (I, [P, P, L, P, L, I, I, I, P]),
         "pcm_quickshift": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
         "pcm_quickshift_device": (I, [P, P, I, I, L, P, D, D, D, P, P, C.POINTER(I)]),
+        "pcm_quickshift_device_batch": (I, [P, I, P, L, P, I, I, L, P, D, D, D, P, P, P, P]),
         "pcm_felzenszwalb": (I, [P, I, I, L, P, D, D, I, P, I, P, C.POINTER(I)]),
         "pcm_felzenszwalb_graph": (I, [I, I, P, P, P, D, I, P, C.POINTER(I)]),
         "pcm_slic": (I, [P, I, I, L, P, I, D, D, P, I, I, I, P, C.POINTER(I)]),
@@ -116,7 +117,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "pcm_abi_version", "pcm_last_error", "pcm_create", "pcm_destroy", "pcm_set_stream", "pcm_use_own_stream", "pcm_get_stream", "pcm_synchronize",
     "pcm_set_features", "pcm_num_features", "pcm_add_model", "pcm_set_novelty", "pcm_num_models", "pcm_crop_rect",
-    "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device", "pcm_felzenszwalb", "pcm_felzenszwalb_graph", "pcm_slic",
+    "pcm_update", "pcm_update_device", "pcm_iou", "pcm_iou_device", "pcm_quickshift", "pcm_quickshift_device", "pcm_quickshift_device_batch", "pcm_felzenszwalb", "pcm_felzenszwalb_graph", "pcm_slic",
     "pcm_prior_device", "pcm_run_frames", "pcm_fit_forest", "pcm_fit_rows", "pcm_pca_moments", "pcm_pca_residuals", "pcm_convert", "pcm_gather_features",
     "pcm_set_debug", "pcm_debug_last", "pcm_debug_tables", "pcm_launch_count", "pcm_transfer_bytes", "pcm_set_label_cache", "pcm_profile_enable", "pcm_profile_read",
     "pcm_host_register", "pcm_host_unregister",
@@ -413,6 +414,23 @@ class Handle:
                                                    C.c_void_p(d_noise) if d_noise else None,
                                                    C.c_void_p(d_labels_out) if d_labels_out else None, C.byref(n)))
         return n.value
+
+    def quickshift_device_batch(self, d_frames, frame_bytes, frame_index, frame_h, frame_w, stride, rects, ratio, kernel_size,
+                                max_dist, d_noise, d_labels_out, label_offsets):
+        """quickshift_device for many crops of a device-resident clip in ONE native call (pcm_quickshift_device_batch):
+        crop k = rects[k] of frame frame_index[k], label map at d_labels_out + 4 * label_offsets[k].  Returns the
+        segment counts (int32 array)."""
+        fi = np.ascontiguousarray(frame_index, np.int32)
+        rc = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
+        off = np.ascontiguousarray(label_offsets, np.int64)
+        if not (len(fi) == len(rc) == len(off)):
+            raise ValueError("frame_index, rects and label_offsets must have one entry per crop")
+        counts = np.zeros(len(fi), np.int32)
+        self._check(self.lib.pcm_quickshift_device_batch(self._h, len(fi), C.c_void_p(d_frames), int(frame_bytes), _ptr(fi), int(frame_h),
+                                                         int(frame_w), int(stride), _ptr(rc), float(ratio), float(kernel_size),
+                                                         float(max_dist), C.c_void_p(d_noise) if d_noise else None,
+                                                         C.c_void_p(d_labels_out), _ptr(off), _ptr(counts)))
+        return counts
 
     def prior_device(self, d_pts_prev, d_des_prev, n_prev, d_prev_mask, prev_stride, prev_w, prev_h, d_pts, d_des, n_cur,
                      d_labels, crop_w, crop_h, n_labels, d_priors):

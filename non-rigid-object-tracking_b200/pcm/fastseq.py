@@ -120,9 +120,14 @@ class ClipContext:
     def prepare(self, config, kinds, want_sift):
         """Everything the sequences of this clip share, computed NOW by the calling thread: tracker boxes, the label
         maps of the over-segmentations in `kinds`, SIFT features.  With a `share` of several ranks this is a collective:
-        every member must call it with the same arguments, in the same order relative to its other clips."""
+        every member must call it with the same arguments, in the same order relative to its other clips.  (The
+        quickshift maps alone are no collective -- every rank computes them on its GPU -- and may be prepared from
+        another thread at the same time.)"""
         bboxes, switch = self.selections(config)
         box_key, _, rects, _ = self.schedule(config, bboxes, switch)
+        if not want_sift and list(kinds) == ["quickshift"]:
+            self.labels("quickshift", box_key, rects)
+            return
         self._collective_ok = True
         try:
             for kind in sorted(kinds):
@@ -183,14 +188,15 @@ class ClipContext:
                     # noise RandomState(42).normal(scale=1e-5, size=(h, w)) is the first h*w values of ONE stream
                     noise = np.random.RandomState(42).normal(scale=0.00001, size=max(sizes))
                     d_noise = torch.from_numpy(noise).to(self.dev)
-                    torch.cuda.synchronize(self.dev)
+                    torch.cuda.current_stream(self.dev).synchronize()
                     fb = self.H * self.W * 3
                     # (one wait per crop, on purpose: enqueueing all crops of a clip at once was measured SLOWER -- thousands of
-                    # queued launches on this stream block the launches of the fitting and sequence threads, round 2)
-                    for k, r in enumerate(flat):
-                        n_labels.append(self.handle.quickshift_device(self.d_frames.data_ptr() + (k // T) * fb, self.H, self.W,
-                                                                      self.W * 3, r, 0.5, 3, 6, d_noise.data_ptr(),
-                                                                      d.data_ptr() + 4 * int(offsets[k])))
+                    # queued launches on this stream block the launches of the fitting and sequence threads, round 2;
+                    # and in ONE native call: a Python loop of short calls re-takes the interpreter lock once per crop,
+                    # which under the fitting threads' load cost ten times the GPU work)
+                    n_labels.extend(int(v) for v in self.handle.quickshift_device_batch(
+                        self.d_frames.data_ptr(), fb, [k // T for k in range(len(flat))], self.H, self.W, self.W * 3, flat,
+                        0.5, 3, 6, d_noise.data_ptr(), d.data_ptr(), offsets[:len(flat)]))
                 host = None
             elif kind == "felzenszwalb":
                 self._check_collective("felzenszwalb label maps")
@@ -216,7 +222,7 @@ class ClipContext:
                         self.share.combine(d)               # the other members' frames arrive here
                         self.share.combine(d_counts)
                         n_labels.extend(int(v) for v in d_counts.cpu().numpy())
-                    torch.cuda.synchronize(self.dev)
+                    torch.cuda.current_stream(self.dev).synchronize()
                     host = None
             else:
                 raise ValueError("no clip-resident over-segmentation for %r" % kind)
@@ -302,7 +308,7 @@ def _clip_sift(self, box_key, rects, workers=4):
         with stages.stage("share_allreduce"):
             self.share.combine(d_pts)                   # zero everywhere but on the member that detected the entry
             self.share.combine(d_des)
-        torch.cuda.synchronize(self.dev)
+        torch.cuda.current_stream(self.dev).synchronize()
         if self.share.size > 1:
             pts, des = d_pts.cpu().numpy(), d_des.cpu().numpy()
         host_pts = [pts[offsets[k]:offsets[k + 1]] for k in range(len(flat))]

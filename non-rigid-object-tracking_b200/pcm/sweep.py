@@ -260,11 +260,14 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
                 elif step in needs[v][0]:
                     clips[v].prepare(cfg, [step], False)
 
-    def ready_after(step, k):
-        """Sequence k can start once `step` is prepared (its label maps, and the SIFT features if it uses the prior)."""
+    def needs_of(k):
+        """What sequence k waits for: the label maps of its over-segmentation, and the SIFT features if it uses the
+        (device-side) prior."""
         p = items[k][3]
-        need = "sift" if (p.get("prior_weight") and gpu_prior) else p["over_segmentation"]
-        return PREPARE_STEPS.index(need) <= PREPARE_STEPS.index(step) if need in PREPARE_STEPS else step == PREPARE_STEPS[-1]
+        need = {p["over_segmentation"]} & set(PREPARE_STEPS)
+        if p.get("prior_weight") and gpu_prior:
+            need.add("sift")
+        return need
 
     local = threading.local()
 
@@ -341,16 +344,52 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
                 cfg = sequence_config(base, polygons, v, items[0][3], videos_path, truth_path)
                 seq_mod.read_clip(seq_mod.resolve_path(cfg["input_video"]), cfg.get("resize_factor") or 1)
                 seq_mod.read_clip(seq_mod.resolve_path(cfg["input_truth"]), cfg.get("resize_factor") or 1)
-        with ThreadPoolExecutor(max_workers=seq_workers) as pool:
-            futures = [pool.submit(prefit, t) for t in prefit_tasks()] if resident else []     # GPU fits start at once ...
-            pending = list(order)
+        tasks = prefit_tasks() if resident else []
+        # The fits get threads of their own -- as many as there are fits, up to PCM_SWEEP_FIT_WORKERS: a fitting thread
+        # waits for ONE long kernel (a CTA per tree), so the GPU takes them all at once, and the sequence threads are
+        # free for the sequences whose models and label maps are there.  (Round 2 timeline, 1 GPU: 52 fits through the
+        # 16 sequence threads occupied all of them for the first 1.7 s of a 3.2 s sweep.)
+        fit_workers = max(1, min(len(tasks), int(os.environ.get("PCM_SWEEP_FIT_WORKERS", "48")))) if tasks else 1
+        side_quickshift = resident and os.environ.get("PCM_SWEEP_SIDE_QUICKSHIFT", "1") != "0"
+        with ThreadPoolExecutor(max_workers=seq_workers) as pool, ThreadPoolExecutor(max_workers=fit_workers) as fit_pool:
+            futures = [fit_pool.submit(prefit, t) for t in tasks]               # GPU fits start at once ...
+            pending, done_steps, guard = list(order), set(), threading.Lock()
+
+            def release(step):
+                """`step` is prepared: start the sequences that now have everything they need."""
+                with guard:
+                    done_steps.add(step)
+                    ready = [k for k in pending if needs_of(k) <= done_steps]
+                    gone = set(ready)
+                    pending[:] = [k for k in pending if k not in gone]
+                    futures.extend(pool.submit(run_one, k) for k in ready)
+
             if resident:
-                # ... while the host prepares the clips; sequences start as soon as what THEY need is there
+                # ... while the clips are prepared: the quickshift maps (GPU work, no collective) on a thread of their
+                # own, the host-side steps (felzenszwalb maps, SIFT detection; collectives between the ranks that share
+                # a clip) on this one.  Sequences start as soon as what THEY need is there.
+                side, side_error = None, []
+                if side_quickshift:
+                    def quickshift_side():
+                        try:
+                            prepare_clips("quickshift")
+                            release("quickshift")
+                        except BaseException as e:          # re-raised on the main thread
+                            side_error.append(e)
+                    side = threading.Thread(target=quickshift_side, name="pcm-quickshift-maps")
+                    side.start()
                 for step in PREPARE_STEPS:
+                    if side is not None and step == "quickshift":
+                        continue
                     prepare_clips(step)
-                    futures += [pool.submit(run_one, k) for k in pending if ready_after(step, k)]
-                    pending = [k for k in pending if not ready_after(step, k)]
-            futures += [pool.submit(run_one, k) for k in pending]
+                    release(step)
+                if side is not None:
+                    side.join()
+                    if side_error:
+                        raise side_error[0]
+            with guard:
+                futures.extend(pool.submit(run_one, k) for k in pending)
+                del pending[:]
             for f in futures:
                 f.result()
     for c in clips.values():
@@ -458,6 +497,14 @@ def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, ou
         if dev is not None:
             torch.cuda.synchronize(dev)
         dist.barrier()
+    blas_limit = None
+    if resident:
+        # the PCA fits call LAPACK from many threads at once: one BLAS thread each instead of a pool per call
+        try:
+            from threadpoolctl import threadpool_limits
+            blas_limit = threadpool_limits(limits=1, user_api="blas")
+        except Exception:
+            pass
     stages.reset()
     t0 = time.time()
     local = run_shard(shards[rank], base, polygons, device=local_rank, max_frames=max_frames, train_jobs=train_jobs,
@@ -467,6 +514,8 @@ def run(base, polygons, videos=None, hyper=None, limit=None, max_frames=None, ou
                                                           r["decode_seconds"], r["wall_seconds"])))
                       if log else None)
     t_local = time.time() - t0
+    if blas_limit is not None:
+        blas_limit.restore_original_limits()
     stages.dump_timeline(".rank%d" % rank if world > 1 else "")
     all_rows = gather(local, world, dist, dev)
     t_all = t_local

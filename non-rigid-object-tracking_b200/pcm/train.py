@@ -9,7 +9,7 @@ procedure restates scikit-learn 1.9's; it is used when the installed scikit-lear
 the result with scikit-learn's `tree_` arrays) and `RandomForestClassifier` itself is used otherwise.
 """
 import ctypes as C
-import functools
+import threading
 
 import numpy as np
 
@@ -23,21 +23,42 @@ def gpu_fit_supported():
     return sklearn.__version__.startswith(VALIDATED_SKLEARN)
 
 
-@functools.lru_cache(maxsize=64)
+_draws, _draw_locks, _draws_guard = {}, {}, threading.Lock()
+
+
 def tree_draws(n_samples, n_estimators, random_state=42):
-    """(counts uint8 [T, n], splitter seeds uint32 [T]) of the forest's trees (they depend on the number of rows,
-    trees and the seed only: cached)."""
-    rs = np.random.RandomState(random_state)
-    counts = np.empty((n_estimators, n_samples), np.uint8)
-    seeds = np.empty(n_estimators, np.uint32)
-    for t in range(n_estimators):
-        seed = rs.randint(MAX_INT32)
-        c = np.bincount(np.random.RandomState(seed).randint(0, n_samples, n_samples), minlength=n_samples)
-        if c.max() > 127:
-            raise ValueError("bootstrap count above 127")
-        counts[t] = c
-        seeds[t] = np.random.RandomState(seed).randint(0, RAND_R_MAX)
-    return counts, seeds
+    """(counts uint8 [T, n], splitter seeds uint32 [T]) of the forest's trees.  They depend on the number of rows, trees
+    and the seed only, and are computed ONCE per such triple, also when several threads ask at the same time (the fits
+    of one row set -- two feature sets x two depths in the sweep -- start together; a plain memo let every one of them
+    spend its 30 ms under the interpreter lock, which serialised the fitting threads of a whole sweep)."""
+    key = (int(n_samples), int(n_estimators), int(random_state))
+    with _draws_guard:
+        if key in _draws:
+            return _draws[key]
+        lock = _draw_locks.setdefault(key, threading.Lock())
+    with lock:
+        with _draws_guard:
+            if key in _draws:
+                return _draws[key]
+        rs = np.random.RandomState(random_state)
+        tree_rs = np.random.RandomState(0)          # re-seeded per tree: RandomState(seed) without the construction
+        counts = np.empty((n_estimators, n_samples), np.uint8)
+        seeds = np.empty(n_estimators, np.uint32)
+        for t in range(n_estimators):
+            seed = rs.randint(MAX_INT32)
+            tree_rs.seed(seed)
+            c = np.bincount(tree_rs.randint(0, n_samples, n_samples), minlength=n_samples)
+            if c.max() > 127:
+                raise ValueError("bootstrap count above 127")
+            counts[t] = c
+            tree_rs.seed(seed)
+            seeds[t] = tree_rs.randint(0, RAND_R_MAX)
+        with _draws_guard:
+            if len(_draws) >= 64:                   # bounded like the memo it replaces
+                _draws.pop(next(iter(_draws)))
+            _draws[key] = (counts, seeds)
+            _draw_locks.pop(key, None)
+        return counts, seeds
 
 
 class GpuForest:

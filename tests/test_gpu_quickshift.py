@@ -152,3 +152,37 @@ def test_masker_uses_native_slic():
         assert b.update(bbox=box, frame=frames[i], mask=mb, color=None) is None
         assert ma[..., 2].any() and np.array_equal(ma, mb)
     a.close(); b.close()
+
+
+def test_quickshift_device_batch_equals_single_crops():
+    """pcm_quickshift_device_batch (the label maps of many crops of a device-resident clip in one native call, what the
+    sweep uses per clip) against pcm_quickshift per crop on the host frames: same maps, same counts, crops of
+    different sizes and frames in any order; the sequence tie noise is the first h*w values of one stream."""
+    import torch
+    from pcm import capi
+    frames = read_video("Video", "frog")[:4]
+    H, W = frames[0].shape[:2]
+    rects = [(150, 60, 133, 159), (10, 5, 64, 48), (200, 100, 90, 120), (0, 0, 40, 33), (301, 77, 55, 61)]
+    index = [0, 3, 1, 2, 3]
+    sizes = [r[2] * r[3] for r in rects]
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    noise = np.random.RandomState(42).normal(scale=0.00001, size=max(sizes))
+    d_frames = torch.from_numpy(np.stack(frames)).cuda()
+    d_noise = torch.from_numpy(noise).cuda()
+    d_labels = torch.full((int(offsets[-1]),), -7, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    h = capi.Handle(0)
+    h.set_features(8, ["hsv", "lab"])
+    counts = h.quickshift_device_batch(d_frames.data_ptr(), H * W * 3, index, H, W, W * 3, rects, 0.5, 3, 6,
+                                       d_noise.data_ptr(), d_labels.data_ptr(), offsets[:-1])
+    got = d_labels.cpu().numpy()
+    for k, r in enumerate(rects):
+        want, n = h.quickshift(frames[index[k]], r, noise=noise[:sizes[k]].reshape(r[3], r[2]))
+        assert counts[k] == n
+        assert np.array_equal(got[offsets[k]:offsets[k + 1]].reshape(r[3], r[2]), want)
+    assert len(h.quickshift_device_batch(d_frames.data_ptr(), H * W * 3, [], H, W, W * 3, [], 0.5, 3, 6, d_noise.data_ptr(),
+                                         d_labels.data_ptr(), [])) == 0
+    with pytest.raises(capi.PcmError):
+        h.quickshift_device_batch(d_frames.data_ptr(), H * W * 3, [0], H, W, W * 3, [(470, 0, 40, 40)], 0.5, 3, 6, d_noise.data_ptr(),
+                                  d_labels.data_ptr(), [0])
+    h.close()
