@@ -131,8 +131,10 @@ public:
     // returns false when the cache is full and the caller has to free the block itself
     bool park(int device, void* p, size_t cap) {
         std::lock_guard<std::mutex> lk(m_);
-        const size_t limit = device < 0 ? ((size_t)1 << 30) : ((size_t)4 << 30);
-        if (total_[device < 0] + cap > limit || blocks_.size() >= 512) return false;
+        // (a sweep closes dozens of handles at once, the fitting ones with ~100 MB each; a block that does not fit here is
+        // cudaFree'd, which waits for the whole device)
+        const size_t limit = device < 0 ? ((size_t)4 << 30) : ((size_t)32 << 30);
+        if (total_[device < 0] + cap > limit || blocks_.size() >= 4096) return false;
         blocks_.push_back({device, p, cap});
         total_[device < 0] += cap;
         return true;
