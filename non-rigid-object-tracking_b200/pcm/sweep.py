@@ -345,12 +345,14 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
                 seq_mod.read_clip(seq_mod.resolve_path(cfg["input_video"]), cfg.get("resize_factor") or 1)
                 seq_mod.read_clip(seq_mod.resolve_path(cfg["input_truth"]), cfg.get("resize_factor") or 1)
         tasks = prefit_tasks() if resident else []
-        # The fits get threads of their own (as many as there are sequence threads; PCM_SWEEP_FIT_WORKERS overrides), so
-        # that the sequence threads are free for the sequences whose models and label maps are there.  Round 2
+        # The fits get threads of their own (half as many as there are sequence threads; PCM_SWEEP_FIT_WORKERS overrides),
+        # so that the sequence threads are free for the sequences whose models and label maps are there.  Round 2
         # timelines (tools/sweep_ab.sh, profiles/README.md), 1 GPU + 16 cores: through the 16 sequence threads the 52
-        # fits held all of them for the first 1.7 s of a 3.2 s sweep; 48 fitting threads are worse than 16 -- a fit is
-        # 6 ms of GPU time and otherwise host work (rows, bootstrap draws, PCA), and the threads fight over the cores.
-        fit_workers = max(1, min(len(tasks), int(os.environ.get("PCM_SWEEP_FIT_WORKERS", "0")) or seq_workers)) if tasks else 1
+        # fits held all of them for the first 1.7 s of a 3.2 s sweep.  A fit is 6 ms of GPU time and otherwise host
+        # work (training rows to the host and back, bootstrap draws, PCA): 8 fitting threads finish the 52 fits as soon
+        # as 16 or 24 do (1.0 - 1.2 s) and leave the cores to the clip preparation; 48 thrash (1.8 - 3 s).
+        fit_workers = int(os.environ.get("PCM_SWEEP_FIT_WORKERS", "0")) or max(4, seq_workers // 2)
+        fit_workers = max(1, min(len(tasks), fit_workers)) if tasks else 1
         side_quickshift = resident and os.environ.get("PCM_SWEEP_SIDE_QUICKSHIFT", "1") != "0"
         with ThreadPoolExecutor(max_workers=seq_workers) as pool, ThreadPoolExecutor(max_workers=fit_workers) as fit_pool:
             futures = [fit_pool.submit(prefit, t) for t in tasks]               # GPU fits start at once ...
