@@ -78,3 +78,54 @@ def test_product_draws_equal_the_oracles_and_scikit_learns():
     for t, est in enumerate(clf.estimators_):
         idx = _generate_sample_indices(est.random_state, n, n, None)
         assert np.array_equal(np.bincount(idx, minlength=n), counts[t])
+
+
+def test_draws_are_computed_once_when_many_threads_ask():
+    """The fits of one row set start together in the sweep: they must share ONE computation of the bootstrap draws
+    (30 ms under the interpreter lock each, otherwise) and get the very same arrays."""
+    import threading
+    from pcm import train
+    n, T = 4321, 12
+    got, errors = [], []
+
+    def ask():
+        try:
+            got.append(train.tree_draws(n, T, 1234))
+        except Exception as e:               # pragma: no cover
+            errors.append(e)
+    threads = [threading.Thread(target=ask) for _ in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors and len(got) == 8
+    assert all(g[0] is got[0][0] and g[1] is got[0][1] for g in got)
+    assert train.tree_draws(n, T, 1234)[0] is got[0][0]          # and later callers
+    counts, seeds = got[0]
+    for t, (c, s) in enumerate(ffo.tree_draws(n, T, 1234)):
+        assert np.array_equal(counts[t], c) and int(seeds[t]) == s
+
+
+def test_stage_timeline_records_intervals(tmp_path, monkeypatch):
+    """pcm.stages with PCM_STAGE_TIMELINE: every stage interval is kept and dumped as JSON (tools/sweep_timeline.py)."""
+    import importlib
+    import json
+    import time
+    path = tmp_path / "timeline.json"
+    monkeypatch.setenv("PCM_STAGE_TIMELINE", str(path))
+    from pcm import stages
+    stages = importlib.reload(stages)
+    try:
+        stages.reset()
+        with stages.stage("outer"):
+            with stages.stage("inner"):
+                time.sleep(0.01)
+        assert stages.dump_timeline(".x") == str(path) + ".x"
+        events = json.load(open(str(path) + ".x"))
+        assert [e["stage"] for e in events] == ["inner", "outer"]
+        inner, outer = events
+        assert outer["start"] <= inner["start"] <= inner["end"] <= outer["end"] and inner["end"] - inner["start"] >= 0.009
+        assert stages.snapshot()["outer"] >= stages.snapshot()["inner"] > 0
+    finally:
+        monkeypatch.delenv("PCM_STAGE_TIMELINE")
+        importlib.reload(stages)
