@@ -213,8 +213,10 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
     boxes, over-segmentation maps and SIFT features are shared by all hyper-parameter sets, forests and PCAs are
     fitted on the GPU and shared through a rank-wide `ModelCache`, and a sequence is one asynchronous pass over the
     device-resident frames.  `seq_workers` threads run sequences concurrently, each on its own CUDA stream: the host
-    stages of one sequence (SIFT priors, Python) overlap the kernels of the others.  Every masker owns its own native
-    context; results do not depend on the schedule.
+    stages of one sequence (SIFT priors, Python) overlap the kernels of the others; the fits run on threads of their
+    own and the clips are prepared beside them (quickshift maps on a side thread, the host-side steps -- collectives
+    when ranks share a clip -- on the calling thread), so a sequence starts as soon as what IT needs exists.  Every
+    masker owns its own native context; results do not depend on the schedule.
     resident=False: the per-frame host-buffer path of `pcm.sequence.run_sequence` (what `main.py` runs)."""
     out = np.zeros((len(items), 3), np.float64)
     done = [0]
@@ -249,7 +251,8 @@ def run_shard(items, base, polygons, device=0, videos_path="Input/SegTrack2/Vide
         # sweep SLOWER -- 55-64 instead of 79 sequences/s: every clip's frames are already spread over all host cores)
         """One kind of what all sequences of a clip share -- the label maps of an over-segmentation, or the SIFT features
         -- for every clip of the shard, in the same (step, clip) order on every rank: the ranks that share a clip split
-        the per-frame host work and all-reduce the pieces (main thread only)."""
+        the per-frame host work and all-reduce the pieces (felzenszwalb, sift: calling thread of run_shard only; the
+        quickshift step involves no collective and may run on another thread)."""
         needs = clip_needs(all_items or items)
         for v in order_v:
             cfg = sequence_config(base, polygons, v, items[0][3], videos_path, truth_path)
