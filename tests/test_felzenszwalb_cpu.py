@@ -91,3 +91,20 @@ def test_felzenszwalb_degenerate_crops(rect):
     """One-pixel-wide, one-pixel-high and single-pixel crops: edge classes that do not exist there are simply absent."""
     frame = np.random.default_rng(23).integers(0, 256, (32, 40, 3), dtype=np.uint8)
     _check(frame, rect, scale=100, sigma=0.5, min_size=3)
+
+
+def test_felzenszwalb_from_many_threads():
+    """The sweep computes the label maps of a clip's frames on a pool of threads; the library keeps its working memory
+    per thread: crops of different sizes, interleaved on 8 threads, give the single-threaded maps."""
+    from concurrent.futures import ThreadPoolExecutor
+    from pcm import capi
+    rng = np.random.default_rng(31)
+    frame = rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    frame[30:90, 40:120] //= 4                                  # some structure besides the noise
+    rects = [(int(x), int(y), int(w), int(h)) for x, y, w, h in
+             zip(rng.integers(0, 60, 24), rng.integers(0, 40, 24), rng.integers(5, 100, 24), rng.integers(5, 80, 24))]
+    want = [capi.felzenszwalb(frame, r, scale=100, sigma=0.5, min_size=20) for r in rects]
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        got = list(pool.map(lambda r: capi.felzenszwalb(frame, r, scale=100, sigma=0.5, min_size=20), rects * 3))
+    for k, (seg, n) in enumerate(got):
+        assert n == want[k % len(rects)][1] and np.array_equal(seg, want[k % len(rects)][0])
