@@ -54,6 +54,22 @@ def test_no_cpu_fallback_without_a_device():
             features="8 hsv_lab", over_segmentation="quickshift")), poly_roi=None, update_mask=False)
 
 
+def test_entry_points_reject_null_arguments_before_touching_a_device():
+    """Argument validation of the device-pointer entry points needs no GPU: a NULL handle / pointer is PCM_E_INVALID
+    with a message, not a crash (the reference's ctypes binding of prim/ passes raw pointers the same way)."""
+    from pcm import capi
+    lib = capi.load_library()
+    n = C.c_int(0)
+    rect = (C.c_int * 4)(0, 0, 4, 4)
+    assert lib.pcm_quickshift_device(None, None, 8, 8, 24, rect, 0.5, 3.0, 6.0, None, None, C.byref(n)) != 0
+    assert b"pcm_quickshift_device" in lib.pcm_last_error()
+    assert lib.pcm_quickshift_device_batch(None, 1, None, 192, None, 8, 8, 24, None, 0.5, 3.0, 6.0, None, None, None, None) != 0
+    assert b"pcm_quickshift_device_batch" in lib.pcm_last_error()
+    assert lib.pcm_run_frames(None, 8, 8, 24, None, 8, None, 0) != 0
+    assert lib.pcm_update_device(None, None, 8, 8, 24, None, None, 0, None, None, None, 8) != 0
+    assert lib.pcm_iou_device(None, None, 8, None, 8, 1, 8, 8, None) != 0
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "non-rigid-object-tracking_b200")
     bad = []
